@@ -1,0 +1,209 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes bindings for oracle/libggdmc_oracle.so (the C restatement)
+and oracle/_ref/libggdmc_ref.so (the reference's own object code, when it was built)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_up = C.POINTER(C.c_uint)
+c_u8p = C.POINTER(C.c_ubyte)
+c_u16p = C.POINTER(C.c_ushort)
+
+
+class Addr(C.Structure):
+    _fields_ = [("pop", C.c_uint), ("iter", C.c_uint), ("sweep", C.c_uint), ("chain", C.c_uint),
+                ("purpose", C.c_uint), ("slot", C.c_uint)]
+
+
+class Rng(C.Structure):
+    _fields_ = [("mode", C.c_int), ("u", c_dp), ("n", C.c_long), ("pos", C.c_long), ("seed", C.c_ulonglong),
+                ("burn_static_ctor", C.c_int), ("first_like_done", C.c_int)]
+
+
+class Model(C.Structure):
+    _fields_ = [("n_acc", C.c_int), ("n_cell", C.c_int), ("npar", C.c_int), ("param_src", c_ip),
+                ("const_val", c_dp), ("posdrift", c_u8p)]
+
+
+class Data(C.Structure):
+    _fields_ = [("n_trial", C.c_int), ("rt", c_dp), ("cell", c_u16p)]
+
+
+class Prior(C.Structure):
+    _fields_ = [("npar", C.c_int), ("p0", c_dp), ("p1", c_dp), ("lower", c_dp), ("upper", c_dp), ("dist", c_ip),
+                ("log_p", c_u8p)]
+
+
+class DE(C.Structure):
+    _fields_ = [("pop_migration_prob", C.c_double), ("sub_migration_prob", C.c_double), ("gamma_precursor", C.c_double),
+                ("rp", C.c_double), ("is_hblocked", C.c_int), ("is_pblocked", C.c_int), ("nparameter", C.c_int),
+                ("nchain", C.c_int), ("jacobi", C.c_int)]
+
+
+class Pop(C.Structure):
+    _fields_ = [("npar", C.c_int), ("nchain", C.c_int), ("nmc", C.c_int), ("thin", C.c_int), ("theta", c_dp),
+                ("lp", c_dp), ("ll", c_dp), ("out_theta", c_dp), ("out_lp", c_dp), ("out_ll", c_dp), ("store_i", C.c_int)]
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle (and oracle/_ref when /root/reference is mounted)."""
+    so = os.path.join(HERE, "libggdmc_oracle.so")
+    srcs = [os.path.join(HERE, f) for f in ("ggdmc_oracle.c", "rmath_port.c", "ggdmc_oracle.h", "rmath_port.h")]
+    stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if stale:
+        subprocess.run(["make", "-C", HERE, "libggdmc_oracle.so"], check=True, capture_output=True)
+    ref = os.path.join(HERE, "_ref", "libggdmc_ref.so")
+    if os.path.exists("/root/reference/src/de.o") and (force or not os.path.exists(ref)):
+        subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(os.path.join(HERE, "libggdmc_oracle.so"))
+        L.orc_uniform.restype = C.c_double
+        L.orc_sumloglike.restype = C.c_double
+        L.orc_sumloglike_rinit.restype = C.c_double
+        L.orc_tnorm_d.restype = C.c_double
+        L.orc_tnorm_d.argtypes = [C.c_double] * 5 + [C.c_int]
+        L.orc_sumlogprior.restype = C.c_double
+        L.orc_sumloghlike.restype = C.c_double
+        L.orc_time_sumloglike.restype = C.c_double
+        L.orc_get_subchains.restype = C.c_int
+        L.orc_pnorm5.restype = C.c_double
+        L.orc_pnorm5.argtypes = [C.c_double] * 3 + [C.c_int] * 2
+        L.orc_dnorm4.restype = C.c_double
+        L.orc_dnorm4.argtypes = [C.c_double] * 3 + [C.c_int]
+        _lib = L
+    return _lib
+
+
+_ref = None
+
+
+def ref_lib() -> Optional[C.CDLL]:
+    """The reference's own object code (src/de.o) behind C wrappers, or None if never built."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(HERE, "_ref", "libggdmc_ref.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.ref_get_subchains.restype = C.c_uint
+        L.ref_tnorm_d.restype = C.c_double
+        L.ref_tnorm_d.argtypes = [C.c_double] * 5 + [C.c_int]
+        L.ref_uniform_stream_pos.restype = C.c_long
+        _ref = L
+    return _ref
+
+
+def f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ptr(a: np.ndarray, t=c_dp):
+    return a.ctypes.data_as(t)
+
+
+class OModel:
+    """Keeps the numpy buffers alive next to the C struct."""
+
+    def __init__(self, param_src, const_val, posdrift, npar):
+        self.param_src = np.ascontiguousarray(param_src, dtype=np.int32)
+        self.const_val = f64(const_val if len(const_val) else [0.0])
+        self.posdrift = np.ascontiguousarray(posdrift, dtype=np.uint8)
+        n_cell, six, n_acc = self.param_src.shape
+        assert six == 6
+        self.c = Model(n_acc, n_cell, int(npar), ptr(self.param_src, c_ip), ptr(self.const_val), ptr(self.posdrift, c_u8p))
+        self.n_acc, self.n_cell, self.npar = n_acc, n_cell, int(npar)
+
+
+class OData:
+    def __init__(self, rt, cell):
+        order = np.argsort(np.asarray(cell), kind="stable")
+        self.order = order
+        self.rt = f64(np.asarray(rt)[order])
+        self.cell = np.ascontiguousarray(np.asarray(cell)[order], dtype=np.uint16)
+        self.c = Data(len(self.rt), ptr(self.rt), ptr(self.cell, c_u16p))
+
+
+class OPrior:
+    def __init__(self, p0, p1, lower, upper, dist, log_p):
+        self.p0, self.p1, self.lower, self.upper = f64(p0), f64(p1), f64(lower), f64(upper)
+        self.dist = np.ascontiguousarray(dist, dtype=np.int32)
+        self.log_p = np.ascontiguousarray(log_p, dtype=np.uint8)
+        self.c = Prior(len(self.p0), ptr(self.p0), ptr(self.p1), ptr(self.lower), ptr(self.upper), ptr(self.dist, c_ip),
+                       ptr(self.log_p, c_u8p))
+
+
+class OPop:
+    """A chain population with sample storage, laid out like the reference's arma objects."""
+
+    def __init__(self, theta0, lp0, ll0, nmc, thin):
+        theta0 = f64(theta0)  # [nchain, npar]
+        self.nchain, self.npar = theta0.shape
+        self.theta = theta0.copy()
+        self.lp, self.ll = f64(lp0).copy(), f64(ll0).copy()
+        self.out_theta = np.full((nmc, self.nchain, self.npar), np.nan)
+        self.out_lp = np.full((nmc, self.nchain), -np.inf)
+        self.out_ll = np.full((nmc, self.nchain), -np.inf)
+        self.out_theta[0], self.out_lp[0], self.out_ll[0] = self.theta, self.lp, self.ll
+        self.c = Pop(self.npar, self.nchain, nmc, thin, ptr(self.theta), ptr(self.lp), ptr(self.ll), ptr(self.out_theta),
+                     ptr(self.out_lp), ptr(self.out_ll), 0)
+
+
+def make_rng(seed: Optional[int] = None, stream: Optional[np.ndarray] = None, burn: bool = False):
+    r = Rng()
+    if stream is not None:
+        s = f64(stream)
+        r.mode, r.u, r.n, r.pos = 0, ptr(s), len(s), 0
+        r._keep = s
+    else:
+        r.mode, r.seed = 1, int(seed)
+    r.burn_static_ctor = 1 if burn else 0
+    r.first_like_done = 0
+    return r
+
+
+def make_de(nparameter, nchain, pop_migration_prob=0.0, sub_migration_prob=0.0, gamma_precursor=2.38, rp=0.001,
+            is_hblocked=False, is_pblocked=False, jacobi=False) -> DE:
+    return DE(pop_migration_prob, sub_migration_prob, gamma_precursor, rp, int(is_hblocked), int(is_pblocked),
+              int(nparameter), int(nchain), int(jacobi))
+
+
+def trial_logdens(m: OModel, d: OData, theta) -> np.ndarray:
+    """Per-trial log densities, returned in the CALLER's original trial order."""
+    th = f64(theta)
+    out = np.zeros(len(d.rt))
+    lib().orc_trial_logdens(C.byref(m.c), C.byref(d.c), ptr(th), ptr(out))
+    back = np.empty_like(out)
+    back[d.order] = out
+    return back
+
+
+def sumloglike(m: OModel, d: OData, theta) -> float:
+    th = f64(theta)
+    return lib().orc_sumloglike(C.byref(m.c), C.byref(d.c), ptr(th), None, None)
+
+
+def sumloglike_rinit(m: OModel, d: OData, theta) -> float:
+    th = f64(theta)
+    return lib().orc_sumloglike_rinit(C.byref(m.c), C.byref(d.c), ptr(th))
+
+
+def sumlogprior(p: OPrior, x, p0=None, p1=None) -> float:
+    xx = f64(x)
+    a = f64(p0) if p0 is not None else None
+    b = f64(p1) if p1 is not None else None
+    return lib().orc_sumlogprior(C.byref(p.c), ptr(a) if a is not None else None, ptr(b) if b is not None else None, ptr(xx))
