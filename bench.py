@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the ggdmc hot path on B200: DE-MCMC iterations of the hierarchical LBA fit.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one DE-MCMC iteration (src/de.cpp:281-381: one phi step + one step of every chain of
+every subject) of BASELINE config 4 -- 1024 synthetic subjects x 768 trials, 78 chains, the README
+B x v model -- with subjects sharded over the N GPUs (strong scaling: total work fixed).
+
+  value     trial-likelihoods/s with data, state and sample storage resident in HBM; the number of
+            trial-likelihoods is counted on the device (migration sweeps evaluate fewer chains)
+  e2e       the same metric through the reference-facing call `ggdmc_b200_run` (the C-ABI twin of
+            .Call("_ggdmc_run")) with HOST buffers: upload of data + start state, K iterations,
+            download of the K stored samples, all inside the timed region
+  roofline  the LBA likelihood kernel against the FP64 FMA peak measured on this GPU by a DFMA
+            microbenchmark (MEASURED_PEAKS.json has no FP64 entry); achieved = 513 algorithmic
+            flop per 2-accumulator trial x trial-likelihoods per launch / mean
+            CUDA-event duration of the launches inside the timed region
+  cpu_baseline  the CPU oracle (a -O2 C restatement of the reference's algorithm, kind "port") timed
+            on one host core on a bounded sample of the same workload
+
+`--impl reference` times the reference's CPU path (the same port, one replicate per host core like
+the reference's `ncore` forked replicates, R/sampling.R:26-55) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+F_TRIAL = {2: 513.0, 3: 755.0, 4: 997.0}  # algorithmic flop per trial-likelihood: 242 * n_acc + 29
+METRIC = "trial-likelihoods/s, DE-MCMC iterations of a hierarchical LBA fit"
+UNIT = "trial-likelihoods/s"
+
+WORKLOADS = {
+    # name: (model fixture, subjects, trials per subject, description)
+    "c4": (6, 1024, 768, "C4: hierarchical LBA B x v model (13 par, 24 cells, 2 acc), 1024 subjects x 768 trials, 78 chains, "
+                         "pop+sub migration 0.05"),
+    "c2": (6, 32, 768, "C2: README hierarchical recovery study, 32 subjects x 768 trials, 78 chains, pop+sub migration 0.05"),
+    "c5": (5, 256, 2048, "C5: 4-accumulator LBA, 96 cells, 17 par, 256 subjects x 2048 trials, 102 chains, pop+sub migration 0.05"),
+}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_hier_sample(model_k: int, n_subject: int, n_trial: int, n_iter: int, seed: int, n_warm: int = 0):
+    """Run the CPU oracle's run_hchains on `n_subject` synthetic subjects; returns (seconds, trial-likelihoods)."""
+    from ggdmc_b200 import synth
+    from ggdmc_b200.workloads import load_model
+    from oracle import binding as ob
+
+    spec = load_model(model_k)
+    ct = spec.ct
+    D, C = ct.npar, 6 * ct.npar
+    om = ob.OModel(ct.param_src, ct.const_val, ct.posdrift, ct.npar)
+
+    def opr(p):
+        return ob.OPrior(p.p0, p.p1, p.lower, p.upper, p.dist, p.log_p)
+
+    opp, ohp = opr(spec.p_prior), opr(spec.h_prior)
+    rng = np.random.default_rng([20260101, seed])
+    center = np.concatenate([spec.pop_mean, spec.pop_scale])
+    phi0 = np.abs(center[None, :] * (1.0 + 0.05 * rng.standard_normal((C, 2 * D))))
+    datas, pops = [], []
+    for s in range(n_subject):
+        th = synth.rtnorm(spec.pop_mean, spec.pop_scale, 0.0, rng)
+        tr = synth.simulate_subject(ct, spec.node_1_index, th, n_trial, rng)
+        od = ob.OData(tr.rt, tr.cell)
+        x0 = np.abs(th[None, :] * (1.0 + 0.05 * rng.standard_normal((C, D))))
+        lp = np.array([ob.sumlogprior(opp, x0[c], phi0[c, :D], phi0[c, D:]) for c in range(C)])
+        ll = np.array([ob.sumloglike(om, od, x0[c]) for c in range(C)])
+        datas.append(od)
+        pops.append(ob.OPop(x0, lp, ll, 2, 1 << 30))
+    phi = ob.OPop(phi0, np.array([ob.sumlogprior(ohp, phi0[c]) for c in range(C)]), np.zeros(C), 2, 1 << 30)
+    de = ob.make_de(2 * D, C, pop_migration_prob=0.05, sub_migration_prob=0.05, jacobi=False)
+    r = ob.make_rng(seed=seed)
+    if n_warm:
+        ob.run_hier(de, phi, pops, opp, ohp, om, datas, r, n_warm)
+    t0 = time.perf_counter()
+    ob.run_hier(de, phi, pops, opp, ohp, om, datas, r, n_iter)
+    dt = time.perf_counter() - t0
+    # crossover sweeps evaluate every chain; the 5 % migration sweeps fewer -- count the nominal
+    # crossover figure scaled by the expected fraction (0.95 + 0.05 * ~0.5)
+    n_lik = n_iter * n_subject * C * n_trial * (0.95 + 0.05 * 0.5)
+    return dt, n_lik
+
+
+def _ref_worker(args):
+    model_k, n_subject, n_trial, steps, warm, seed = args
+    return oracle_hier_sample(model_k, n_subject, n_trial, steps, seed, n_warm=warm)
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU path (oracle port), one replicate per host core, bounded sample."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    model_k, S, ntr, desc = WORKLOADS[args.workload]
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    n_sub = 4  # bounded sample: 4 of the subjects per replicate process
+    from oracle import binding as ob
+    ob.build()
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(model_k, n_sub, ntr, args.steps, args.warmup, 1000 + i) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    tmax = max(r[0] for r in res)
+    total = sum(r[1] for r in res)
+    value = total / tmax
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tmax / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "sample": f"{n_sub} subjects x {ntr} trials x {6 * 13 if model_k == 6 else 102} chains per replicate process"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} replicate processes (one per host core, like the reference's ncore forks), each "
+                                   f"{args.steps} DE-MCMC iterations over {n_sub} subjects of the workload; oracle C port at -O2; "
+                                   f"wall {wall:.1f} s"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--schedule", default="parallel", choices=["parallel", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    from ggdmc_b200 import _lib as B
+    from ggdmc_b200 import engine as E
+    from ggdmc_b200 import workloads as W
+
+    B.build()
+    if E.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: ggdmc_b200 has no CPU fallback")
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+        uid = [E.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        E.comm_init(world, rank, uid[0], local_rank)
+    else:
+        import ctypes
+        # make device `local_rank` current for this process without torch
+        cudart = ctypes.CDLL("libcudart.so.12") if os.path.exists("/usr/local/cuda/lib64/libcudart.so.12") else None
+        if cudart is not None and local_rank:
+            cudart.cudaSetDevice(local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    model_k, S, ntr, desc = WORKLOADS[args.workload]
+    s0, s1 = rank * S // world, (rank + 1) * S // world
+    schedule = B.SCHEDULE_PARALLEL if args.schedule == "parallel" else B.SCHEDULE_REFERENCE
+
+    fp64_peak = E.measure_fp64_tflops(local_rank) if rank == 0 else 0.0
+
+    w = W.hierarchical(args.workload, model_k, S, ntr, n_replicate=1, subject_begin=s0, subject_end=s1)
+    n_acc = w.spec.ct.n_acc
+    seeds = [9032]
+    K, Wm = args.steps, args.warmup
+    tun = W.tuning_for(w, nmc=2, thin=1 << 30, seeds=seeds, schedule=schedule, subject_begin=s0, n_subject_total=S, device=local_rank)
+    eng = E.Engine(w.spec.ct, w.trials, w.spec.p_prior, w.spec.h_prior, tun, w.phi_start, w.subj_start)
+
+    eng.iterate(Wm)
+    eng.counters()
+    eng.profile(True)
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms = eng.iterate_flushed(K, 256 << 20)
+    clocks = sampler.stop()
+    barrier()
+    n_lik_local, like_ms, like_launches = eng.counters()
+    launches = eng.launch_count - launches0
+    ms_max = allmax(ms)
+    n_lik = allsum(float(n_lik_local))
+    value = n_lik / (ms_max * 1e-3)
+    eng.profile(False)
+
+    # ---- roofline of the likelihood kernel (rank 0's launches) --------------------------------
+    roofline = None
+    if rank == 0 and like_launches > 0:
+        per_launch_s = like_ms * 1e-3 / like_launches
+        lik_per_launch = n_lik_local / like_launches
+        achieved = F_TRIAL[n_acc] * lik_per_launch / per_launch_s / 1e12
+        bytes_per_launch = 10.0 * lik_per_launch
+        roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                    "kernel": "gg::k_like", "peak_source": "DFMA microbenchmark on this GPU (ggdmc_b200_measure_fp64_tflops), burst",
+                    "flop_per_trial_lik": F_TRIAL[n_acc], "trial_lik_per_launch": lik_per_launch,
+                    "launch_ms": per_launch_s * 1e3, "kernel_share_of_step": like_ms / ms,
+                    "hbm_side": {"algorithmic_GBps": bytes_per_launch / per_launch_s / 1e9, "bytes_per_trial_lik": 10}}
+
+    # ---- end to end through the reference-facing call with host buffers -----------------------
+    e2e = None
+    if not args.no_e2e:
+        tun2 = W.tuning_for(w, nmc=K + 1, thin=1, seeds=seeds, schedule=schedule, subject_begin=s0, n_subject_total=S, device=local_rank)
+        barrier()
+        t0 = time.perf_counter()
+        phi_out, subj_out = E.run_hier(w.spec.ct, w.trials, w.spec.p_prior, w.spec.h_prior, tun2, w.phi_start, w.subj_start)
+        dt = time.perf_counter() - t0
+        dt_max = allmax(dt)
+        h2d = sum(t.rt.nbytes + t.cell.nbytes for t in w.trials) + sum(s.theta.nbytes + s.lp.nbytes + s.ll.nbytes for s in w.subj_start)
+        h2d += w.phi_start.theta.nbytes + w.phi_start.lp.nbytes + w.phi_start.ll.nbytes
+        d2h = sum(o.theta.nbytes + o.lp.nbytes + o.ll.nbytes for o in subj_out) + phi_out.theta.nbytes + phi_out.lp.nbytes + phi_out.ll.nbytes
+        e2e = {"value": (n_lik / K) * K / dt_max, "unit": UNIT, "h2d_bytes_per_step": allsum(h2d) / K, "d2h_bytes_per_step": allsum(d2h) / K,
+               "ms_per_step": 1e3 * dt_max / K,
+               "call": "ggdmc_b200_run (C-ABI twin of .Call('_ggdmc_run')), pageable host buffers, thin = 1, nmc = steps + 1; "
+                       "trial-likelihoods per iteration taken from the resident phase's device counter"}
+        assert np.all(np.isfinite(phi_out.theta))
+    eng.close()
+
+    # ---- CPU baseline: the oracle port on one host core, bounded sample ------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as ob
+        ob.build()
+        dt1, n1 = oracle_hier_sample(model_k, 2, ntr, 1, 7)
+        iters = int(max(1, min(50, 12.0 / max(dt1 * 4, 1e-3))))  # aim at ~12 s of CPU work on 8 subjects
+        dtc, nc = oracle_hier_sample(model_k, 8, ntr, iters, 8)
+        cpu = {"value": nc / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{iters} DE-MCMC iterations (run_hchains restatement, reference chain order) over 8 subjects x {ntr} trials x "
+                         f"{w.nchain} chains of the same synthetic population; {dtc:.1f} s on one host core, gcc -O2"}
+        R = ob.ref_lib()
+        if R is not None:  # the reference's own object code (-O0 build) on the density alone, for context
+            g = np.load(os.path.join(ROOT, "tests", "golden", f"lba_data{model_k}.npz"))
+            tr = w.trials[0]
+            om = ob.OModel(w.spec.ct.param_src, w.spec.ct.const_val, w.spec.ct.posdrift, w.spec.ct.npar)
+            th = ob.f64(w.true_theta[0])
+            import ctypes as C
+            cells = np.unique(tr.cell)
+            Ps, rts = [], []
+            for cc in cells:
+                P = np.zeros((6, n_acc))
+                ob.lib().orc_cell_params(C.byref(om.c), ob.ptr(th), int(cc), ob.ptr(P))
+                Ps.append(P)
+                rts.append(ob.f64(tr.rt[tr.cell == cc]))
+            u = np.zeros(1 << 16)
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 2.0:
+                R.ref_set_uniform_stream(ob.ptr(u), len(u))
+                for P, r in zip(Ps, rts):
+                    o = np.empty_like(r)
+                    R.ref_lba_cell(ob.ptr(P), n_acc, ob.ptr(om.posdrift, ob.c_u8p), ob.ptr(r), len(r), ob.ptr(o))
+                reps += 1
+            cpu["reference_object_code_density_only"] = {
+                "value": reps * len(tr.rt) / (time.perf_counter() - t0), "unit": UNIT, "cores": 1,
+                "note": "lba_class::{set_parameters,validate_parameters,dlba} of the reference's src/de.o (author's -O0 build) "
+                        "through oracle/_ref, density only (no log/sum, no sampler)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "schedule": args.schedule, "subjects_per_gpu": s1 - s0, "nchain": w.nchain,
+                       "trials_per_subject": ntr, "l2": "flushed: 256 MiB memset before every timed iteration, outside the event brackets",
+                       "timing": "CUDA events on the engine stream around each iteration, summed; max over ranks",
+                       "seeds": seeds},
+            "iters_per_s": K / (ms_max * 1e-3),
+            "trial_lik_per_iter": n_lik / K,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        E.comm_finalize()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1030 @@
+// ggdmc_b200 -- host side of the engine: device state, launch sequences, C ABI.
+//
+// Replaces the C++ side of the reference's .Call boundary: run_subject / run_hyper / run
+// (src/de2R.cpp:8-171) and the drivers de_class::run_chains / run_hchains (src/de.cpp:201-242,
+// 272-383).  No PyTorch, no CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/ggdmc_b200.h"
+#include "gg_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+
+using namespace gg;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_CHECK(expr)                                                                                         \
+    do {                                                                                                         \
+        cudaError_t e_ = (expr);                                                                                 \
+        if (e_ != cudaSuccess)                                                                                   \
+            throw Error(GGDMC_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr);    \
+    } while (0)
+
+void require(bool ok, const char *msg)
+{
+    if (!ok) throw Error(GGDMC_ERR_ARG, msg);
+}
+
+template <class T>
+struct DBuf { // device buffer
+    T *p = nullptr;
+    size_t n = 0;
+    DBuf() = default;
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    ~DBuf() { if (p) cudaFree(p); }
+    void alloc(size_t count)
+    {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        if (count) CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void zero() { if (n) CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T))); }
+    void upload(const T *h, size_t count)
+    {
+        alloc(count);
+        if (count) CUDA_CHECK(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void upload(const std::vector<T> &h) { upload(h.data(), h.size()); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen: single-GPU use has no NCCL dependency at all
+// ---------------------------------------------------------------------------------------------
+struct Nccl {
+    typedef struct { char internal[128]; } UniqueId;
+    typedef void *Comm;
+    void *lib = nullptr;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    Comm comm = nullptr;
+    int n_rank = 1, rank = 0;
+
+    void load()
+    {
+        if (lib) return;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) throw Error(GGDMC_ERR_COMM, std::string("cannot load libnccl: ") + dlerror());
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy)
+            throw Error(GGDMC_ERR_COMM, "libnccl lacks required symbols");
+    }
+    void check(int r, const char *what)
+    {
+        if (r != 0)
+            throw Error(GGDMC_ERR_COMM, std::string("NCCL error in ") + what + ": " + (GetErrorString ? GetErrorString(r) : "?"));
+    }
+};
+Nccl g_nccl;
+
+// ---------------------------------------------------------------------------------------------
+// uploads
+// ---------------------------------------------------------------------------------------------
+struct ModelDev {
+    DBuf<int> param_src;
+    DBuf<double> const_val;
+    DBuf<uint8_t> posdrift;
+    DevModel d{};
+    void upload(const ggdmc_model_t *m)
+    {
+        require(m && m->n_acc >= 1 && m->n_acc <= 16 && m->n_cell >= 1 && m->npar >= 1, "bad model dimensions");
+        require(m->n_cell < 65535, "too many cells");
+        const size_t n = (size_t)m->n_cell * 6 * m->n_acc;
+        for (size_t i = 0; i < n; ++i) {
+            const int s = m->param_src[i];
+            require(s >= 0 ? s < m->npar : (-1 - s) < m->n_const, "param_src out of range");
+        }
+        param_src.upload(m->param_src, n);
+        std::vector<double> cv(m->const_val, m->const_val + std::max(m->n_const, 0));
+        if (cv.empty()) cv.push_back(0.0);
+        const_val.upload(cv);
+        posdrift.upload(m->posdrift, m->n_acc);
+        d.n_acc = m->n_acc; d.n_cell = m->n_cell; d.npar = m->npar; d.n_const = m->n_const;
+        d.param_src = param_src.p; d.const_val = const_val.p; d.posdrift = posdrift.p;
+    }
+    size_t table_bytes() const { return (size_t)d.n_cell * d.n_acc * sizeof(CellAcc); }
+};
+
+struct PriorDev {
+    DBuf<double> p0, p1, lower, upper;
+    DBuf<int> dist;
+    DBuf<uint8_t> log_p;
+    DevPrior d{};
+    void upload(const ggdmc_prior_t *p)
+    {
+        require(p && p->npar >= 1, "bad prior");
+        p0.upload(p->p0, p->npar); p1.upload(p->p1, p->npar);
+        lower.upload(p->lower, p->npar); upper.upload(p->upper, p->npar);
+        dist.upload(p->dist, p->npar); log_p.upload(p->log_p, p->npar);
+        d.npar = p->npar; d.p0 = p0.p; d.p1 = p1.p; d.lower = lower.p; d.upper = upper.p; d.dist = dist.p; d.log_p = log_p.p;
+    }
+};
+
+// Trials of all local subjects: grouped by cell (stable), each subject padded to a multiple of 8
+// trials with cell = 0xFFFF so that 16-byte vector loads never cross into the next subject.
+struct TrialsDev {
+    DBuf<double> rt;
+    DBuf<uint16_t> cell;
+    DBuf<int64_t> offset;
+    DBuf<int> count;
+    DBuf<unsigned long long> counter;
+    std::vector<int> h_count;
+    std::vector<std::vector<int>> order; // per subject: position in the grouped array -> caller's trial index
+    int S = 0, max_count = 0;
+    int64_t total = 0;
+    TrialData d{};
+    void upload(const ggdmc_trials_t *t, int n_cell, bool keep_order)
+    {
+        require(t && t->n_subject >= 1, "no subjects");
+        S = t->n_subject;
+        std::vector<int64_t> off(S);
+        h_count.resize(S);
+        std::vector<double> hrt;
+        std::vector<uint16_t> hcl;
+        if (keep_order) order.resize(S);
+        int64_t pos = 0;
+        for (int s = 0; s < S; ++s) {
+            const int64_t b = t->subject_offset[s], e = t->subject_offset[s + 1];
+            require(e >= b && e - b < (int64_t)1 << 31, "bad subject_offset");
+            const int n = (int)(e - b);
+            std::vector<int> idx(n);
+            std::iota(idx.begin(), idx.end(), 0);
+            for (int i = 0; i < n; ++i) require(t->cell[b + i] < n_cell, "cell index out of range");
+            std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return t->cell[b + x] < t->cell[b + y]; });
+            off[s] = pos;
+            h_count[s] = n;
+            max_count = std::max(max_count, n);
+            const int npad = (n + 7) & ~7;
+            hrt.resize(pos + npad, 0.0);
+            hcl.resize(pos + npad, 0xFFFF);
+            for (int i = 0; i < n; ++i) {
+                hrt[pos + i] = t->rt[b + idx[i]];
+                hcl[pos + i] = t->cell[b + idx[i]];
+            }
+            if (keep_order) order[s] = idx;
+            pos += npad;
+            total += n;
+        }
+        rt.upload(hrt); cell.upload(hcl); offset.upload(off); count.upload(h_count);
+        counter.alloc(1); counter.zero();
+        d.rt = rt.p; d.cell = cell.p; d.offset = offset.p; d.count = count.p; d.counter = counter.p;
+    }
+    void set_chunking(int64_t blocks_per_split_unit)
+    {
+        // enough blocks to fill 148 SMs a few times over, at least 256 trials per block
+        int want = (int)std::max<int64_t>(1, (4 * 148 + blocks_per_split_unit - 1) / blocks_per_split_unit);
+        int max_split = std::max(1, (max_count + 255) / 256);
+        int nsplit = std::min(want, max_split);
+        if (max_count > 8192) nsplit = std::max(nsplit, (max_count + 4095) / 4096);
+        int chunk = ((std::max(1, (max_count + nsplit - 1) / nsplit)) + 7) & ~7;
+        nsplit = std::max(1, (max_count + chunk - 1) / chunk);
+        d.chunk = chunk;
+        d.nsplit = nsplit;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// one level of the sampler on the device
+// ---------------------------------------------------------------------------------------------
+struct LevelDev {
+    DBuf<double> theta, lp, ll, prop, prop_lp, out_theta, out_lp, out_ll;
+    DBuf<int> target, mode, mig_n, mig_list, para, mode0;
+    Level L{};
+    int n_rep = 1;
+    void create(int npop, int n_rep_, int C, int D, int nmc, int thin)
+    {
+        n_rep = n_rep_;
+        const size_t PC = (size_t)npop * C;
+        theta.alloc(PC * D); lp.alloc(PC); ll.alloc(PC); prop.alloc(PC * D); prop_lp.alloc(PC);
+        prop.zero(); prop_lp.zero();
+        target.alloc(PC); mode.alloc(npop); mig_n.alloc(npop); mig_list.alloc(PC); para.alloc(npop); mode0.alloc(npop);
+        CUDA_CHECK(cudaMemset(target.p, 0xFF, PC * sizeof(int)));
+        mode.zero(); mig_n.zero(); mig_list.zero(); para.zero(); mode0.zero();
+        out_theta.alloc(PC * D * nmc); out_lp.alloc(PC * nmc); out_ll.alloc(PC * nmc);
+        L.npop = npop; L.nchain = C; L.npar = D; L.nmc = nmc; L.thin = thin;
+        L.theta = theta.p; L.lp = lp.p; L.ll = ll.p; L.prop = prop.p; L.prop_lp = prop_lp.p;
+        L.target = target.p; L.mode = mode.p; L.mig_n = mig_n.p; L.mig_list = mig_list.p; L.para = para.p; L.mode0 = mode0.p;
+        L.out_theta = out_theta.p; L.out_lp = out_lp.p; L.out_ll = out_ll.p;
+    }
+};
+
+int pick_device(int requested)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        throw Error(GGDMC_ERR_CUDA, "no CUDA device: ggdmc_b200 has no CPU fallback");
+    if (requested >= 0) {
+        require(requested < n, "device ordinal out of range");
+        CUDA_CHECK(cudaSetDevice(requested));
+        return requested;
+    }
+    int cur = 0;
+    CUDA_CHECK(cudaGetDevice(&cur));
+    return cur;
+}
+
+template <class K>
+void allow_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+constexpr int kLikeBlock = 128;
+constexpr int kHyperBlock = 256;
+constexpr int kProposeWarps = 4;
+
+size_t like_smem(const DevModel &M, int D)
+{
+    size_t b = (size_t)M.n_cell * M.n_acc * sizeof(CellAcc) + (size_t)D * 8 + (kLikeBlock / 32) * 8 + (size_t)M.n_cell * M.n_acc;
+    return (b + 15) & ~(size_t)15;
+}
+
+void launch_like(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step,
+                 double *ll_part, cudaStream_t st)
+{
+    dim3 grid(step < 0 ? L.npop * L.nchain : L.npop, T.nsplit);
+    const size_t sm = like_smem(M, L.npar);
+    require(sm <= 220 * 1024, "cell table does not fit in shared memory");
+    switch (M.n_acc) {
+    case 2:
+        allow_smem(k_like<2, kLikeBlock>, sm);
+        k_like<2, kLikeBlock><<<grid, kLikeBlock, sm, st>>>(L, M, T, d_iter, sweep, step, ll_part);
+        break;
+    case 3:
+        allow_smem(k_like<3, kLikeBlock>, sm);
+        k_like<3, kLikeBlock><<<grid, kLikeBlock, sm, st>>>(L, M, T, d_iter, sweep, step, ll_part);
+        break;
+    case 4:
+        allow_smem(k_like<4, kLikeBlock>, sm);
+        k_like<4, kLikeBlock><<<grid, kLikeBlock, sm, st>>>(L, M, T, d_iter, sweep, step, ll_part);
+        break;
+    default:
+        allow_smem(k_like<0, kLikeBlock>, sm);
+        k_like<0, kLikeBlock><<<grid, kLikeBlock, sm, st>>>(L, M, T, d_iter, sweep, step, ll_part);
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// the engine
+// ---------------------------------------------------------------------------------------------
+struct ggdmc_engine {
+    // kind: 0 independent subjects (run_subject), 1 hyper only (run_hyper), 2 hierarchy (run)
+    int kind = 0;
+    int device = 0;
+    int R = 1, S = 0, C = 0, D = 0, D2 = 0, nmc = 0, thin = 1;
+    int schedule = GGDMC_SCHEDULE_PARALLEL;
+    int is_hblocked = 0, is_pblocked = 0;
+    int subject_begin = 0;
+    uint32_t h_iter = 0;
+    int64_t launches = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // optional per-launch timing of the likelihood kernel (bench.py roofline)
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
+    double like_ms = 0.0;
+    int64_t like_launches = 0;
+
+    ModelDev model;
+    PriorDev p_prior, h_prior;
+    TrialsDev trials;
+    LevelDev subj, phi;
+    DBuf<uint64_t> seeds;
+    DBuf<uint32_t> d_iter;
+    DBuf<double> ll_part, hpart, hsum, hyper_data;
+    HyperArgs H{};
+
+    ~ggdmc_engine()
+    {
+        for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    void common_init(const ggdmc_config_t *cfg)
+    {
+        require(cfg != nullptr, "null config");
+        if (cfg->nchain <= 2) throw Error(GGDMC_ERR_CHAINS, "Require three or more chains."); // src/de.cpp:7-10
+        require(cfg->nchain <= 65535, "nchain too large");
+        require(cfg->nmc >= 1 && cfg->thin >= 1, "nmc and thin must be >= 1");
+        require(cfg->n_replicate >= 1 && cfg->seed != nullptr, "need n_replicate >= 1 seeds");
+        require(cfg->schedule == GGDMC_SCHEDULE_REFERENCE || cfg->schedule == GGDMC_SCHEDULE_PARALLEL, "bad schedule");
+        require(cfg->nparameter >= 1, "de_input nparameter must be >= 1");
+        device = pick_device(cfg->device);
+        R = cfg->n_replicate; C = cfg->nchain; nmc = cfg->nmc; thin = cfg->thin;
+        schedule = cfg->schedule; is_hblocked = cfg->is_hblocked; is_pblocked = cfg->is_pblocked;
+        subject_begin = cfg->subject_begin;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreate(&ev0));
+        CUDA_CHECK(cudaEventCreate(&ev1));
+        seeds.upload(cfg->seed, R);
+        uint32_t z = 0;
+        d_iter.upload(&z, 1);
+    }
+
+    void init_level_state(LevelDev &lv, const ggdmc_start_t *starts, int n_items, int D_)
+    {
+        // starts[i] holds [R][C][D_] for item i (subject or phi); device population p = r * n_items + i
+        const size_t CD = (size_t)C * D_;
+        std::vector<double> th((size_t)R * n_items * CD), lp((size_t)R * n_items * C), ll(lp.size());
+        for (int i = 0; i < n_items; ++i) {
+            require(starts[i].theta && starts[i].lp && starts[i].ll, "null start state");
+            for (int r = 0; r < R; ++r) {
+                const size_t p = (size_t)r * n_items + i;
+                std::memcpy(&th[p * CD], starts[i].theta + (size_t)r * CD, CD * 8);
+                std::memcpy(&lp[p * C], starts[i].lp + (size_t)r * C, (size_t)C * 8);
+                std::memcpy(&ll[p * C], starts[i].ll + (size_t)r * C, (size_t)C * 8);
+            }
+        }
+        CUDA_CHECK(cudaMemcpy(lv.theta.p, th.data(), th.size() * 8, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(lv.lp.p, lp.data(), lp.size() * 8, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(lv.ll.p, ll.data(), ll.size() * 8, cudaMemcpyHostToDevice));
+        // slot 0 of the storage = start state
+        const int npop = R * n_items;
+        for (int p = 0; p < npop; ++p) {
+            CUDA_CHECK(cudaMemcpy(lv.out_theta.p + (size_t)p * nmc * CD, lv.theta.p + (size_t)p * CD, CD * 8, cudaMemcpyDeviceToDevice));
+            CUDA_CHECK(cudaMemcpy(lv.out_lp.p + (size_t)p * nmc * C, lv.lp.p + (size_t)p * C, (size_t)C * 8, cudaMemcpyDeviceToDevice));
+            CUDA_CHECK(cudaMemcpy(lv.out_ll.p + (size_t)p * nmc * C, lv.ll.p + (size_t)p * C, (size_t)C * 8, cudaMemcpyDeviceToDevice));
+        }
+    }
+
+    // ---- construction for the three run kinds ------------------------------------------------
+    void create_lba(const ggdmc_model_t *m, const ggdmc_trials_t *t, const ggdmc_prior_t *pp, const ggdmc_prior_t *hp,
+                    const ggdmc_config_t *cfg, const ggdmc_start_t *phi_start, const ggdmc_start_t *subj_start)
+    {
+        common_init(cfg);
+        kind = hp ? 2 : 0;
+        model.upload(m);
+        D = m->npar;
+        require(pp && pp->npar == D, "p_prior length != model npar");
+        p_prior.upload(pp);
+        trials.upload(t, m->n_cell, false);
+        S = t->n_subject;
+        trials.set_chunking((int64_t)R * S * C);
+        subj.create(R * S, R, C, D, nmc, thin);
+        Level &L = subj.L;
+        L.pops_per_rep = S; L.pop_id_base = subject_begin; L.is_phi = 0;
+        L.gamma = cfg->gamma_precursor / std::sqrt(2.0 * cfg->nparameter); // src/de.cpp:12,24
+        L.rp = cfg->rp; L.mig_prob = cfg->sub_migration_prob;
+        L.seed = seeds.p; L.prior = p_prior.d; L.prior_ovr = nullptr;
+        L.nmove = std::min(D, kind == 2 ? cfg->nparameter / 2 : cfg->nparameter); // src/de.cpp:136 / :592
+        init_level_state(subj, subj_start, S, D);
+        ll_part.alloc((size_t)R * S * C * trials.d.nsplit);
+        ll_part.zero();
+        if (kind == 2) {
+            D2 = 2 * D;
+            require(hp->npar == D2, "h_prior length != 2 * npar");
+            h_prior.upload(hp);
+            phi.create(R, R, C, D2, nmc, thin);
+            Level &P = phi.L;
+            P.pops_per_rep = 1; P.pop_id_base = 0; P.is_phi = 1;
+            P.gamma = L.gamma; P.rp = cfg->rp; P.mig_prob = cfg->pop_migration_prob;
+            P.seed = seeds.p; P.prior = h_prior.d; P.prior_ovr = nullptr;
+            P.nmove = std::min(D2, cfg->nparameter);
+            init_level_state(phi, phi_start, 1, D2);
+            L.prior_ovr = phi.theta.p; // src/de.cpp:599-600, 646-649
+            setup_hyper(subj.theta.p, (int)((size_t)S * C * D), C * D, D, 1);
+        }
+    }
+
+    void create_hyper(const ggdmc_prior_t *pp, const ggdmc_prior_t *hp, const double *data_theta, int n_subject,
+                      const ggdmc_config_t *cfg, const ggdmc_start_t *start)
+    {
+        common_init(cfg);
+        kind = 1;
+        require(pp && hp && data_theta && n_subject >= 1, "bad run_hyper arguments");
+        D = pp->npar; D2 = 2 * D; S = n_subject;
+        require(hp->npar == D2, "h_prior length != 2 * npar");
+        p_prior.upload(pp);
+        h_prior.upload(hp);
+        hyper_data.upload(data_theta, (size_t)S * D);
+        phi.create(R, R, C, D2, nmc, thin);
+        Level &P = phi.L;
+        P.pops_per_rep = 1; P.pop_id_base = 0; P.is_phi = 1;
+        P.gamma = cfg->gamma_precursor / std::sqrt(2.0 * cfg->nparameter);
+        P.rp = cfg->rp; P.mig_prob = cfg->sub_migration_prob; // run_chains uses m_sub_migration_prob, src/de.cpp:205-206
+        P.seed = seeds.p; P.prior = h_prior.d; P.prior_ovr = nullptr;
+        P.nmove = std::min(D2, cfg->nparameter);
+        init_level_state(phi, start, 1, D2);
+        setup_hyper(hyper_data.p, 0, D, 0, 0);
+    }
+
+    void setup_hyper(const double *x, int rep_stride, int subj_stride, int chain_stride, int need_cur)
+    {
+        H.like = p_prior.d;
+        H.x = x; H.x_rep_stride = rep_stride; H.x_subj_stride = subj_stride; H.x_chain_stride = chain_stride;
+        H.S = S; H.D = D; H.need_cur = need_cur;
+        // split subjects over blocks so that K4 fills the GPU (R*C blocks alone would not)
+        int want = std::max(1, (2 * 148 + R * C - 1) / (R * C));
+        int spb = std::max(16, (S + want - 1) / want);
+        H.subj_per_block = spb;
+        H.nsplit = (S + spb - 1) / spb;
+        hpart.alloc((size_t)R * C * 2 * H.nsplit);
+        hpart.zero();
+        hsum.alloc((size_t)R * C * 2);
+        hsum.zero();
+    }
+
+    // likelihood launch, optionally bracketed by CUDA events on the launching stream
+    void timed_like(const Level &L, int sweep, int step)
+    {
+        if (!profile) {
+            launch_like(L, model.d, trials.d, d_iter.p, sweep, step, ll_part.p, stream);
+            return;
+        }
+        if (prof_used + 2 > prof_ev.size()) {
+            for (int i = 0; i < 2; ++i) {
+                cudaEvent_t e;
+                CUDA_CHECK(cudaEventCreate(&e));
+                prof_ev.push_back(e);
+            }
+        }
+        CUDA_CHECK(cudaEventRecord(prof_ev[prof_used], stream));
+        launch_like(L, model.d, trials.d, d_iter.p, sweep, step, ll_part.p, stream);
+        CUDA_CHECK(cudaEventRecord(prof_ev[prof_used + 1], stream));
+        prof_used += 2;
+    }
+    void collect_profile()
+    {
+        for (size_t i = 0; i + 1 < prof_used; i += 2) {
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]));
+            like_ms += ms;
+            ++like_launches;
+        }
+        prof_used = 0;
+    }
+
+    // ---- one sweep at each level --------------------------------------------------------------
+    void sweep_lba(int sweep, int decide_once, int para_idx)
+    {
+        Level &L = subj.L;
+        const size_t prop_sm = (size_t)kProposeWarps * D * 8;
+        k_sweep_begin<<<L.npop, 128, (size_t)2 * C * sizeof(int), stream>>>(L, d_iter.p, sweep, decide_once, para_idx);
+        ++launches;
+        if (schedule == GGDMC_SCHEDULE_PARALLEL) {
+            k_propose<kProposeWarps><<<L.npop, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1);
+            timed_like(L, sweep, -1);
+            const int n = L.npop * C;
+            k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, ll_part.p, trials.d.nsplit);
+            launches += 3;
+        } else {
+            for (int step = 0; step < C; ++step) {
+                k_propose<kProposeWarps><<<L.npop, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step);
+                timed_like(L, sweep, step);
+                k_accept<<<(L.npop + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, step, ll_part.p, trials.d.nsplit);
+                launches += 3;
+            }
+        }
+        CUDA_CHECK(cudaGetLastError());
+    }
+
+    void hyper_eval(int step)
+    {
+        Level &P = phi.L;
+        const size_t sm = (size_t)(6 * D + kHyperBlock / 32) * 8;
+        dim3 grid(step < 0 ? R * C : R, H.nsplit, step < 0 ? 1 : 2);
+        k_hyper<kHyperBlock><<<grid, kHyperBlock, sm, stream>>>(P, H, step, hpart.p);
+        const int n = R * C * 2;
+        k_hyper_reduce<<<(n + 127) / 128, 128, 0, stream>>>(hpart.p, n, H.nsplit, hsum.p);
+        launches += 2;
+        if (kind == 2 && g_nccl.comm && g_nccl.n_rank > 1) {
+            // the one exchange of the path: partial sums over the local subjects -> sums over all subjects
+            g_nccl.check(g_nccl.AllReduce(hsum.p, hsum.p, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, g_nccl.comm, stream),
+                         "ncclAllReduce");
+        }
+    }
+
+    void sweep_phi(int sweep, int decide_once, int para_idx)
+    {
+        Level &P = phi.L;
+        const size_t prop_sm = (size_t)kProposeWarps * D2 * 8;
+        const int need_cur = H.need_cur;
+        k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), stream>>>(P, d_iter.p, sweep, decide_once, para_idx);
+        ++launches;
+        if (schedule == GGDMC_SCHEDULE_PARALLEL) {
+            k_propose<kProposeWarps><<<R, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, -1);
+            hyper_eval(-1);
+            const int n = R * C;
+            k_phi_accept<<<(n + 127) / 128, 128, 0, stream>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur);
+            launches += 2;
+        } else {
+            for (int step = 0; step < C; ++step) {
+                k_propose<kProposeWarps><<<R, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, step);
+                hyper_eval(step);
+                k_phi_accept<<<(R + 127) / 128, 128, 0, stream>>>(P, d_iter.p, sweep, step, hsum.p, need_cur);
+                launches += 2;
+            }
+        }
+        CUDA_CHECK(cudaGetLastError());
+    }
+
+    void store(LevelDev &lv)
+    {
+        const size_t total = (size_t)lv.L.npop * C * lv.L.npar;
+        int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+        k_store<<<blocks, 256, 0, stream>>>(lv.L, d_iter.p);
+        ++launches;
+    }
+
+    // one DE-MCMC iteration: run_chains body (src/de.cpp:208-240) or run_hchains body (:281-381)
+    void iteration()
+    {
+        k_iter_advance<<<1, 1, 0, stream>>>(d_iter.p);
+        ++launches;
+        ++h_iter;
+        if (kind == 2) {
+            if (is_hblocked)
+                for (int p = 0; p < D2; ++p) sweep_phi(p, 0, p);
+            else
+                sweep_phi(0, 0, -1);
+            if (is_pblocked)
+                for (int p = 0; p < D; ++p) sweep_lba(p, 0, p);
+            else
+                sweep_lba(0, 0, -1);
+            store(subj);
+            store(phi);
+        } else if (kind == 0) {
+            if (is_pblocked)
+                for (int p = 0; p < subj.L.nmove; ++p) sweep_lba(p, 1, p);
+            else
+                sweep_lba(0, 1, -1);
+            store(subj);
+        } else {
+            if (is_pblocked)
+                for (int p = 0; p < phi.L.nmove; ++p) sweep_phi(p, 1, p);
+            else
+                sweep_phi(0, 1, -1);
+            store(phi);
+        }
+    }
+
+    void iterate(int n_iter, float *elapsed_ms, ggdmc_progress_fn progress, void *user, int report_length)
+    {
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaEventRecord(ev0, stream));
+        for (int i = 0; i < n_iter; ++i) {
+            iteration();
+            if (progress && report_length > 0 && h_iter % (uint32_t)thin == 0) {
+                uint32_t stored = h_iter / (uint32_t)thin; // theta_phi::print_progress, @hdr/theta.h:76-85
+                if ((stored + 1) % (uint32_t)report_length == 0) progress((int32_t)(stored + 1), user);
+            }
+        }
+        CUDA_CHECK(cudaEventRecord(ev1, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaGetLastError());
+        if (elapsed_ms) CUDA_CHECK(cudaEventElapsedTime(elapsed_ms, ev0, ev1));
+        if (profile) collect_profile();
+    }
+
+    // Timed iterations with an L2 flush (a memset larger than L2) before each one; only the iterations
+    // themselves are inside the event brackets.  Returns the summed per-iteration time.
+    void iterate_flushed(int n_iter, size_t flush_bytes, float *elapsed_ms)
+    {
+        CUDA_CHECK(cudaSetDevice(device));
+        DBuf<unsigned char> flush;
+        flush.alloc(flush_bytes);
+        std::vector<cudaEvent_t> ev((size_t)2 * n_iter);
+        for (auto &e : ev) CUDA_CHECK(cudaEventCreate(&e));
+        for (int i = 0; i < n_iter; ++i) {
+            CUDA_CHECK(cudaMemsetAsync(flush.p, i & 0xff, flush_bytes, stream));
+            CUDA_CHECK(cudaEventRecord(ev[2 * i], stream));
+            iteration();
+            CUDA_CHECK(cudaEventRecord(ev[2 * i + 1], stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaGetLastError());
+        double total = 0.0;
+        for (int i = 0; i < n_iter; ++i) {
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+            total += ms;
+        }
+        for (auto &e : ev) cudaEventDestroy(e);
+        if (elapsed_ms) *elapsed_ms = (float)total;
+        if (profile) collect_profile();
+    }
+
+    // device storage -> the caller's posterior arrays
+    void download_level(LevelDev &lv, int n_items, ggdmc_samples_t *outs)
+    {
+        const int D_ = lv.L.npar;
+        const size_t blk = (size_t)nmc * C * D_, blk1 = (size_t)nmc * C;
+        for (int i = 0; i < n_items; ++i) {
+            require(outs[i].theta && outs[i].lp && outs[i].ll, "null output arrays");
+            for (int r = 0; r < R; ++r) {
+                const size_t p = (size_t)r * n_items + i;
+                CUDA_CHECK(cudaMemcpy(outs[i].theta + (size_t)r * blk, lv.out_theta.p + p * blk, blk * 8, cudaMemcpyDeviceToHost));
+                CUDA_CHECK(cudaMemcpy(outs[i].lp + (size_t)r * blk1, lv.out_lp.p + p * blk1, blk1 * 8, cudaMemcpyDeviceToHost));
+                CUDA_CHECK(cudaMemcpy(outs[i].ll + (size_t)r * blk1, lv.out_ll.p + p * blk1, blk1 * 8, cudaMemcpyDeviceToHost));
+            }
+            outs[i].npar = D_; outs[i].nchain = C; outs[i].nmc = nmc;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+namespace {
+int fail(char err[256], const std::exception &e, int code)
+{
+    if (err) {
+        std::snprintf(err, 256, "%s", e.what());
+    }
+    return code;
+}
+#define GG_TRY try {
+#define GG_CATCH                                                    \
+    }                                                               \
+    catch (const Error &e) { return fail(err, e, e.code); }         \
+    catch (const std::exception &e) { return fail(err, e, GGDMC_ERR_ARG); } \
+    return GGDMC_OK;
+} // namespace
+
+extern "C" {
+
+int ggdmc_b200_abi_version(void) { return GGDMC_B200_ABI_VERSION; }
+
+int ggdmc_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int ggdmc_b200_engine_create(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const ggdmc_prior_t *p_prior,
+                             const ggdmc_prior_t *h_prior, const ggdmc_config_t *cfg, const ggdmc_start_t *phi_start,
+                             const ggdmc_start_t *subj_start, ggdmc_engine_t **engine, char err[256])
+{
+    GG_TRY
+    require(engine != nullptr, "null engine pointer");
+    *engine = nullptr;
+    require(model && trials && p_prior && cfg && subj_start, "null argument");
+    require(h_prior == nullptr || phi_start != nullptr, "hierarchical fit needs a phi start state");
+    auto *e = new ggdmc_engine();
+    try {
+        e->create_lba(model, trials, p_prior, h_prior, cfg, phi_start, subj_start);
+    } catch (...) {
+        delete e;
+        throw;
+    }
+    *engine = e;
+    GG_CATCH
+}
+
+int ggdmc_b200_engine_iterate(ggdmc_engine_t *engine, int32_t n_iter, float *elapsed_ms, char err[256])
+{
+    GG_TRY
+    require(engine && n_iter >= 0, "bad arguments");
+    engine->iterate(n_iter, elapsed_ms, nullptr, nullptr, 0);
+    GG_CATCH
+}
+
+int ggdmc_b200_engine_iterate_flushed(ggdmc_engine_t *engine, int32_t n_iter, int64_t flush_bytes, float *elapsed_ms, char err[256])
+{
+    GG_TRY
+    require(engine && n_iter >= 0 && flush_bytes > 0, "bad arguments");
+    engine->iterate_flushed(n_iter, (size_t)flush_bytes, elapsed_ms);
+    GG_CATCH
+}
+
+int ggdmc_b200_engine_time_likelihood(ggdmc_engine_t *engine, int32_t reps, float *elapsed_ms, int64_t *n_trial_lik, char err[256])
+{
+    GG_TRY
+    require(engine && reps >= 1 && engine->kind != 1, "bad arguments");
+    ggdmc_engine &e = *engine;
+    CUDA_CHECK(cudaSetDevice(e.device));
+    // proposals for every chain (crossover sweep), then the likelihood kernel alone, `reps` times
+    Level &L = e.subj.L;
+    const double saved = L.mig_prob;
+    L.mig_prob = 0.0;
+    k_sweep_begin<<<L.npop, 128, (size_t)2 * e.C * sizeof(int), e.stream>>>(L, e.d_iter.p, 0, 1, -1);
+    k_propose<kProposeWarps><<<L.npop, kProposeWarps * 32, (size_t)kProposeWarps * e.D * 8, e.stream>>>(L, e.d_iter.p, 0, -1);
+    L.mig_prob = saved;
+    launch_like(L, e.model.d, e.trials.d, e.d_iter.p, 0, -1, e.ll_part.p, e.stream); // warm-up
+    CUDA_CHECK(cudaEventRecord(e.ev0, e.stream));
+    for (int i = 0; i < reps; ++i) launch_like(L, e.model.d, e.trials.d, e.d_iter.p, 0, -1, e.ll_part.p, e.stream);
+    CUDA_CHECK(cudaEventRecord(e.ev1, e.stream));
+    CUDA_CHECK(cudaStreamSynchronize(e.stream));
+    e.launches += 3 + reps;
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e.ev0, e.ev1));
+    if (elapsed_ms) *elapsed_ms = ms / reps;
+    if (n_trial_lik) *n_trial_lik = (int64_t)e.R * e.C * e.trials.total;
+    GG_CATCH
+}
+
+int ggdmc_b200_engine_state(ggdmc_engine_t *engine, double *phi_theta, double *phi_lp, double *phi_ll, double *subj_theta,
+                            double *subj_lp, double *subj_ll, char err[256])
+{
+    GG_TRY
+    require(engine != nullptr, "null engine");
+    ggdmc_engine &e = *engine;
+    CUDA_CHECK(cudaSetDevice(e.device));
+    CUDA_CHECK(cudaStreamSynchronize(e.stream));
+    auto get = [&](double *dst, DBuf<double> &src) {
+        if (dst && src.n) CUDA_CHECK(cudaMemcpy(dst, src.p, src.n * 8, cudaMemcpyDeviceToHost));
+    };
+    get(phi_theta, e.phi.theta); get(phi_lp, e.phi.lp); get(phi_ll, e.phi.ll);
+    get(subj_theta, e.subj.theta); get(subj_lp, e.subj.lp); get(subj_ll, e.subj.ll);
+    GG_CATCH
+}
+
+int64_t ggdmc_b200_engine_launch_count(const ggdmc_engine_t *engine) { return engine ? engine->launches : 0; }
+
+int ggdmc_b200_engine_profile(ggdmc_engine_t *engine, int32_t enable, char err[256])
+{
+    GG_TRY
+    require(engine != nullptr, "null engine");
+    engine->profile = enable != 0;
+    GG_CATCH
+}
+
+int ggdmc_b200_engine_counters(ggdmc_engine_t *engine, int64_t *trial_lik, double *like_ms, int64_t *like_launches, char err[256])
+{
+    GG_TRY
+    require(engine != nullptr, "null engine");
+    ggdmc_engine &e = *engine;
+    CUDA_CHECK(cudaSetDevice(e.device));
+    CUDA_CHECK(cudaStreamSynchronize(e.stream));
+    unsigned long long n = 0;
+    if (e.trials.counter.p) {
+        CUDA_CHECK(cudaMemcpy(&n, e.trials.counter.p, sizeof(n), cudaMemcpyDeviceToHost));
+        e.trials.counter.zero();
+    }
+    if (trial_lik) *trial_lik = (int64_t)n;
+    if (like_ms) *like_ms = e.like_ms;
+    if (like_launches) *like_launches = e.like_launches;
+    e.like_ms = 0.0;
+    e.like_launches = 0;
+    GG_CATCH
+}
+
+void ggdmc_b200_engine_destroy(ggdmc_engine_t *engine)
+{
+    if (!engine) return;
+    cudaSetDevice(engine->device);
+    delete engine;
+}
+
+int ggdmc_b200_run_subject(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const ggdmc_prior_t *p_prior,
+                           const ggdmc_config_t *cfg, const ggdmc_start_t *start, ggdmc_samples_t *out,
+                           ggdmc_progress_fn progress, void *user, char err[256])
+{
+    GG_TRY
+    require(model && trials && p_prior && cfg && start && out, "null argument");
+    require(trials->n_subject == 1, "run_subject takes exactly one subject");
+    ggdmc_engine e;
+    e.create_lba(model, trials, p_prior, nullptr, cfg, nullptr, start);
+    e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length); // m_nsample - 1 iterations
+    e.download_level(e.subj, 1, out);
+    GG_CATCH
+}
+
+int ggdmc_b200_run_hyper(const ggdmc_prior_t *p_prior, const ggdmc_prior_t *h_prior, const double *data_theta, int32_t n_subject,
+                         const ggdmc_config_t *cfg, const ggdmc_start_t *start, ggdmc_samples_t *out,
+                         ggdmc_progress_fn progress, void *user, char err[256])
+{
+    GG_TRY
+    require(cfg && start && out, "null argument");
+    ggdmc_engine e;
+    e.create_hyper(p_prior, h_prior, data_theta, n_subject, cfg, start);
+    e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length);
+    e.download_level(e.phi, 1, out);
+    GG_CATCH
+}
+
+int ggdmc_b200_run(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const ggdmc_prior_t *p_prior,
+                   const ggdmc_prior_t *h_prior, const ggdmc_config_t *cfg, const ggdmc_start_t *phi_start,
+                   const ggdmc_start_t *subj_start, ggdmc_samples_t *phi_out, ggdmc_samples_t *subj_out,
+                   ggdmc_progress_fn progress, void *user, char err[256])
+{
+    GG_TRY
+    require(model && trials && p_prior && h_prior && cfg && phi_start && subj_start && phi_out && subj_out, "null argument");
+    ggdmc_engine e;
+    e.create_lba(model, trials, p_prior, h_prior, cfg, phi_start, subj_start);
+    e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length);
+    e.download_level(e.subj, e.S, subj_out);
+    e.download_level(e.phi, 1, phi_out);
+    GG_CATCH
+}
+
+int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta, int32_t n_theta,
+                             double *out, char err[256])
+{
+    GG_TRY
+    require(model && trials && theta && out && n_theta >= 1, "bad arguments");
+    require(trials->n_subject == 1, "trial_logdens takes exactly one subject");
+    pick_device(-1);
+    ModelDev M;
+    M.upload(model);
+    TrialsDev T;
+    T.upload(trials, model->n_cell, true);
+    const int ntr = T.h_count[0];
+    DBuf<double> d_theta, d_out;
+    d_theta.upload(theta, (size_t)n_theta * model->npar);
+    d_out.alloc((size_t)n_theta * std::max(ntr, 1));
+    const size_t sm = ((size_t)M.d.n_cell * M.d.n_acc * sizeof(CellAcc) + (size_t)model->npar * 8 + (size_t)M.d.n_cell * M.d.n_acc + 15) & ~(size_t)15;
+    allow_smem(k_trial_logdens<128>, sm);
+    if (ntr > 0) {
+        dim3 grid(n_theta, std::min(64, (ntr + 127) / 128));
+        k_trial_logdens<128><<<grid, 128, sm>>>(M.d, T.rt.p, T.cell.p, ntr, d_theta.p, d_out.p);
+        CUDA_CHECK(cudaGetLastError());
+        std::vector<double> h((size_t)n_theta * ntr);
+        CUDA_CHECK(cudaMemcpy(h.data(), d_out.p, h.size() * 8, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < n_theta; ++k)
+            for (int i = 0; i < ntr; ++i) out[(size_t)k * ntr + T.order[0][i]] = h[(size_t)k * ntr + i];
+    }
+    GG_CATCH
+}
+
+int ggdmc_b200_sumloglike(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta, int32_t n_theta,
+                          double *out, char err[256])
+{
+    GG_TRY
+    require(model && trials && theta && out && n_theta >= 1, "bad arguments");
+    pick_device(-1);
+    ModelDev M;
+    M.upload(model);
+    TrialsDev T;
+    T.upload(trials, model->n_cell, false);
+    const int S = T.S, D = model->npar;
+    T.set_chunking((int64_t)S * n_theta);
+    DBuf<double> d_theta, d_part;
+    DBuf<int> d_target, d_mode;
+    DBuf<uint64_t> d_seed;
+    DBuf<uint32_t> d_iter;
+    const size_t n = (size_t)S * n_theta;
+    d_theta.upload(theta, n * D);
+    d_part.alloc(n * T.d.nsplit);
+    d_target.alloc(n); d_target.zero();
+    d_mode.alloc(S); d_mode.zero();
+    uint64_t z64 = 0; uint32_t z32 = 0;
+    d_seed.upload(&z64, 1); d_iter.upload(&z32, 1);
+    Level L{};
+    L.npop = S; L.nchain = n_theta; L.npar = D; L.pops_per_rep = S; L.prop = d_theta.p; L.target = d_target.p;
+    L.mode = d_mode.p; L.seed = d_seed.p;
+    launch_like(L, M.d, T.d, d_iter.p, 0, -1, d_part.p, 0);
+    std::vector<double> h(n * T.d.nsplit);
+    CUDA_CHECK(cudaMemcpy(h.data(), d_part.p, h.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) {
+        double v = 0.0;
+        for (int k = 0; k < T.d.nsplit; ++k) v += h[i * T.d.nsplit + k];
+        out[i] = v;
+    }
+    GG_CATCH
+}
+
+int ggdmc_b200_sumlogprior(const ggdmc_prior_t *prior, const double *x, const double *p0, const double *p1, int32_t n, double *out,
+                           char err[256])
+{
+    GG_TRY
+    require(prior && x && out && n >= 1, "bad arguments");
+    pick_device(-1);
+    PriorDev P;
+    P.upload(prior);
+    DBuf<double> dx, d0, d1, dout;
+    const size_t m = (size_t)n * prior->npar;
+    dx.upload(x, m);
+    if (p0) d0.upload(p0, m);
+    if (p1) d1.upload(p1, m);
+    dout.alloc(n);
+    k_sumlogprior<<<(n + 127) / 128, 128>>>(P.d, dx.p, d0.p, d1.p, n, dout.p);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpy(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    GG_CATCH
+}
+
+int ggdmc_b200_select_chains(int32_t nchain, int32_t n, const int32_t *k, const double *u_partner, int32_t *out_partner,
+                             const double *u_mig, int32_t *out_mig, int32_t *out_nmig, char err[256])
+{
+    GG_TRY
+    require(nchain >= 3 && n >= 1, "bad arguments");
+    require(!u_partner || (k && out_partner), "partner selection needs k and out_partner");
+    require(!u_mig || (out_mig && out_nmig), "migration selection needs out_mig and out_nmig");
+    pick_device(-1);
+    DBuf<int> dk, dop, dom, don;
+    DBuf<double> dup, dum;
+    if (u_partner) { dk.upload(k, n); dup.upload(u_partner, (size_t)n * (nchain - 1)); dop.alloc((size_t)2 * n); }
+    if (u_mig) { dum.upload(u_mig, (size_t)n * (nchain + 1)); dom.alloc((size_t)n * nchain); don.alloc(n); }
+    k_select_chains<<<(n + 63) / 64, 64>>>(nchain, n, dk.p, dup.p, dop.p, dum.p, dom.p, don.p);
+    CUDA_CHECK(cudaGetLastError());
+    if (u_partner) CUDA_CHECK(cudaMemcpy(out_partner, dop.p, (size_t)2 * n * 4, cudaMemcpyDeviceToHost));
+    if (u_mig) {
+        CUDA_CHECK(cudaMemcpy(out_mig, dom.p, (size_t)n * nchain * 4, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(out_nmig, don.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+    GG_CATCH
+}
+
+void ggdmc_b200_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    out[0] = out[1] = out[2] = out[3] = 0;
+    uint32_t *d = nullptr;
+    if (cudaMalloc(&d, 10 * sizeof(uint32_t)) != cudaSuccess) return;
+    cudaMemcpy(d, ctr, 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + 4, key, 8, cudaMemcpyHostToDevice);
+    k_philox<<<1, 1>>>(d, d + 4, d + 6);
+    cudaMemcpy(out, d + 6, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+}
+
+double ggdmc_b200_measure_fp64_tflops(int32_t device, char err[256])
+{
+    try {
+        pick_device(device);
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device < 0 ? 0 : device));
+        const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+        DBuf<double> out;
+        out.alloc((size_t)blocks * threads);
+        cudaEvent_t a, b;
+        CUDA_CHECK(cudaEventCreate(&a));
+        CUDA_CHECK(cudaEventCreate(&b));
+        k_dfma_peak<<<blocks, threads>>>(out.p, 1000, 0.999999, 1e-9);
+        double best = 0.0;
+        for (int rep = 0; rep < 5; ++rep) {
+            CUDA_CHECK(cudaEventRecord(a));
+            k_dfma_peak<<<blocks, threads>>>(out.p, iters, 0.999999, 1e-9);
+            CUDA_CHECK(cudaEventRecord(b));
+            CUDA_CHECK(cudaEventSynchronize(b));
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+            double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+            best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        return best;
+    } catch (const std::exception &e) {
+        fail(err, e, 0);
+        return -1.0;
+    }
+}
+
+int ggdmc_b200_comm_unique_id(uint8_t id[128], char err[256])
+{
+    GG_TRY
+    g_nccl.load();
+    Nccl::UniqueId u;
+    g_nccl.check(g_nccl.GetUniqueId(&u), "ncclGetUniqueId");
+    std::memcpy(id, u.internal, 128);
+    GG_CATCH
+}
+
+int ggdmc_b200_comm_init(int32_t n_rank, int32_t rank, const uint8_t id[128], int32_t device, char err[256])
+{
+    GG_TRY
+    require(n_rank >= 1 && rank >= 0 && rank < n_rank, "bad rank");
+    pick_device(device);
+    if (n_rank == 1) { g_nccl.n_rank = 1; g_nccl.rank = 0; return GGDMC_OK; }
+    g_nccl.load();
+    Nccl::UniqueId u;
+    std::memcpy(u.internal, id, 128);
+    g_nccl.check(g_nccl.CommInitRank(&g_nccl.comm, n_rank, u, rank), "ncclCommInitRank");
+    g_nccl.n_rank = n_rank;
+    g_nccl.rank = rank;
+    GG_CATCH
+}
+
+void ggdmc_b200_comm_finalize(void)
+{
+    if (g_nccl.comm) {
+        g_nccl.CommDestroy(g_nccl.comm);
+        g_nccl.comm = nullptr;
+    }
+    g_nccl.n_rank = 1;
+    g_nccl.rank = 0;
+}
+
+} // extern "C"

@@ -1,0 +1,716 @@
+// ggdmc_b200 -- CUDA kernels of the DE-MCMC step (sm_100a).
+//
+//   K0 k_sweep_begin  : per population, migration-vs-crossover decision and the migration set
+//                       (src/de.cpp:210, 296, 310, 348, 362 and get_subchains :62-78)
+//   K1 k_propose      : crossover / migration proposals + their log prior
+//                       (src/de.cpp:119-141, 164-184, 394-426, 488-518, 575-603, 627-652)
+//   K2 k_like         : LBA sum-log-likelihood of every proposal (the FP64 hot kernel)
+//                       (@hdr/likelihood.h:73-108, 272-292 + @hdr/lba.h)
+//   K3 k_accept       : Metropolis accept / commit (src/de.cpp:81-108)
+//   K4 k_hyper        : phi-level hyper-likelihood partial sums over the local subjects
+//                       (src/de.cpp:245-270), k_hyper_reduce, k_phi_accept (:397-400, 427-463,
+//                       494-500, 519-549)
+//      k_store        : thinned sample storage (@hdr/theta.h:61-74)
+//
+// A "population" is one set of nchain chains: a (replicate, subject) pair at the subject level,
+// a replicate at the phi level.  `step < 0` processes every chain of the sweep at once from the
+// sweep-start state (PARALLEL schedule); `step >= 0` processes only sweep position `step`
+// (REFERENCE schedule: the host walks step = 0 .. nchain-1 so chains are updated in place, one
+// after another, exactly like the reference's loops).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gg_lba.cuh"
+#include "gg_rng.cuh"
+
+namespace gg {
+
+struct DevModel {
+    int n_acc, n_cell, npar, n_const;
+    const int *param_src;
+    const double *const_val;
+    const uint8_t *posdrift;
+};
+
+struct DevPrior {
+    int npar;
+    const double *p0, *p1, *lower, *upper;
+    const int *dist;
+    const uint8_t *log_p;
+};
+
+// One level (subject or phi) of the sampler.
+struct Level {
+    int npop;        // populations on this device at this level
+    int nchain;      // C
+    int npar;        // length of one chain's vector
+    int nmove;       // leading parameters perturbed by an unblocked sweep (src/de.cpp:592: half at the subject level of a hierarchy)
+    int pops_per_rep; // populations per replicate (S at the subject level, 1 at the phi level)
+    int pop_id_base;  // global id of local population 0 within a replicate (subject_begin), phi: unused
+    int is_phi;       // population id is kPopPhi
+    double gamma, rp, mig_prob;
+    // state
+    double *theta, *lp, *ll;          // [npop][C][npar], [npop][C]
+    double *prop, *prop_lp;           // proposals
+    int *target;                      // [npop][C] chain compared against / overwritten by the proposal of this chain, -1 = none
+    int *mode;                        // [npop] 0 crossover, 1 migration
+    int *mig_n;                       // [npop]
+    int *mig_list;                    // [npop][C] sorted migration set
+    int *para;                        // [npop] parameter moved by this sweep, -1 = all (blocked sweeps)
+    int *mode0;                       // [npop] decision of sweep 0 (run_chains draws once per iteration, src/de.cpp:210)
+    const uint64_t *seed;             // [n_replicate]
+    // prior of the moved vector
+    DevPrior prior;
+    const double *prior_ovr;          // phi state [n_rep][C][2*npar] when the prior's p0/p1 come from phi chain (src/de.cpp:599-600), else null
+    // storage
+    double *out_theta, *out_lp, *out_ll; // [npop][nmc][C][npar], [npop][nmc][C]
+    int nmc, thin;
+};
+
+__device__ __forceinline__ uint32_t pop_global_id(const Level &L, int p)
+{
+    return L.is_phi ? kPopPhi : (uint32_t)(L.pop_id_base + (p % L.pops_per_rep));
+}
+
+__device__ __forceinline__ DrawAddr make_addr(const Level &L, int p, uint32_t iter, int sweep, int chain)
+{
+    DrawAddr a;
+    a.seed = L.seed[p / L.pops_per_rep];
+    a.pop = pop_global_id(L, p);
+    a.iter = iter;
+    a.sweep = sweep < 0 ? 0u : (uint32_t)sweep;
+    a.chain = (uint32_t)chain;
+    return a;
+}
+
+// nmath runif(a, b) with the uniform already drawn (a == b handled by the callers' formulas:
+// -rp + 2 rp u == -0 + 0 when rp == 0)
+__device__ __forceinline__ double runif_from(double lo, double hi, double u)
+{
+    return __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide sum of one double per thread (warp shuffles, then one shared-memory pass)
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK>
+__device__ __forceinline__ double block_sum(double v, double *scratch /* [BLOCK/32] */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = (lane < BLOCK / 32) ? scratch[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    return r; // valid in thread 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: sweep prologue
+// ------------------------------------------------------------------------------------------------
+// decide_once = 0: a fresh migration/crossover draw for every sweep (run_hchains, src/de.cpp:283-319,
+//                  :345-371); para_idx is the host's blocked-parameter index (-1 = all).
+// decide_once = 1: run_chains (src/de.cpp:201-242): ONE draw per iteration (made in sweep 0); a
+//                  migration is a single unblocked sweep, so migrating populations idle (mode 2)
+//                  in the remaining blocked sweeps.
+__global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int decide_once, int para_idx)
+{
+    extern __shared__ int sm_keys[]; // keys [C], ranks [C]
+    const int p = blockIdx.x, C = L.nchain, tid = threadIdx.x;
+    const uint32_t iter = *d_iter;
+    __shared__ int s_mode, s_n;
+    DrawAddr a = make_addr(L, p, iter, decide_once ? 0 : sweep, 0);
+    if (tid == 0) {
+        int mode;
+        if (decide_once && sweep > 0) {
+            mode = L.mode0[p] ? 2 : 0;
+        } else {
+            double u = draw_uniform(a, U_DECIDE, 0);
+            mode = (u < L.mig_prob) ? 1 : 0;
+            L.mode0[p] = mode;
+        }
+        s_mode = mode;
+        L.mode[p] = mode;
+        L.para[p] = (decide_once && mode == 1) ? -1 : para_idx;
+        if (mode == 1) { // get_subchains, src/de.cpp:64-70
+            double prop = draw_uniform(a, U_MIG_N, 0);
+            unsigned n = (unsigned)ceil((double)C * prop);
+            n = n < 2u ? 2u : n;
+            n = n > (unsigned)C ? (unsigned)C : n;
+            s_n = (int)n;
+            L.mig_n[p] = (int)n;
+        } else if (mode == 2) {
+            L.mig_n[p] = 0;
+        }
+    }
+    for (int c = tid; c < C; c += blockDim.x) L.target[p * C + c] = -1;
+    __syncthreads();
+    if (s_mode != 1) return;
+    // arma::shuffle keys for all chains, then the n smallest keys (ties by position), sorted by index
+    for (int blk = tid; blk * 4 < C; blk += blockDim.x) {
+        U4 w = draw_block(a, U_MIG_KEYS, (uint32_t)blk);
+        int j = blk * 4;
+        sm_keys[j] = shuffle_key(word_to_uniform(w.x));
+        if (j + 1 < C) sm_keys[j + 1] = shuffle_key(word_to_uniform(w.y));
+        if (j + 2 < C) sm_keys[j + 2] = shuffle_key(word_to_uniform(w.z));
+        if (j + 3 < C) sm_keys[j + 3] = shuffle_key(word_to_uniform(w.w));
+    }
+    __syncthreads();
+    const int n = s_n;
+    int *sm_rank = sm_keys + C;
+    for (int j = tid; j < C; j += blockDim.x) {
+        const int kj = sm_keys[j];
+        int rank = 0;
+        for (int k = 0; k < C; ++k) {
+            const int kk = sm_keys[k];
+            rank += (kk < kj) || (kk == kj && k < j);
+        }
+        sm_rank[j] = rank;
+    }
+    __syncthreads();
+    for (int j = tid; j < C; j += blockDim.x) {
+        if (sm_rank[j] < n) { // selected: position among the selected chains in ascending index order
+            int pos = 0;
+            for (int k = 0; k < j; ++k) pos += sm_rank[k] < n;
+            L.mig_list[p * C + pos] = j;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: proposals + log prior of the proposal.  One block per population, one warp per chain.
+// ------------------------------------------------------------------------------------------------
+
+// lexicographic (key, pos) minimum across the warp
+__device__ __forceinline__ void warp_min_keypos(int &key, int &pos)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int k2 = __shfl_xor_sync(0xffffffffu, key, o);
+        int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
+        if (k2 < key || (k2 == key && p2 < pos)) { key = k2; pos = p2; }
+    }
+}
+
+// get_chains(i, 2), src/de.cpp:54-60: the two smallest shuffle keys among the other chains
+__device__ __forceinline__ void pick_partners(const DrawAddr &a, int C, int i, int lane, int &c0, int &c1)
+{
+    const int nother = C - 1;
+    const int INTMAX = 0x7fffffff;
+    int k1 = INTMAX, p1 = INTMAX, k2 = INTMAX, p2 = INTMAX; // lane-local best two
+    for (int blk = lane; blk * 4 < nother; blk += 32) {
+        U4 w = draw_block(a, U_PARTNER, (uint32_t)blk);
+        uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int j = blk * 4 + q;
+            if (j < nother) {
+                int k = shuffle_key(word_to_uniform(ws[q]));
+                if (k < k1 || (k == k1 && j < p1)) { k2 = k1; p2 = p1; k1 = k; p1 = j; }
+                else if (k < k2 || (k == k2 && j < p2)) { k2 = k; p2 = j; }
+            }
+        }
+    }
+    int bk = k1, bp = p1;
+    warp_min_keypos(bk, bp);
+    // second: each lane offers its best candidate that is not the global minimum
+    int sk = (k1 == bk && p1 == bp) ? k2 : k1;
+    int sp = (k1 == bk && p1 == bp) ? p2 : p1;
+    warp_min_keypos(sk, sp);
+    c0 = bp + (bp >= i);
+    c1 = sp + (sp >= i);
+}
+
+// prior_class::sumlogprior with arma::accu's two-accumulator order (@hdr/prior.h:469-476)
+__device__ __forceinline__ double sum_arma_order(const double *v, int n)
+{
+    double a1 = 0.0, a2 = 0.0;
+    int i = 0;
+    for (; i + 1 < n; i += 2) { a1 += v[i]; a2 += v[i + 1]; }
+    if (i < n) a1 += v[i];
+    return a1 + a2;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t *d_iter, int sweep, int step)
+{
+    extern __shared__ double sm_prop[]; // [WARPS][npar] prior terms scratch
+    const int p = blockIdx.x, C = L.nchain, D = L.npar;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t iter = *d_iter;
+    const int mode = L.mode[p];
+    const int para_idx = L.para[p];
+    const int nsteps = mode ? L.mig_n[p] : C;
+    double *scratch = sm_prop + w * D;
+    const int k_begin = step < 0 ? w : step, k_end = step < 0 ? nsteps : (step < nsteps ? step + 1 : 0);
+    const int k_stride = step < 0 ? WARPS : 1;
+    if (step >= 0 && w != 0) return;
+    for (int k = k_begin; k < k_end; k += k_stride) {
+        int src, tgt, c0 = 0, c1 = 0;
+        if (mode) {
+            src = L.mig_list[p * C + k];
+            tgt = L.mig_list[p * C + ((k + 1 == nsteps) ? 0 : k + 1)];
+        } else {
+            src = k;
+            tgt = k;
+        }
+        DrawAddr a = make_addr(L, p, iter, sweep, src);
+        if (!mode) pick_partners(a, C, src, lane, c0, c1);
+        const double *th = L.theta + ((size_t)p * C + src) * D;
+        const double *t0 = L.theta + ((size_t)p * C + c0) * D;
+        const double *t1 = L.theta + ((size_t)p * C + c1) * D;
+        double *pr = L.prop + ((size_t)p * C + src) * D;
+        const double *ovr = L.prior_ovr ? L.prior_ovr + ((size_t)(p / L.pops_per_rep) * C + src) * 2 * D : nullptr;
+        for (int d = lane; d < D; d += 32) {
+            double x = th[d];
+            const bool moved = para_idx >= 0 ? (d == para_idx) : (d < L.nmove);
+            if (moved) {
+                double u = draw_uniform(a, U_NOISE, (uint32_t)d);
+                double noise = runif_from(-L.rp, L.rp, u);
+                double inc = mode ? noise : __dadd_rn(noise, __dmul_rn(L.gamma, __dsub_rn(t0[d], t1[d])));
+                x = __dadd_rn(x, inc);
+            }
+            pr[d] = x;
+            const double q0 = ovr ? ovr[d] : L.prior.p0[d], q1 = ovr ? ovr[D + d] : L.prior.p1[d];
+            scratch[d] = dprior1(L.prior.dist[d], x, q0, q1, L.prior.lower[d], L.prior.upper[d], L.prior.log_p[d] != 0);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            L.prop_lp[p * C + src] = sum_arma_order(scratch, D);
+            L.target[p * C + src] = tgt;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: LBA sum-log-likelihood
+// ------------------------------------------------------------------------------------------------
+struct TrialData {
+    const double *rt;        // [ntot_padded] grouped by cell within subject
+    const uint16_t *cell;    // [ntot_padded]; 0xFFFF = padding
+    const int64_t *offset;   // [S] start of each subject (multiple of 8)
+    const int *count;        // [S] trials of each subject
+    int chunk;               // trials per block (multiple of 8)
+    int nsplit;              // blocks per (population, chain)
+    unsigned long long *counter; // trial-likelihoods evaluated so far (one atomicAdd per block)
+};
+
+constexpr double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
+
+// running product of densities as (mantissa in [1,2), exponent) -- replaces one log() per trial
+// (@hdr/likelihood.h:284-288 sums log(density) trial by trial) by one multiply + integer work.
+struct LogProd {
+    double m;
+    int e;
+    double extra; // log of factors that are 0, subnormal, inf or NaN (rare)
+    __device__ __forceinline__ void init() { m = 1.0; e = 0; extra = 0.0; }
+    __device__ __forceinline__ void mul(double x)
+    {
+        long long b = __double_as_longlong(x);
+        int ex = (int)((b >> 52) & 0x7ff);
+        if ((unsigned)(ex - 1) < 0x7feu && b > 0) {
+            m *= __longlong_as_double((b & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll);
+            long long mb = __double_as_longlong(m);
+            e += ex - 1023 + (int)((mb >> 52) & 0x7ff) - 1023;
+            m = __longlong_as_double((mb & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll);
+        } else {
+            extra += log(x);
+        }
+    }
+    __device__ __forceinline__ double value() const { return fma((double)e, kLn2Hi, fma((double)e, kLn2Lo, log(m))) + extra; }
+};
+
+// Builds the (cell, accumulator) table of one parameter vector in shared memory.
+template <int BLOCK>
+__device__ __forceinline__ void build_cell_table(const DevModel &M, const double *theta_s, CellAcc *ent, uint8_t *bad,
+                                                 const DrawAddr &addr)
+{
+    const int n = M.n_cell * M.n_acc, na = M.n_acc;
+    for (int k = threadIdx.x; k < n; k += BLOCK) {
+        const int c = k / na, j = k - c * na;
+        const int *src = M.param_src + (size_t)c * 6 * na + j;
+        double v[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            int s = src[r * na];
+            v[r] = s >= 0 ? theta_s[s] : M.const_val[-1 - s];
+        }
+        double u = 0.0;
+        if (v[4] != 0.0) u = draw_uniform(addr, U_ST0, (uint32_t)k);
+        bad[k] = cellacc_build(ent[k], v[0], v[1], v[2], v[3], v[4], v[5], M.posdrift[j] != 0, u) ? 1 : 0;
+    }
+    __syncthreads();
+    // a cell is invalid when any of its accumulators is (@hdr/lba.h:121-146); fold into bad[c*na]
+    for (int c = threadIdx.x; c < M.n_cell; c += BLOCK) {
+        uint8_t b = 0;
+        for (int j = 0; j < na; ++j) b |= bad[c * na + j];
+        bad[c * na] = b;
+    }
+    __syncthreads();
+}
+
+template <int NACC, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_like(Level L, DevModel M, TrialData T, const uint32_t *d_iter, int sweep, int step,
+                                                double *ll_part /* [npop][C][nsplit] */)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int C = L.nchain, D = L.npar, na = M.n_acc;
+    int p, chain;
+    if (step < 0) {
+        p = blockIdx.x / C;
+        chain = blockIdx.x - p * C;
+    } else {
+        p = blockIdx.x;
+        const int mode = L.mode[p];
+        if (mode) {
+            if (step >= L.mig_n[p]) return;
+            chain = L.mig_list[p * C + step];
+        } else
+            chain = step;
+    }
+    if (L.target[p * C + chain] < 0) return;
+    const int split = blockIdx.y;
+    const int s = p % L.pops_per_rep;
+    const int ntr = T.count[s];
+    const int t_begin = split * T.chunk;
+    double *part = ll_part + ((size_t)p * C + chain) * T.nsplit + split;
+    if (t_begin >= ntr) {
+        if (threadIdx.x == 0) *part = 0.0;
+        return;
+    }
+    CellAcc *ent = reinterpret_cast<CellAcc *>(sm_raw);
+    double *theta_s = reinterpret_cast<double *>(ent + M.n_cell * na);
+    double *red = theta_s + D;
+    uint8_t *bad = reinterpret_cast<uint8_t *>(red + BLOCK / 32);
+    const double *th = L.prop + ((size_t)p * C + chain) * D;
+    for (int d = threadIdx.x; d < D; d += BLOCK) theta_s[d] = th[d];
+    __syncthreads();
+    DrawAddr addr = make_addr(L, p, *d_iter, sweep, chain);
+    build_cell_table<BLOCK>(M, theta_s, ent, bad, addr);
+
+    const int t_end = min(ntr, t_begin + T.chunk);
+    const double *rt = T.rt + T.offset[s];
+    const uint16_t *cl = T.cell + T.offset[s];
+    LogProd acc;
+    acc.init();
+    // two trials per thread per pass: one 16-byte RT load + one 4-byte cell load (subjects are padded
+    // to a multiple of 8 trials with cell = 0xFFFF)
+    for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
+        const double2 r2 = __ldg(reinterpret_cast<const double2 *>(rt + t));
+        const ushort2 c2 = __ldg(reinterpret_cast<const ushort2 *>(cl + t));
+        {
+            const int c = c2.x;
+            double pdf = bad[c * na] ? kFloor : n1pdf<NACC>(r2.x, ent + c * na, na);
+            acc.mul(pdf);
+        }
+        if (t + 1 < t_end) {
+            const int c = c2.y;
+            double pdf = bad[c * na] ? kFloor : n1pdf<NACC>(r2.y, ent + c * na, na);
+            acc.mul(pdf);
+        }
+    }
+    double v = block_sum<BLOCK>(acc.value(), red);
+    if (threadIdx.x == 0) {
+        *part = v;
+        if (T.counter) atomicAdd(T.counter, (unsigned long long)(t_end - t_begin));
+    }
+}
+
+// per-trial log densities of one subject for n_theta parameter vectors (parity / init entry point)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_trial_logdens(DevModel M, const double *rt, const uint16_t *cl, int ntr,
+                                                         const double *theta, double *out)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int na = M.n_acc, D = M.npar, k = blockIdx.x;
+    CellAcc *ent = reinterpret_cast<CellAcc *>(sm_raw);
+    double *theta_s = reinterpret_cast<double *>(ent + M.n_cell * na);
+    uint8_t *bad = reinterpret_cast<uint8_t *>(theta_s + D);
+    for (int d = threadIdx.x; d < D; d += BLOCK) theta_s[d] = theta[(size_t)k * D + d];
+    __syncthreads();
+    DrawAddr addr = {0, 0, 0, 0, 0};
+    build_cell_table<BLOCK>(M, theta_s, ent, bad, addr);
+    for (int t = blockIdx.y * BLOCK + threadIdx.x; t < ntr; t += gridDim.y * BLOCK) {
+        const int c = cl[t];
+        double pdf = bad[c * na] ? kFloor : n1pdf<0>(rt[t], ent + c * na, na);
+        out[(size_t)k * ntr + t] = log(pdf);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: Metropolis accept / commit at the subject level (update_theta, src/de.cpp:81-108)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *ll_part, int nsplit)
+{
+    const int C = L.nchain, D = L.npar;
+    int p, src;
+    if (step < 0) {
+        int g = blockIdx.x * blockDim.x + threadIdx.x;
+        if (g >= L.npop * C) return;
+        p = g / C;
+        src = g - p * C;
+    } else {
+        p = blockIdx.x * blockDim.x + threadIdx.x;
+        if (p >= L.npop) return;
+        const int mode = L.mode[p];
+        if (mode) {
+            if (step >= L.mig_n[p]) return;
+            src = L.mig_list[p * C + step];
+        } else
+            src = step;
+    }
+    const int tgt = L.target[p * C + src];
+    if (tgt < 0) return;
+    double tmp_ll = 0.0;
+    const double *part = ll_part + ((size_t)p * C + src) * nsplit;
+    for (int k = 0; k < nsplit; ++k) tmp_ll += part[k];
+    const double tmp_lp = L.prop_lp[p * C + src];
+    const double cur = L.lp[p * C + tgt] + L.ll[p * C + tgt];     // src/de.cpp:121 / :189-190 / :577 / :656-657
+    const double mh = exp((tmp_lp + tmp_ll) - cur);               // :147
+    if (isnan(mh)) return;                                         // :83-87, no draw
+    DrawAddr a = make_addr(L, p, *d_iter, sweep, src);
+    if (draw_uniform(a, U_ACCEPT, 0) < mh) {                       // :88
+        const double *pr = L.prop + ((size_t)p * C + src) * D;
+        double *th = L.theta + ((size_t)p * C + tgt) * D;
+        for (int d = 0; d < D; ++d) th[d] = pr[d];
+        L.lp[p * C + tgt] = tmp_lp;
+        L.ll[p * C + tgt] = tmp_ll;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: hyper-likelihood partial sums.  Block (population r, chain c, subject split).
+//   sums[..][0] = sum_s log p(x_s | phi_c)   (current phi of chain c; src/de.cpp:397-398, 494-500)
+//   sums[..][1] = sum_s log p(x_s | phi'_c)  (proposal made FROM chain c; :427, :519-520)
+// x_s = theta of subject s, chain c (hierarchy) or row s of the data matrix (run_hyper,
+// @hdr/likelihood.h:257-271).
+// ------------------------------------------------------------------------------------------------
+struct HyperArgs {
+    DevPrior like;            // p_prior: lower/upper/dist/log_p of the subject-level parameters
+    const double *x;          // subject thetas [n_rep][S][C][D] or data [S][D]
+    int x_rep_stride, x_subj_stride, x_chain_stride; // in doubles
+    int S;                    // local subjects
+    int D;                    // subject-level npar (phi vector is 2 D)
+    int subj_per_block, nsplit;
+    int need_cur;             // refresh current hyper-likelihood (hierarchy) or not (run_hyper)
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_hyper(Level L, HyperArgs H, int step, double *hpart /* [npop][C][2][nsplit] */)
+{
+    extern __shared__ double sm_h[]; // cur: mean[D] sd[D] logden[D]; prop: same; then reduction scratch
+    const int C = L.nchain, D = H.D;
+    int r, c;
+    if (step < 0) {
+        r = blockIdx.x / C;
+        c = blockIdx.x - r * C;
+    } else {
+        r = blockIdx.x;
+        const int mode = L.mode[r];
+        if (mode) { // in-place migration step: both the source chain (z = 0) and the chain it is compared with (z = 1)
+            const int n = L.mig_n[r];
+            if (step >= n) return;
+            c = blockIdx.z == 0 ? L.mig_list[r * C + step] : L.mig_list[r * C + ((step + 1 == n) ? 0 : step + 1)];
+        } else {
+            if (blockIdx.z != 0) return;
+            c = step;
+        }
+    }
+    const int split = blockIdx.y;
+    const bool has_prop = L.target[r * C + c] >= 0;
+    double *cm = sm_h, *cs = cm + D, *cl = cs + D, *pm = cl + D, *ps = pm + D, *pl = ps + D, *red = pl + D;
+    const double *phi_c = L.theta + ((size_t)r * C + c) * 2 * D;
+    const double *phi_p = L.prop + ((size_t)r * C + c) * 2 * D;
+    for (int d = threadIdx.x; d < D; d += BLOCK) {
+        const double lo = H.like.lower[d], up = H.like.upper[d];
+        double m = phi_c[d], s = phi_c[D + d];
+        cm[d] = m; cs[d] = s;
+        cl[d] = log(pnorm5(up, m, s, true) - pnorm5(lo, m, s, true)); // tnorm_class::set_parameters, @hdr/tnorm.h:59-67
+        m = phi_p[d]; s = phi_p[D + d];
+        pm[d] = m; ps[d] = s;
+        pl[d] = log(pnorm5(up, m, s, true) - pnorm5(lo, m, s, true));
+    }
+    __syncthreads();
+    const int s_begin = split * H.subj_per_block, s_end = min(H.S, s_begin + H.subj_per_block);
+    const int n_el = (s_end - s_begin) * D;
+    const double *xbase = H.x + (size_t)r * H.x_rep_stride + (size_t)c * H.x_chain_stride;
+    double sum_c = 0.0, sum_p = 0.0;
+    for (int e = threadIdx.x; e < n_el; e += BLOCK) {
+        const int si = e / D, d = e - si * D;
+        const double x = xbase[(size_t)(s_begin + si) * H.x_subj_stride + d];
+        const int dist = H.like.dist[d];
+        const bool lg = H.like.log_p[d] != 0;
+        const double lo = H.like.lower[d], up = H.like.upper[d];
+        if (dist == 1 && lg) { // TNORM, log scale: the hierarchical fits of the reference
+            const bool outside = (x < lo) || (x > up);
+            if (H.need_cur) sum_c += outside ? -INFINITY : dnorm4(x, cm[d], cs[d], true) - cl[d];
+            if (has_prop) sum_p += outside ? -INFINITY : dnorm4(x, pm[d], ps[d], true) - pl[d];
+        } else {
+            if (H.need_cur) sum_c += dprior1(dist, x, cm[d], cs[d], lo, up, lg);
+            if (has_prop) sum_p += dprior1(dist, x, pm[d], ps[d], lo, up, lg);
+        }
+    }
+    double vc = block_sum<BLOCK>(sum_c, red);
+    double vp = block_sum<BLOCK>(sum_p, red);
+    if (threadIdx.x == 0) {
+        double *o = hpart + (((size_t)r * C + c) * 2) * H.nsplit + split;
+        o[0] = vc;
+        o[H.nsplit] = vp;
+    }
+}
+
+// [npop*C*2][nsplit] -> [npop*C*2]
+__global__ void k_hyper_reduce(const double *hpart, int n, int nsplit, double *hsum)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = 0.0;
+    for (int k = 0; k < nsplit; ++k) v += hpart[(size_t)i * nsplit + k];
+    hsum[i] = v;
+}
+
+// phi-level accept (src/de.cpp:397-400, 427-463 and :494-500, 519-549)
+__global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *hsum, int need_cur)
+{
+    const int C = L.nchain, D = L.npar;
+    int r, src;
+    if (step < 0) {
+        int g = blockIdx.x * blockDim.x + threadIdx.x;
+        if (g >= L.npop * C) return;
+        r = g / C;
+        src = g - r * C;
+    } else {
+        r = blockIdx.x * blockDim.x + threadIdx.x;
+        if (r >= L.npop) return;
+        const int mode = L.mode[r];
+        if (mode) {
+            if (step >= L.mig_n[r]) return;
+            src = L.mig_list[r * C + step];
+        } else
+            src = step;
+    }
+    const int tgt = L.target[r * C + src];
+    if (tgt < 0) return;
+    const double tmp_ll = hsum[((size_t)r * C + src) * 2 + 1];
+    const double tmp_lp = L.prop_lp[r * C + src];
+    double cur_ll = L.ll[r * C + tgt];
+    if (need_cur) {
+        cur_ll = hsum[((size_t)r * C + tgt) * 2 + 0];
+        if (step >= 0 && L.mode[r]) L.ll[r * C + src] = hsum[((size_t)r * C + src) * 2 + 0]; // :494-496 (in place order only)
+        L.ll[r * C + tgt] = cur_ll; // :397-398 / :498-500
+    }
+    const double cur = L.lp[r * C + tgt] + cur_ll;
+    const double mh = exp((tmp_lp + tmp_ll) - cur);
+    if (isnan(mh)) return;
+    DrawAddr a = make_addr(L, r, *d_iter, sweep, src);
+    if (draw_uniform(a, U_ACCEPT, 0) < mh) {
+        const double *pr = L.prop + ((size_t)r * C + src) * D;
+        double *th = L.theta + ((size_t)r * C + tgt) * D;
+        for (int d = 0; d < D; ++d) th[d] = pr[d];
+        L.lp[r * C + tgt] = tmp_lp;
+        L.ll[r * C + tgt] = tmp_ll;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// storage (theta_phi::store, @hdr/theta.h:61-74) and the iteration counter
+// ------------------------------------------------------------------------------------------------
+__global__ void k_store(Level L, const uint32_t *d_iter)
+{
+    const uint32_t iter = *d_iter;
+    if (iter % (uint32_t)L.thin != 0) return;
+    const uint32_t slot = iter / (uint32_t)L.thin;
+    if (slot >= (uint32_t)L.nmc) return;
+    const size_t CD = (size_t)L.nchain * L.npar, C = L.nchain;
+    const size_t total = (size_t)L.npop * CD;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i / CD, r = i - p * CD;
+        L.out_theta[(p * L.nmc + slot) * CD + r] = L.theta[i];
+        if (r < C) {
+            L.out_lp[(p * L.nmc + slot) * C + r] = L.lp[p * C + r];
+            L.out_ll[(p * L.nmc + slot) * C + r] = L.ll[p * C + r];
+        }
+    }
+}
+
+__global__ void k_iter_advance(uint32_t *d_iter) { *d_iter += 1; }
+
+// ------------------------------------------------------------------------------------------------
+// test / utility kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sumlogprior(DevPrior P, const double *x, const double *p0, const double *p1, int n, double *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int D = P.npar;
+    double a1 = 0.0, a2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+        const double q0 = p0 ? p0[(size_t)i * D + d] : P.p0[d], q1 = p1 ? p1[(size_t)i * D + d] : P.p1[d];
+        double v = dprior1(P.dist[d], x[(size_t)i * D + d], q0, q1, P.lower[d], P.upper[d], P.log_p[d] != 0);
+        if (d & 1) a2 += v; else a1 += v;
+    }
+    out[i] = a1 + a2;
+}
+
+// get_chains / get_subchains from explicit uniforms (bit-exact index-selection check)
+__global__ void k_select_chains(int C, int n, const int *k, const double *u_partner, int *out_partner, const double *u_mig,
+                                int *out_mig, int *out_nmig)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (u_partner) {
+        const double *u = u_partner + (size_t)i * (C - 1);
+        int k1 = 0x7fffffff, p1 = 0x7fffffff, k2 = 0x7fffffff, p2 = 0x7fffffff;
+        for (int j = 0; j < C - 1; ++j) {
+            int key = shuffle_key(u[j]);
+            if (key < k1 || (key == k1 && j < p1)) { k2 = k1; p2 = p1; k1 = key; p1 = j; }
+            else if (key < k2 || (key == k2 && j < p2)) { k2 = key; p2 = j; }
+        }
+        out_partner[2 * i] = p1 + (p1 >= k[i]);
+        out_partner[2 * i + 1] = p2 + (p2 >= k[i]);
+    }
+    if (u_mig) {
+        const double *u = u_mig + (size_t)i * (C + 1);
+        unsigned nn = (unsigned)ceil((double)C * u[0]);
+        nn = nn < 2u ? 2u : nn;
+        nn = nn > (unsigned)C ? (unsigned)C : nn;
+        out_nmig[i] = (int)nn;
+        int pos = 0;
+        for (int j = 0; j < C; ++j) {
+            int kj = shuffle_key(u[1 + j]), rank = 0;
+            for (int q = 0; q < C; ++q) {
+                int kq = shuffle_key(u[1 + q]);
+                rank += (kq < kj) || (kq == kj && q < j);
+            }
+            if (rank < (int)nn) out_mig[(size_t)i * C + pos++] = j;
+        }
+        for (; pos < C; ++pos) out_mig[(size_t)i * C + pos] = -1;
+    }
+}
+
+__global__ void k_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out)
+{
+    U4 c = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    U4 r = philox4x32_10(c, key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// FP64 peak: 8 independent DFMA chains per thread
+__global__ void k_dfma_peak(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+} // namespace gg

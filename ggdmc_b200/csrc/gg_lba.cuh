@@ -1,0 +1,104 @@
+// ggdmc_b200 -- LBA node-1 density (n1PDF): winner's defective PDF x survivors' (1 - CDF).
+//
+// Replaces lba_class::{set_parameters, validate_parameters, d, p, dlba} (@hdr/lba.h:88-146,
+// 213-345, 560-572) and design_class::set_parameter_values (@hdr/design_light.h:314-344).
+// The reference rebuilds a 6 x n_acc parameter matrix per cell per likelihood call and walks the
+// trials of that cell; here the per-(cell, accumulator) quantities that do not depend on the trial
+// -- the parameters themselves, max(Phi(mean_v/sd_v), 1e-10), and the reciprocals the trial loop
+// multiplies by -- are computed once per (chain, cell, accumulator) into a shared-memory table
+// (CellAcc) and every trial only gathers its cell's row.  Branch structure, floors (1e-10), the
+// clamp of the survivor CDF to [1e-10, 1] and the NaN -> 1e-10 rules are the reference's.
+#pragma once
+#include "gg_math.cuh"
+
+namespace gg {
+
+struct CellAcc {
+    double b, A, mean_v, sd_v, t0a, inv_sdv, inv_A, inv_denom;
+};
+
+// Entry (cell, column j) of the table.  P* are the raw core parameters of that column
+// (A, B, mean_v, sd_v, st0, t0); u_st0 is the uniform of `t0 + st0 * U` (@hdr/lba.h:117).
+// Returns true when this accumulator makes the cell INVALID (@hdr/lba.h:121-146).
+GG_HD bool cellacc_build(CellAcc &e, double A, double B, double mean_v, double sd_v, double st0, double t0,
+                         bool posdrift, double u_st0)
+{
+    double b = A + B; // design_light.h:336-340: row B += row A
+    double denom = posdrift ? fmax(pnorm_std(mean_v / sd_v), kFloor) : 1.0; // lba.h:112-115
+    e.b = b;
+    e.A = A;
+    e.mean_v = mean_v;
+    e.sd_v = sd_v;
+    e.t0a = (st0 != 0.0) ? t0 + st0 * u_st0 : t0 + st0 * 0.0; // lba.h:117 (t0 + 0*U == t0 + 0)
+    e.inv_sdv = 1.0 / sd_v;
+    e.inv_A = 1.0 / A;
+    e.inv_denom = 1.0 / denom;
+    return (A < 0.0) || (b < 0.0) || (b < A) || (sd_v < 0.0) || (st0 < 0.0) || (t0 < 0.0);
+}
+
+struct PhiPair { double cdf, pdf; };
+
+// Phi(z) and phi(z) of the standard normal (Rf_pnorm5(z,0,1,1,0), Rf_dnorm4(z,0,1,0)).
+GG_HD PhiPair norm_both(double z)
+{
+    PhiPair r;
+    r.cdf = pnorm_std(z);
+    r.pdf = dnorm_std(z);
+    return r;
+}
+
+// density of one trial whose cell's table row is e[0 .. n_acc)
+template <int NACC>
+GG_HD double n1pdf(double rt, const CellAcc *e, int n_acc_rt)
+{
+    const int n_acc = NACC > 0 ? NACC : n_acc_rt;
+    double t0a = e[0].t0a;
+    double dt = rt - t0a;
+    double rdt = 1.0 / dt;
+    double pdf;
+    {
+        const double b = e[0].b, A = e[0].A, mv = e[0].mean_v, sv = e[0].sd_v;
+        if (0.0 > dt) { // lba.h:217-219
+            pdf = kFloor;
+        } else if (A < kFloor) { // lba.h:221-227
+            pdf = fmax(b / (dt * dt) * dnorm4(b / dt, mv, sv, false) * e[0].inv_denom, kFloor);
+        } else { // lba.h:231-244
+            double rts = e[0].inv_sdv * rdt, tv = mv * dt;
+            PhiPair n1 = norm_both((b - tv) * rts);
+            PhiPair n2 = norm_both(((b - A) - tv) * rts);
+            double t1 = mv * (n1.cdf - n2.cdf);
+            double t2 = sv * (n2.pdf - n1.pdf);
+            pdf = fmax((t1 + t2) * (e[0].inv_A * e[0].inv_denom), kFloor);
+        }
+        if (isnan(pdf)) pdf = kFloor; // lba.h:247
+    }
+#pragma unroll
+    for (int j = 1; j < n_acc; ++j) { // p(), lba.h:286-345
+        const double b = e[j].b, A = e[j].A, mv = e[j].mean_v, sv = e[j].sd_v;
+        if (e[j].t0a != t0a) {
+            t0a = e[j].t0a;
+            dt = rt - t0a;
+            rdt = 1.0 / dt;
+        }
+        double cdf;
+        if (0.0 > dt) { // :310-312
+            cdf = kFloor;
+        } else if (A < kFloor) { // :315-320
+            cdf = pnorm5(b / dt, mv, sv, false) * e[j].inv_denom;
+            cdf = cdf < kFloor ? kFloor : (1.0 < cdf ? 1.0 : cdf);
+        } else { // :324-338
+            double ts = sv * dt, rts = e[j].inv_sdv * rdt, tv = mv * dt;
+            double x1 = b - tv, x2 = x1 - A;
+            PhiPair n1 = norm_both(x1 * rts);
+            PhiPair n2 = norm_both(x2 * rts);
+            double s = x2 * n2.cdf - x1 * n1.cdf + ts * (n2.pdf - n1.pdf);
+            cdf = (1.0 + s * e[j].inv_A) * e[j].inv_denom;
+            cdf = cdf < kFloor ? kFloor : (1.0 < cdf ? 1.0 : cdf); // std::clamp (NaN passes through)
+        }
+        pdf = pdf * (1.0 - cdf);      // :341
+        if (isnan(pdf)) pdf = kFloor; // :342
+    }
+    return pdf;
+}
+
+} // namespace gg

@@ -1,0 +1,117 @@
+"""The BASELINE.json workload shapes, built from synthetic data.
+
+  C1  single-subject LBA B x v model (13 par, 24 cells, 2 acc, 768 trials), 39 chains
+  C2  hierarchical recovery study: 32 subjects x 768 trials, 78 chains
+  C3  likelihood-only sweep: 5-par 2-acc model, 15 chains, 1e3 .. 1e7 trials
+  C4  scaled hierarchy: 1024 subjects x 768 trials, 78 chains (subjects sharded over GPUs)
+  C5  4-accumulator model, 96 cells, 17 par, 102 chains, 256 subjects x 2048 trials
+
+The model tables (cell table, generating population values, prior layout) come from the committed
+fixtures tests/golden/lba_data{6,5,2}.npz, which were extracted from the reference's own fixture
+files; the data are simulated here.  Start states are the generating values with jitter and their
+log prior / log likelihood are evaluated ON THE GPU through the C ABI (the job of
+initialise_theta / initialise_phi, R/phi.R:141-332, minus the rejection sampling).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from . import engine as E
+from . import synth
+from .model import CellTable, PriorTable, Trials
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+@dataclass
+class ModelSpec:
+    ct: CellTable
+    node_1_index: np.ndarray
+    pop_mean: np.ndarray
+    pop_scale: np.ndarray
+    p_prior: PriorTable  # hyper-likelihood layout (tnorm, lower 0)
+    h_prior: PriorTable  # prior on phi
+    sub_prior: PriorTable  # single-subject prior
+
+
+def _prior(g, prefix) -> PriorTable:
+    return PriorTable(len(g[f"{prefix}_p0"]), g[f"{prefix}_p0"].copy(), g[f"{prefix}_p1"].copy(), g[f"{prefix}_lower"].copy(),
+                      g[f"{prefix}_upper"].copy(), g[f"{prefix}_dist"].astype(np.int32), g[f"{prefix}_log_p"].astype(np.uint8),
+                      [str(s) for s in g[f"{prefix}_names"]])
+
+
+def load_model(k: int) -> ModelSpec:
+    g = np.load(os.path.join(GOLDEN, f"lba_data{k}.npz"))
+    ct = CellTable(int(g["param_src"].shape[2]), int(g["param_src"].shape[0]), len(g["pnames"]), g["param_src"].astype(np.int32),
+                   g["const_val"].astype(np.float64), g["posdrift"].astype(np.uint8), [str(s) for s in g["pnames"]],
+                   [str(s) for s in g["cell_names"]])
+    return ModelSpec(ct, g["node_1_index"].astype(np.int64), g["pop_mean"].copy(), g["pop_scale"].copy(), _prior(g, "p_prior"),
+                     _prior(g, "h_prior"), _prior(g, "sub_prior"))
+
+
+@dataclass
+class HierWorkload:
+    name: str
+    spec: ModelSpec
+    true_theta: np.ndarray  # [S, npar]
+    trials: List[Trials]
+    nchain: int
+    phi_start: E.PopState
+    subj_start: List[E.PopState]
+
+    @property
+    def n_trial_total(self) -> int:
+        return int(sum(len(t.rt) for t in self.trials))
+
+
+def hierarchical(name: str, model_k: int, n_subject: int, n_trial: int, n_replicate: int = 1, data_seed: int = 20260101,
+                 subject_begin: int = 0, subject_end: Optional[int] = None, start_seed: int = 1234) -> HierWorkload:
+    """Build subjects [subject_begin, subject_end) of an n_subject-subject hierarchical workload.
+
+    Data and start states of a subject depend only on (data_seed, global subject index), so every
+    rank of a sharded run builds exactly its slice of the same global problem.
+    """
+    spec = load_model(model_k)
+    ct = spec.ct
+    subject_end = n_subject if subject_end is None else subject_end
+    D, C = ct.npar, 3 * 2 * ct.npar  # nchain = 3 x (number of phi parameters), R/sampling.R:1-10
+    R = n_replicate
+    thetas, trials = [], []
+    for s in range(subject_begin, subject_end):
+        rng = np.random.default_rng([data_seed, s])
+        th = synth.rtnorm(spec.pop_mean, spec.pop_scale, 0.0, rng)
+        thetas.append(th)
+        trials.append(synth.simulate_subject(ct, spec.node_1_index, th, n_trial, rng))
+    thetas = np.stack(thetas)
+    # phi start: replicated on every rank -> seeded without the rank
+    prng = np.random.default_rng([start_seed, 0xF1])
+    center = np.concatenate([spec.pop_mean, spec.pop_scale])
+    phi0 = center[None, None, :] * (1.0 + 0.05 * prng.standard_normal((R, C, 2 * D)))
+    phi0 = np.abs(phi0)
+    subj0 = np.empty((len(trials), R, C, D))
+    for i, s in enumerate(range(subject_begin, subject_end)):
+        srng = np.random.default_rng([start_seed, s])
+        subj0[i] = np.abs(thetas[i][None, None, :] * (1.0 + 0.05 * srng.standard_normal((R, C, D))))
+    # log prior / log likelihood of the start states, on the GPU
+    S = len(trials)
+    ll = E.sumloglike(ct, trials, subj0.reshape(S, R * C, D)).reshape(S, R, C)
+    lp = np.empty((S, R, C))
+    for i in range(S):
+        x = subj0[i].reshape(R * C, D)
+        lp[i] = E.sumlogprior(spec.p_prior, x, phi0.reshape(R * C, 2 * D)[:, :D], phi0.reshape(R * C, 2 * D)[:, D:]).reshape(R, C)
+    phi_lp = E.sumlogprior(spec.h_prior, phi0.reshape(R * C, 2 * D)).reshape(R, C)
+    phi_ll = lp.sum(axis=0)  # local subjects only; refreshed (and all-reduced) by the first phi step anyway
+    return HierWorkload(name, spec, thetas, trials, C, E.PopState(phi0, phi_lp, phi_ll),
+                        [E.PopState(subj0[i], lp[i], ll[i]) for i in range(S)])
+
+
+def tuning_for(w: HierWorkload, nmc: int, thin: int, seeds, schedule=None, pop_migration_prob=0.05, sub_migration_prob=0.05,
+               subject_begin=0, n_subject_total=0, device=-1) -> E.Tuning:
+    from . import _lib as B
+    return E.Tuning(nmc=nmc, nchain=w.nchain, thin=thin, nparameter=2 * w.spec.ct.npar, pop_migration_prob=pop_migration_prob,
+                    sub_migration_prob=sub_migration_prob, schedule=B.SCHEDULE_PARALLEL if schedule is None else schedule,
+                    seeds=list(seeds), subject_begin=subject_begin, n_subject_total=n_subject_total, device=device)

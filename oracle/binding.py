@@ -207,3 +207,30 @@ def sumlogprior(p: OPrior, x, p0=None, p1=None) -> float:
     a = f64(p0) if p0 is not None else None
     b = f64(p1) if p1 is not None else None
     return lib().orc_sumlogprior(C.byref(p.c), ptr(a) if a is not None else None, ptr(b) if b is not None else None, ptr(xx))
+
+
+def run_subject(de: DE, pop: OPop, prior: OPrior, m: OModel, d: OData, rng: Rng, pop_id: int, n_iter: int) -> None:
+    lib().orc_run_subject(C.byref(de), C.byref(pop.c), C.byref(prior.c), C.byref(m.c), C.byref(d.c), C.byref(rng), C.c_uint(pop_id),
+                          C.c_uint(n_iter))
+
+
+def run_hyper(de: DE, phi: OPop, p_prior: OPrior, h_prior: OPrior, data_theta, rng: Rng, n_iter: int) -> None:
+    x = f64(data_theta)
+    lib().orc_run_hyper(C.byref(de), C.byref(phi.c), C.byref(p_prior.c), C.byref(h_prior.c), ptr(x), int(x.shape[0]), C.byref(rng),
+                        C.c_uint(n_iter))
+
+
+def run_hier(de: DE, phi: OPop, subj: Sequence[OPop], p_prior: OPrior, h_prior: OPrior, m: OModel, datas: Sequence[OData],
+             rng: Rng, n_iter: int, first_subject_id: int = 0) -> None:
+    S = len(subj)
+    pops = (Pop * S)(*[s.c for s in subj])
+    ds = (Data * S)(*[d.c for d in datas])
+    lib().orc_run_hier(C.byref(de), C.byref(phi.c), pops, S, C.byref(p_prior.c), C.byref(h_prior.c), C.byref(m.c), ds,
+                       C.byref(rng), C.c_uint(n_iter), C.c_uint(first_subject_id))
+    for i, s in enumerate(subj):  # store_i lives in the struct copies
+        s.c.store_i = pops[i].store_i
+
+
+def time_sumloglike(m: OModel, d: OData, thetas, reps: int) -> float:
+    th = f64(thetas)
+    return lib().orc_time_sumloglike(C.byref(m.c), C.byref(d.c), ptr(th), int(th.shape[0]), int(reps))

@@ -552,8 +552,11 @@ static void migration_(const orc_de *de, orc_pop *t, const ctx_t *c, orc_rng *r,
         orc_addr base = {pop, iter, para_idx < 0 ? 0u : (unsigned)para_idx, (unsigned)cur_chain, 0, 0};
         double next_ll = sll[next];
         if (c->kind == 2) { /* :494-500 */
-            double l_cur = like_(c, src + (size_t)cur_chain * np, cur_chain, r, &base);
-            t->ll[cur_chain] = l_cur;
+            if (!de->jacobi) { /* in-place order: refresh the source chain too (it may have just been replaced) */
+                double l_cur = like_(c, src + (size_t)cur_chain * np, cur_chain, r, &base);
+                t->ll[cur_chain] = l_cur;
+            }
+            /* snapshot order: every selected chain is `next` exactly once, so this refreshes them all */
             next_ll = like_(c, src + (size_t)next * np, next, r, &base);
             t->ll[next] = next_ll;
         }

@@ -41,6 +41,8 @@ def main():
         ct = build_cell_table(dmi["model"], dmi["node_1_index"], dmi["is_positive_drift"])
         out.update(param_src=ct.param_src, const_val=ct.const_val, posdrift=ct.posdrift, pnames=np.array(ct.pnames),
                    cell_names=np.array(ct.cell_names))
+        out["node_1_index"] = np.asarray(dmi["node_1_index"]).astype(np.int32)
+        out["accumulators"] = np.array([str(a) for a in dmi["model"]["accumulators"]])
         # single subject
         tr = flatten_data(dmi["data"], ct.cell_names)
         ss = d["sub_samples"]
@@ -72,6 +74,14 @@ def main():
         out["n_pop"] = np.array(npop)
         # the hyper_dmi data matrix (nsubject x npar "true" thetas) for run_hyper
         out["hyper_data"] = np.asarray(d["hyper_dmi"]["data"], dtype=np.float64)
+        # generating values of the recovery study (README.md:44-66): handy as sane start points
+        def by_pnames(v):  # named numeric vector -> model pnames order
+            names = list(v.names)
+            return np.array([float(np.asarray(v)[names.index(n)]) for n in ct.pnames])
+        out["p_vector"] = by_pnames(d["p_vector"])
+        out["pop_mean"] = by_pnames(d["pop_mean"])
+        out["pop_scale"] = by_pnames(d["pop_scale"])
+        out["ps"] = np.asarray(d["ps"], dtype=np.float64)
         path = os.path.join(ROOT, "tests", "golden", f"lba_data{k}.npz")
         np.savez_compressed(path, **out)
         print(path, os.path.getsize(path) // 1024, "KiB", "cells", ct.n_cell, "acc", ct.n_acc, "npar", ct.npar)

@@ -1,0 +1,40 @@
+// TEST INFRASTRUCTURE ONLY: compiles the engine's device math headers (gg_math.cuh, gg_lba.cuh,
+// gg_rng.cuh) as plain host C++ so the arithmetic can be checked against the oracle / mpmath
+// without a GPU.  The product never runs this code path; it exists to catch formula errors
+// before spending GPU time.
+#include "../../ggdmc_b200/csrc/gg_lba.cuh"
+#include "../../ggdmc_b200/csrc/gg_rng.cuh"
+
+extern "C" {
+// P rows: A, B (NOT yet b), mean_v, sd_v, st0, t0
+int hm_lba_cell(const double *P, int n_acc, const unsigned char *posdrift, const double *rt, int n, double *out)
+{
+    gg::CellAcc e[16];
+    bool bad = false;
+    for (int j = 0; j < n_acc; ++j)
+        bad |= gg::cellacc_build(e[j], P[0 * n_acc + j], P[1 * n_acc + j], P[2 * n_acc + j], P[3 * n_acc + j],
+                                 P[4 * n_acc + j], P[5 * n_acc + j], posdrift[j] != 0, 0.0);
+    for (int i = 0; i < n; ++i) out[i] = bad ? gg::kFloor : gg::n1pdf<0>(rt[i], e, n_acc);
+    return bad ? 0 : 1;
+}
+double hm_pnorm_std(double z) { return gg::pnorm_std(z); }
+double hm_dnorm_std(double z) { return gg::dnorm_std(z); }
+double hm_pnorm5(double x, double mu, double s, int lower) { return gg::pnorm5(x, mu, s, lower != 0); }
+double hm_dnorm4(double x, double mu, double s, int lg) { return gg::dnorm4(x, mu, s, lg != 0); }
+double hm_dprior1(int dist, double x, double p0, double p1, double lo, double up, int lg)
+{
+    return gg::dprior1(dist, x, p0, p1, lo, up, lg != 0);
+}
+void hm_philox(const unsigned *ctr, const unsigned *key, unsigned *out)
+{
+    gg::U4 c = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    gg::U4 r = gg::philox4x32_10(c, key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+double hm_draw_uniform(unsigned long long seed, unsigned pop, unsigned iter, unsigned sweep, unsigned chain,
+                       unsigned purpose, unsigned slot)
+{
+    gg::DrawAddr a = {seed, pop, iter, sweep, chain};
+    return gg::draw_uniform(a, purpose, slot);
+}
+}

@@ -1,0 +1,187 @@
+"""GPU sampler tests (-m gpu): whole DE-MCMC trajectories from the CUDA engine against the oracle.
+
+Both sides draw every uniform from the same counter-addressed Philox source, and the proposal
+arithmetic is done with the same IEEE operations, so theta trajectories must agree EXACTLY (a
+difference could only come from an accept decision whose MH ratio lies within ~1e-13 of its
+uniform); log prior / log likelihood values agree to FP64 rounding."""
+import numpy as np
+import pytest
+
+from ggdmc_b200 import _lib as B
+from ggdmc_b200 import engine as E
+from ggdmc_b200.model import Trials
+from oracle import binding as ob
+from helpers import load_fixture, sane_starts
+
+pytestmark = pytest.mark.gpu
+
+SCHEDULES = [(B.SCHEDULE_PARALLEL, True), (B.SCHEDULE_REFERENCE, False)]
+
+
+def subject_start(fx, od, oprior, nchain, rng, center=None, phi=None):
+    th = sane_starts(fx, nchain, rng, center=center)
+    D = th.shape[1]
+    lp = np.array([ob.sumlogprior(oprior, th[c], None if phi is None else phi[c, :D], None if phi is None else phi[c, D:])
+                   for c in range(nchain)])
+    ll = np.array([ob.sumloglike(fx.om, od, th[c]) for c in range(nchain)])
+    return th, lp, ll
+
+
+def compare(gpu: E.PopSamples, r: int, pop: ob.OPop, what: str):
+    th, lp, ll = gpu.theta[r], gpu.lp[r], gpu.ll[r]
+    same = np.array_equal(th, pop.out_theta)
+    if not same:
+        bad = np.argwhere(th != pop.out_theta)
+        raise AssertionError(f"{what}: theta trajectories differ first at (slot, chain, par) = {bad[0]}, {len(bad)} entries")
+    for a, b, nm in ((lp, pop.out_lp, "lp"), (ll, pop.out_ll, "ll")):
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin), f"{what}: {nm} finiteness differs"
+        assert np.all(np.abs(a[fin] - b[fin]) <= 1e-9 * np.maximum(1.0, np.abs(b[fin]))), f"{what}: {nm} differs"
+
+
+@pytest.mark.parametrize("schedule,jacobi", SCHEDULES)
+@pytest.mark.parametrize("pblocked", [False, True])
+def test_run_subject_trajectory(schedule, jacobi, pblocked):
+    """run_subject (src/de2R.cpp:8-23): crossover + migration sweeps, thinning, storage."""
+    fx = load_fixture(2)
+    rng = np.random.default_rng(7)
+    tr, od = fx.trials("sub"), fx.odata("sub")
+    prior, oprior = fx.prior("sub_prior"), fx.oprior("sub_prior")
+    D, nchain, nmc, thin = fx.ct.npar, 3 * fx.ct.npar, 5, 2
+    seeds = [9032, 77]
+    starts = [subject_start(fx, od, oprior, nchain, rng) for _ in seeds]
+    tun = E.Tuning(nmc=nmc, nchain=nchain, thin=thin, nparameter=D, sub_migration_prob=0.35, is_pblocked=pblocked, schedule=schedule,
+                   seeds=seeds)
+    st = E.PopState(np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts]), np.stack([s[2] for s in starts]))
+    out = E.run_subject(fx.ct, tr, prior, tun, st)
+    for r, seed in enumerate(seeds):
+        pop = ob.OPop(*starts[r], nmc, thin)
+        de = ob.make_de(D, nchain, sub_migration_prob=0.35, is_pblocked=pblocked, jacobi=jacobi)
+        ob.run_subject(de, pop, oprior, fx.om, od, ob.make_rng(seed=seed), 0, (nmc - 1) * thin)
+        compare(out, r, pop, f"run_subject seed {seed}")
+    assert not np.array_equal(out.theta[0], out.theta[1])
+    assert not np.array_equal(out.theta[0, 0], out.theta[0, -1])  # chains moved
+
+
+@pytest.mark.parametrize("schedule,jacobi", SCHEDULES)
+def test_run_hyper_trajectory(schedule, jacobi):
+    """run_hyper (src/de2R.cpp:30-47): phi chains against a fixed matrix of subject thetas."""
+    fx = load_fixture(2)
+    rng = np.random.default_rng(8)
+    pp, hp, opp, ohp = fx.prior("p_prior"), fx.prior("h_prior"), fx.oprior("p_prior"), fx.oprior("h_prior")
+    data = fx.g["hyper_data"]
+    D = pp.npar
+    nchain, nmc, thin = 3 * 2 * D, 6, 2
+    center = np.concatenate([fx.g["pop_mean"], fx.g["pop_scale"]])
+    phi0 = center[None, :] * (1.0 + 0.1 * rng.standard_normal((nchain, 2 * D)))
+    lp0 = np.array([ob.sumlogprior(ohp, phi0[c]) for c in range(nchain)])
+    ll0 = np.array([sum(ob.sumlogprior(opp, data[s], phi0[c, :D], phi0[c, D:]) for s in range(data.shape[0])) for c in range(nchain)])
+    seed = 4242
+    tun = E.Tuning(nmc=nmc, nchain=nchain, thin=thin, nparameter=2 * D, sub_migration_prob=0.3, schedule=schedule, seeds=[seed])
+    out = E.run_hyper(pp, hp, data, tun, E.PopState(phi0, lp0, ll0))
+    pop = ob.OPop(phi0, lp0, ll0, nmc, thin)
+    de = ob.make_de(2 * D, nchain, sub_migration_prob=0.3, jacobi=jacobi)
+    ob.run_hyper(de, pop, opp, ohp, data, ob.make_rng(seed=seed), (nmc - 1) * thin)
+    compare(out, 0, pop, "run_hyper")
+    assert not np.array_equal(out.theta[0, 0], out.theta[0, -1])
+
+
+def hier_setup(fx, S, nchain, rng):
+    D = fx.ct.npar
+    opp, ohp = fx.oprior("p_prior"), fx.oprior("h_prior")
+    center = np.concatenate([fx.g["pop_mean"], fx.g["pop_scale"]])
+    phi0 = center[None, :] * (1.0 + 0.1 * rng.standard_normal((nchain, 2 * D)))
+    subj = []
+    for s in range(S):
+        od = fx.odata(f"pop{s}")
+        subj.append(subject_start(fx, od, opp, nchain, rng, center=fx.g["ps"][s], phi=phi0))
+    lp0 = np.array([ob.sumlogprior(ohp, phi0[c]) for c in range(nchain)])
+    ll0 = np.array([sum(ob.sumlogprior(opp, subj[s][0][c], phi0[c, :D], phi0[c, D:]) for s in range(S)) for c in range(nchain)])
+    return (phi0, lp0, ll0), subj
+
+
+@pytest.mark.parametrize("schedule,jacobi", SCHEDULES)
+@pytest.mark.parametrize("blocked", [False, True])
+def test_run_hierarchical_trajectory(schedule, jacobi, blocked):
+    """run (src/de2R.cpp:123-171 -> run_hchains): phi step, subject steps with phi-driven priors,
+    stale-lp and refreshed-hyper-ll quirks, migration at both levels, per-parameter blocking."""
+    fx = load_fixture(2)
+    rng = np.random.default_rng(21)
+    S = fx.n_pop
+    D = fx.ct.npar
+    nchain, nmc, thin = 3 * 2 * D, 4, 2
+    if blocked:
+        nmc = 3
+    phi_s, subj_s = hier_setup(fx, S, nchain, rng)
+    seed = 31337
+    kw = dict(pop_migration_prob=0.3, sub_migration_prob=0.3, is_hblocked=blocked, is_pblocked=blocked)
+    tun = E.Tuning(nmc=nmc, nchain=nchain, thin=thin, nparameter=2 * D, schedule=schedule, seeds=[seed], **kw)
+    phi_out, subj_out = E.run_hier(fx.ct, [fx.trials(f"pop{s}") for s in range(S)], fx.prior("p_prior"), fx.prior("h_prior"), tun,
+                                   E.PopState(*phi_s), [E.PopState(*s) for s in subj_s])
+    phi = ob.OPop(*phi_s, nmc, thin)
+    pops = [ob.OPop(*s, nmc, thin) for s in subj_s]
+    de = ob.make_de(2 * D, nchain, jacobi=jacobi, **kw)
+    ob.run_hier(de, phi, pops, fx.oprior("p_prior"), fx.oprior("h_prior"), fx.om, [fx.odata(f"pop{s}") for s in range(S)],
+                ob.make_rng(seed=seed), (nmc - 1) * thin)
+    compare(phi_out, 0, phi, "phi")
+    for s in range(S):
+        compare(subj_out[s], 0, pops[s], f"subject {s}")
+    assert not np.array_equal(phi_out.theta[0, 0], phi_out.theta[0, -1])
+
+
+def test_replicates_batch_equals_separate_runs():
+    fx = load_fixture(2)
+    rng = np.random.default_rng(3)
+    tr, od = fx.trials("sub"), fx.odata("sub")
+    prior, oprior = fx.prior("sub_prior"), fx.oprior("sub_prior")
+    D, nchain = fx.ct.npar, 3 * fx.ct.npar
+    seeds = [5, 6, 7]
+    starts = [subject_start(fx, od, oprior, nchain, rng) for _ in seeds]
+    st = E.PopState(np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts]), np.stack([s[2] for s in starts]))
+    tun = E.Tuning(nmc=4, nchain=nchain, thin=3, nparameter=D, sub_migration_prob=0.2, seeds=seeds)
+    both = E.run_subject(fx.ct, tr, prior, tun, st)
+    for r, seed in enumerate(seeds):
+        one = E.run_subject(fx.ct, tr, prior, E.Tuning(nmc=4, nchain=nchain, thin=3, nparameter=D, sub_migration_prob=0.2, seeds=[seed]),
+                            E.PopState(*starts[r]))
+        assert np.array_equal(one.theta[0], both.theta[r]) and np.array_equal(one.ll[0], both.ll[r])
+
+
+def test_subject_shard_equals_slice_of_full_run():
+    """Independent-subject engine: running subjects [2, 4) with subject_begin = 2 reproduces the
+    same trajectories as the full run (draw addresses use GLOBAL subject ids)."""
+    fx = load_fixture(2)
+    rng = np.random.default_rng(13)
+    S, D = fx.n_pop, fx.ct.npar
+    nchain = 3 * D
+    prior, oprior = fx.prior("sub_prior"), fx.oprior("sub_prior")
+    trials = [fx.trials(f"pop{s}") for s in range(S)]
+    starts = [subject_start(fx, fx.odata(f"pop{s}"), oprior, nchain, rng, center=fx.g["ps"][s]) for s in range(S)]
+    tun = E.Tuning(nmc=2, nchain=nchain, thin=1, nparameter=D, sub_migration_prob=0.2, seeds=[99])
+    full = E.Engine(fx.ct, trials, prior, None, tun, None, [E.PopState(*s) for s in starts])
+    full.iterate(6)
+    a = full.state()
+    tun2 = E.Tuning(nmc=2, nchain=nchain, thin=1, nparameter=D, sub_migration_prob=0.2, seeds=[99], subject_begin=2, n_subject_total=S)
+    part = E.Engine(fx.ct, trials[2:], prior, None, tun2, None, [E.PopState(*s) for s in starts[2:]])
+    part.iterate(6)
+    b = part.state()
+    assert np.array_equal(a["theta"][:, 2:], b["theta"]) and np.array_equal(a["ll"][:, 2:], b["ll"])
+    assert full.launch_count > 0
+    full.close()
+    part.close()
+
+
+def test_error_behaviour():
+    """"Require three or more chains." (src/de.cpp:7-10) and argument errors surface as exceptions."""
+    fx = load_fixture(2)
+    tr = fx.trials("sub")
+    prior = fx.prior("sub_prior")
+    D = fx.ct.npar
+    st = E.PopState(np.ones((2, D)), np.zeros(2), np.zeros(2))
+    with pytest.raises(B.GgdmcError) as ei:
+        E.run_subject(fx.ct, tr, prior, E.Tuning(nmc=3, nchain=2, nparameter=D), st)
+    assert ei.value.code == B.ERR_CHAINS and "three or more chains" in str(ei.value)
+    bad = Trials(tr.rt, np.full(len(tr.rt), 9999, np.uint16))
+    st = E.PopState(np.ones((3, D)), np.zeros(3), np.zeros(3))
+    with pytest.raises(B.GgdmcError) as ei:
+        E.run_subject(fx.ct, bad, prior, E.Tuning(nmc=3, nchain=3, nparameter=D), st)
+    assert ei.value.code == B.ERR_ARG

@@ -1,0 +1,249 @@
+"""CPU tests: the oracle against the reference's known answers and against the reference's own
+object code; host-compiled device arithmetic against the oracle; C-ABI exports."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from helpers import load_fixture, sane_starts
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6])
+def test_golden_single_subject(k):
+    """sub_samples@log_likelihoods[,1] / @summed_log_prior[,1] of the reference fixtures."""
+    fx = load_fixture(k)
+    d = fx.odata("sub")
+    pr = fx.oprior("sub_prior")
+    th = fx.g["sub_theta"]
+    n_clean = 0
+    for c in range(th.shape[0]):
+        ld = ob.trial_logdens(fx.om, d, th[c])
+        v = ob.sumloglike_rinit(fx.om, d, th[c])
+        gold = fx.g["sub_ll"][c]
+        if np.all(ld > np.log(1e-12)):  # no (1 - cdf) ~ 0 trials: must match to rounding
+            assert abs(v - gold) <= 1e-12 * abs(gold), (k, c, v, gold)
+            n_clean += 1
+        else:  # cancellation-dominated trials present: same to ~1 %
+            assert abs(v - gold) <= 0.3 * abs(gold)
+        assert abs(ob.sumlogprior(pr, th[c]) - fx.g["sub_lp"][c]) <= 1e-13 * max(1.0, abs(fx.g["sub_lp"][c]))
+    assert n_clean >= 0.8 * th.shape[0]
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6])
+def test_golden_hierarchical(k):
+    """pop_samples: subject ll / lp goldens, phi hyper-likelihood and hyper-prior goldens."""
+    fx = load_fixture(k)
+    pp, hp = fx.oprior("p_prior"), fx.oprior("h_prior")
+    n_clean = n_all = 0
+    for s in range(fx.n_pop):
+        d = fx.odata(f"pop{s}")
+        ths = fx.g["pop_theta_all"][s]
+        for c in range(ths.shape[0]):
+            ld = ob.trial_logdens(fx.om, d, ths[c])
+            v = ob.sumloglike_rinit(fx.om, d, ths[c])
+            gold = fx.g[f"pop{s}_ll"][c]
+            n_all += 1
+            if np.all(ld > np.log(1e-12)):
+                assert abs(v - gold) <= 1e-12 * abs(gold), (k, s, c, v, gold)
+                n_clean += 1
+            else:
+                assert abs(v - gold) <= 0.3 * abs(gold)
+            lp = ob.sumlogprior(pp, ths[c])
+            assert abs(lp - fx.g[f"pop{s}_lp"][c]) <= 1e-13 * max(1.0, abs(lp))
+    assert n_clean >= 0.8 * n_all
+    phi = fx.g["phi_theta"]
+    npar = phi.shape[1] // 2
+    allth = fx.g["pop_theta_all"]
+    for c in range(phi.shape[0]):
+        tot = sum(ob.sumlogprior(pp, allth[s, c], phi[c, :npar], phi[c, npar:]) for s in range(allth.shape[0]))
+        assert abs(tot - fx.g["phi_ll"][c]) <= 1e-13 * abs(fx.g["phi_ll"][c])
+        assert abs(ob.sumlogprior(hp, phi[c]) - fx.g["phi_lp"][c]) <= 1e-13 * abs(fx.g["phi_lp"][c])
+
+
+needs_ref = pytest.mark.skipif(ob.ref_lib() is None, reason="oracle/_ref (reference object code) was never built")
+
+
+@needs_ref
+@pytest.mark.parametrize("k", [3, 6])
+def test_density_bitwise_vs_reference_object_code(k):
+    """orc_lba_cell == lba_class::dlba of /root/reference/src/de.o, bit for bit (same Phi/phi shim)."""
+    fx = load_fixture(k)
+    R, L = ob.ref_lib(), ob.lib()
+    na = fx.ct.n_acc
+    rng = np.random.default_rng(k)
+    n = 0
+    for s in range(2):
+        rt, cell = fx.g[f"pop{s}_rt"], fx.g[f"pop{s}_cell"]
+        thetas = list(fx.g["pop_theta_all"][s][::6]) + list(sane_starts(fx, 6, rng))
+        for th in thetas:
+            th = ob.f64(th)
+            for cc in np.unique(cell):
+                P = np.zeros((6, na))
+                L.orc_cell_params(C.byref(fx.om.c), ob.ptr(th), int(cc), ob.ptr(P))
+                r = ob.f64(rt[cell == cc])
+                o1, o2 = np.zeros_like(r), np.zeros_like(r)
+                u = np.zeros(4 * na + 8)
+                R.ref_set_uniform_stream(ob.ptr(u), len(u))
+                R.ref_lba_cell(ob.ptr(P), na, ob.ptr(fx.om.posdrift, ob.c_u8p), ob.ptr(r), len(r), ob.ptr(o2))
+                L.orc_lba_cell(ob.ptr(P), na, ob.ptr(fx.om.posdrift, ob.c_u8p), None, ob.ptr(r), len(r), ob.ptr(o1))
+                assert np.array_equal(o1, o2)
+                n += len(r)
+    assert n > 10000
+
+
+@needs_ref
+def test_selection_bitwise_vs_reference_object_code():
+    """get_chains / get_subchains of de.o vs the restatement, same injected uniforms (tie-free keys)."""
+    R, L = ob.ref_lib(), ob.lib()
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        nchain = int(rng.integers(3, 130))
+        k = int(rng.integers(0, nchain))
+        u = ob.f64(rng.uniform(size=2 * nchain + 5))
+        keys = (u * 2147483647.0).astype(np.int64)
+        if len(np.unique(keys[:nchain + 1])) != nchain + 1:
+            continue
+        R.ref_set_uniform_stream(ob.ptr(u), len(u))
+        o = (C.c_uint * 2)()
+        R.ref_get_chains(nchain, k, 2, o)
+        r = ob.make_rng(stream=u)
+        a, o2 = ob.Addr(), (C.c_uint * 2)()
+        L.orc_get_chains(nchain, k, 2, C.byref(r), C.byref(a), o2)
+        assert list(o) == list(o2) and r.pos == R.ref_uniform_stream_pos() == nchain - 1
+        R.ref_set_uniform_stream(ob.ptr(u), len(u))
+        s1 = (C.c_uint * nchain)()
+        n1 = R.ref_get_subchains(nchain, s1)
+        r = ob.make_rng(stream=u)
+        s2 = (C.c_uint * nchain)()
+        n2 = L.orc_get_subchains(nchain, C.byref(r), C.byref(a), s2)
+        assert n1 == n2 and list(s1[:n1]) == list(s2[:n2]) and r.pos == R.ref_uniform_stream_pos() == nchain + 1
+
+
+@needs_ref
+def test_tnorm_bitwise_vs_reference_object_code():
+    R, L = ob.ref_lib(), ob.lib()
+    rng = np.random.default_rng(3)
+    for _ in range(20000):
+        x, mean, sd = rng.uniform(-1, 12), rng.uniform(-2, 8), rng.uniform(-0.2, 4)
+        lo, up, lg = rng.choice([0.0, -np.inf, 0.5]), rng.choice([np.inf, 10.0]), int(rng.integers(0, 2))
+        a, b = R.ref_tnorm_d(x, mean, sd, lo, up, lg), L.orc_tnorm_d(x, mean, sd, lo, up, lg)
+        assert a == b or (np.isnan(a) and np.isnan(b))
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    L = ob.lib()
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        o = (C.c_uint * 4)()
+        L.orc_philox4x32_10((C.c_uint * 4)(*ctr), (C.c_uint * 2)(*key), o)
+        assert list(o) == want
+
+
+@pytest.fixture(scope="module")
+def hostmath():
+    """The engine's device math headers compiled as host C++ (arithmetic check without a GPU)."""
+    out = os.path.join(ROOT, "tests", "host", "libhostmath.so")
+    src = os.path.join(ROOT, "tests", "host", "host_math_harness.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", src, "-o", out], check=True)
+    H = C.CDLL(out)
+    for f in ("hm_pnorm_std", "hm_dnorm_std", "hm_pnorm5", "hm_dnorm4", "hm_dprior1", "hm_draw_uniform"):
+        getattr(H, f).restype = C.c_double
+    H.hm_pnorm_std.argtypes = [C.c_double]
+    H.hm_dnorm_std.argtypes = [C.c_double]
+    H.hm_pnorm5.argtypes = [C.c_double] * 3 + [C.c_int]
+    H.hm_dnorm4.argtypes = [C.c_double] * 3 + [C.c_int]
+    H.hm_dprior1.argtypes = [C.c_int] + [C.c_double] * 5 + [C.c_int]
+    H.hm_draw_uniform.argtypes = [C.c_ulonglong] + [C.c_uint] * 6
+    return H
+
+
+def test_device_math_on_host_matches_oracle(hostmath):
+    """gg_lba.cuh / gg_math.cuh (host build) vs the oracle on fixture cells: <= 1e-10 rel on log density."""
+    H, L = hostmath, ob.lib()
+    for k in (3, 6):
+        fx = load_fixture(k)
+        na = fx.ct.n_acc
+        rng = np.random.default_rng(k)
+        rt, cell = fx.g["pop0_rt"], fx.g["pop0_cell"]
+        thetas = list(fx.g["pop_theta_all"][0][::4]) + list(sane_starts(fx, 10, rng))
+        worst = 0.0
+        for th in thetas:
+            th = ob.f64(th)
+            for cc in np.unique(cell):
+                P = np.zeros((6, na))
+                L.orc_cell_params(C.byref(fx.om.c), ob.ptr(th), int(cc), ob.ptr(P))
+                r = ob.f64(rt[cell == cc])
+                o1, o2 = np.zeros_like(r), np.zeros_like(r)
+                L.orc_lba_cell(ob.ptr(P), na, ob.ptr(fx.om.posdrift, ob.c_u8p), None, ob.ptr(r), len(r), ob.ptr(o1))
+                P2 = P.copy()
+                P2[1] -= P2[0]
+                H.hm_lba_cell(ob.ptr(ob.f64(P2)), na, ob.ptr(fx.om.posdrift, ob.c_u8p), ob.ptr(r), len(r), ob.ptr(o2))
+                ok = (o1 > 1e-9) & (o2 > 1e-9)
+                if ok.any():
+                    rel = np.abs(np.log(o1[ok]) - np.log(o2[ok])) / np.maximum(np.abs(np.log(o1[ok])), 1.0)
+                    worst = max(worst, rel.max())
+                assert np.all(np.abs(o1 - o2) <= 1e-9 * np.maximum(o1, 1e-10) + 1e-14)
+        assert worst <= 1e-10
+
+
+def test_device_prior_math_on_host_matches_oracle(hostmath):
+    H, L = hostmath, ob.lib()
+    rng = np.random.default_rng(0)
+    for dist in (1, 2, 3, 4, 5, 6, 7):
+        for _ in range(2000):
+            x, p0, p1 = rng.uniform(-1, 6), rng.uniform(0.1, 4), rng.uniform(0.1, 4)
+            lo, up, lg = float(rng.choice([0.0, -np.inf, 0.5])), float(rng.choice([np.inf, 10.0])), int(rng.integers(0, 2))
+            if dist == 2:
+                lo, up = 0.0, 10.0
+            pr = ob.OPrior([p0], [p1], [lo], [up], [dist], [lg])
+            xx, out = ob.f64([x]), np.zeros(1)
+            L.orc_dprior(C.byref(pr.c), ob.ptr(pr.p0), ob.ptr(pr.p1), ob.ptr(xx), ob.ptr(out))
+            got = H.hm_dprior1(dist, x, p0, p1, lo, up, lg)
+            a = out[0]
+            assert (np.isnan(a) and np.isnan(got)) or a == got or abs(a - got) <= 1e-12 * max(1.0, abs(a)), (dist, x, p0, p1, lo, up, lg, a, got)
+
+
+def test_uniform_addressing_matches_oracle(hostmath):
+    """Same (seed, pop, iter, sweep, chain, purpose, slot) -> same uniform in engine code and oracle."""
+    H, L = hostmath, ob.lib()
+    rng = np.random.default_rng(4)
+    for _ in range(500):
+        seed = int(rng.integers(0, 2**63))
+        pop, it, sw, ch, pu, sl = (int(rng.integers(0, 2**32)), int(rng.integers(0, 2**32)), int(rng.integers(0, 4096)),
+                                   int(rng.integers(0, 65536)), int(rng.integers(0, 7)), int(rng.integers(0, 1000)))
+        r = ob.make_rng(seed=seed)
+        a = ob.Addr(pop, it, sw, ch, pu, sl)
+        assert L.orc_uniform(C.byref(r), C.byref(a)) == H.hm_draw_uniform(seed, pop, it, sw, ch, pu, sl)
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """libggdmc_b200.so loads (no GPU needed) and exports everything include/ggdmc_b200.h declares."""
+    from ggdmc_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "ggdmc_b200.h")).read()
+    declared = set(re.findall(r"\b(ggdmc_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.ggdmc_b200_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the compute entry points fail loudly (GGDMC_ERR_CUDA)."""
+    from ggdmc_b200 import _lib, engine
+    if engine.device_count() > 0:
+        pytest.skip("a GPU is present")
+    fx = load_fixture(2)
+    with pytest.raises(_lib.GgdmcError) as ei:
+        engine.trial_logdens(fx.ct, fx.trials("sub"), fx.g["sub_theta"][:2])
+    assert ei.value.code == _lib.ERR_CUDA
