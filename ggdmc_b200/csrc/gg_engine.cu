@@ -7,6 +7,8 @@
 #include "gg_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -353,28 +355,21 @@ struct ggdmc_engine {
 
     void init_level_state(LevelDev &lv, const ggdmc_start_t *starts, int n_items, int D_)
     {
-        // starts[i] holds [R][C][D_] for item i (subject or phi); device population p = r * n_items + i
-        const size_t CD = (size_t)C * D_;
-        std::vector<double> th((size_t)R * n_items * CD), lp((size_t)R * n_items * C), ll(lp.size());
+        // starts[i] holds [R][C][D_] for item i (subject or phi); device population p = i * R + r,
+        // so item i's block is one contiguous copy
+        const size_t CD = (size_t)C * D_, blk = (size_t)R * CD, blk1 = (size_t)R * C;
+        std::vector<double> th((size_t)n_items * blk), lp((size_t)n_items * blk1), ll(lp.size());
         for (int i = 0; i < n_items; ++i) {
             require(starts[i].theta && starts[i].lp && starts[i].ll, "null start state");
-            for (int r = 0; r < R; ++r) {
-                const size_t p = (size_t)r * n_items + i;
-                std::memcpy(&th[p * CD], starts[i].theta + (size_t)r * CD, CD * 8);
-                std::memcpy(&lp[p * C], starts[i].lp + (size_t)r * C, (size_t)C * 8);
-                std::memcpy(&ll[p * C], starts[i].ll + (size_t)r * C, (size_t)C * 8);
-            }
+            std::memcpy(&th[i * blk], starts[i].theta, blk * 8);
+            std::memcpy(&lp[i * blk1], starts[i].lp, blk1 * 8);
+            std::memcpy(&ll[i * blk1], starts[i].ll, blk1 * 8);
         }
-        CUDA_CHECK(cudaMemcpy(lv.theta.p, th.data(), th.size() * 8, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(lv.lp.p, lp.data(), lp.size() * 8, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(lv.ll.p, ll.data(), ll.size() * 8, cudaMemcpyHostToDevice));
-        // slot 0 of the storage = start state
-        const int npop = R * n_items;
-        for (int p = 0; p < npop; ++p) {
-            CUDA_CHECK(cudaMemcpy(lv.out_theta.p + (size_t)p * nmc * CD, lv.theta.p + (size_t)p * CD, CD * 8, cudaMemcpyDeviceToDevice));
-            CUDA_CHECK(cudaMemcpy(lv.out_lp.p + (size_t)p * nmc * C, lv.lp.p + (size_t)p * C, (size_t)C * 8, cudaMemcpyDeviceToDevice));
-            CUDA_CHECK(cudaMemcpy(lv.out_ll.p + (size_t)p * nmc * C, lv.ll.p + (size_t)p * C, (size_t)C * 8, cudaMemcpyDeviceToDevice));
-        }
+        CUDA_CHECK(cudaMemcpyAsync(lv.theta.p, th.data(), th.size() * 8, cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaMemcpyAsync(lv.lp.p, lp.data(), lp.size() * 8, cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaMemcpyAsync(lv.ll.p, ll.data(), ll.size() * 8, cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream)); // the staging vectors die here
+        store(lv); // d_iter == 0: slot 0 of the storage = start state (@hdr/theta.h: slot 1 in R)
     }
 
     // ---- construction for the three run kinds ------------------------------------------------
@@ -392,7 +387,7 @@ struct ggdmc_engine {
         trials.set_chunking((int64_t)R * S * C);
         subj.create(R * S, R, C, D, nmc, thin);
         Level &L = subj.L;
-        L.pops_per_rep = S; L.pop_id_base = subject_begin; L.is_phi = 0;
+        L.n_rep = R; L.pop_id_base = subject_begin; L.is_phi = 0;
         L.gamma = cfg->gamma_precursor / std::sqrt(2.0 * cfg->nparameter); // src/de.cpp:12,24
         L.rp = cfg->rp; L.mig_prob = cfg->sub_migration_prob;
         L.seed = seeds.p; L.prior = p_prior.d; L.prior_ovr = nullptr;
@@ -406,13 +401,13 @@ struct ggdmc_engine {
             h_prior.upload(hp);
             phi.create(R, R, C, D2, nmc, thin);
             Level &P = phi.L;
-            P.pops_per_rep = 1; P.pop_id_base = 0; P.is_phi = 1;
+            P.n_rep = R; P.pop_id_base = 0; P.is_phi = 1;
             P.gamma = L.gamma; P.rp = cfg->rp; P.mig_prob = cfg->pop_migration_prob;
             P.seed = seeds.p; P.prior = h_prior.d; P.prior_ovr = nullptr;
             P.nmove = std::min(D2, cfg->nparameter);
             init_level_state(phi, phi_start, 1, D2);
             L.prior_ovr = phi.theta.p; // src/de.cpp:599-600, 646-649
-            setup_hyper(subj.theta.p, (int)((size_t)S * C * D), C * D, D, 1);
+            setup_hyper(subj.theta.p, C * D, R * C * D, D, 1);
         }
     }
 
@@ -429,7 +424,7 @@ struct ggdmc_engine {
         hyper_data.upload(data_theta, (size_t)S * D);
         phi.create(R, R, C, D2, nmc, thin);
         Level &P = phi.L;
-        P.pops_per_rep = 1; P.pop_id_base = 0; P.is_phi = 1;
+        P.n_rep = R; P.pop_id_base = 0; P.is_phi = 1;
         P.gamma = cfg->gamma_precursor / std::sqrt(2.0 * cfg->nparameter);
         P.rp = cfg->rp; P.mig_prob = cfg->sub_migration_prob; // run_chains uses m_sub_migration_prob, src/de.cpp:205-206
         P.seed = seeds.p; P.prior = h_prior.d; P.prior_ovr = nullptr;
@@ -634,21 +629,34 @@ struct ggdmc_engine {
         if (profile) collect_profile();
     }
 
-    // device storage -> the caller's posterior arrays
+    // device storage -> the caller's posterior arrays.  Device order is item-major
+    // ([item][R][nmc][C][D]), i.e. exactly the concatenation of the per-item host arrays; when the
+    // caller's arrays are adjacent in memory (the Python binding and the R glue allocate them that
+    // way) the whole level comes back in three large copies.
     void download_level(LevelDev &lv, int n_items, ggdmc_samples_t *outs)
     {
         const int D_ = lv.L.npar;
-        const size_t blk = (size_t)nmc * C * D_, blk1 = (size_t)nmc * C;
+        const size_t blk = (size_t)R * nmc * C * D_, blk1 = (size_t)R * nmc * C;
+        bool contiguous = true;
         for (int i = 0; i < n_items; ++i) {
             require(outs[i].theta && outs[i].lp && outs[i].ll, "null output arrays");
-            for (int r = 0; r < R; ++r) {
-                const size_t p = (size_t)r * n_items + i;
-                CUDA_CHECK(cudaMemcpy(outs[i].theta + (size_t)r * blk, lv.out_theta.p + p * blk, blk * 8, cudaMemcpyDeviceToHost));
-                CUDA_CHECK(cudaMemcpy(outs[i].lp + (size_t)r * blk1, lv.out_lp.p + p * blk1, blk1 * 8, cudaMemcpyDeviceToHost));
-                CUDA_CHECK(cudaMemcpy(outs[i].ll + (size_t)r * blk1, lv.out_ll.p + p * blk1, blk1 * 8, cudaMemcpyDeviceToHost));
-            }
+            if (i > 0 && (outs[i].theta != outs[i - 1].theta + blk || outs[i].lp != outs[i - 1].lp + blk1 ||
+                          outs[i].ll != outs[i - 1].ll + blk1))
+                contiguous = false;
             outs[i].npar = D_; outs[i].nchain = C; outs[i].nmc = nmc;
         }
+        if (contiguous) {
+            CUDA_CHECK(cudaMemcpyAsync(outs[0].theta, lv.out_theta.p, (size_t)n_items * blk * 8, cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(outs[0].lp, lv.out_lp.p, (size_t)n_items * blk1 * 8, cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(outs[0].ll, lv.out_ll.p, (size_t)n_items * blk1 * 8, cudaMemcpyDeviceToHost, stream));
+        } else {
+            for (int i = 0; i < n_items; ++i) {
+                CUDA_CHECK(cudaMemcpyAsync(outs[i].theta, lv.out_theta.p + i * blk, blk * 8, cudaMemcpyDeviceToHost, stream));
+                CUDA_CHECK(cudaMemcpyAsync(outs[i].lp, lv.out_lp.p + i * blk1, blk1 * 8, cudaMemcpyDeviceToHost, stream));
+                CUDA_CHECK(cudaMemcpyAsync(outs[i].ll, lv.out_ll.p + i * blk1, blk1 * 8, cudaMemcpyDeviceToHost, stream));
+            }
+        }
+        CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 };
 
@@ -656,6 +664,18 @@ struct ggdmc_engine {
 // C ABI
 // ---------------------------------------------------------------------------------------------
 namespace {
+struct PhaseTimer { // GGDMC_B200_TIMING=1 prints host wall time per phase of a run* call to stderr
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    PhaseTimer() : on(std::getenv("GGDMC_B200_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *what)
+    {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[ggdmc_b200] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 int fail(char err[256], const std::exception &e, int code)
 {
     if (err) {
@@ -831,11 +851,18 @@ int ggdmc_b200_run(const ggdmc_model_t *model, const ggdmc_trials_t *trials, con
 {
     GG_TRY
     require(model && trials && p_prior && h_prior && cfg && phi_start && subj_start && phi_out && subj_out, "null argument");
-    ggdmc_engine e;
-    e.create_lba(model, trials, p_prior, h_prior, cfg, phi_start, subj_start);
-    e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length);
-    e.download_level(e.subj, e.S, subj_out);
-    e.download_level(e.phi, 1, phi_out);
+    PhaseTimer pt;
+    {
+        ggdmc_engine e;
+        e.create_lba(model, trials, p_prior, h_prior, cfg, phi_start, subj_start);
+        pt.lap("create");
+        e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length);
+        pt.lap("iterate");
+        e.download_level(e.subj, e.S, subj_out);
+        e.download_level(e.phi, 1, phi_out);
+        pt.lap("download");
+    }
+    pt.lap("destroy");
     GG_CATCH
 }
 
@@ -892,7 +919,7 @@ int ggdmc_b200_sumloglike(const ggdmc_model_t *model, const ggdmc_trials_t *tria
     uint64_t z64 = 0; uint32_t z32 = 0;
     d_seed.upload(&z64, 1); d_iter.upload(&z32, 1);
     Level L{};
-    L.npop = S; L.nchain = n_theta; L.npar = D; L.pops_per_rep = S; L.prop = d_theta.p; L.target = d_target.p;
+    L.npop = S; L.nchain = n_theta; L.npar = D; L.n_rep = 1; L.prop = d_theta.p; L.target = d_target.p;
     L.mode = d_mode.p; L.seed = d_seed.p;
     launch_like(L, M.d, T.d, d_iter.p, 0, -1, d_part.p, 0);
     std::vector<double> h(n * T.d.nsplit);

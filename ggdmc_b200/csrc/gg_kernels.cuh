@@ -45,8 +45,9 @@ struct Level {
     int nchain;      // C
     int npar;        // length of one chain's vector
     int nmove;       // leading parameters perturbed by an unblocked sweep (src/de.cpp:592: half at the subject level of a hierarchy)
-    int pops_per_rep; // populations per replicate (S at the subject level, 1 at the phi level)
-    int pop_id_base;  // global id of local population 0 within a replicate (subject_begin), phi: unused
+    int n_rep;        // replicates; populations are item-major: p = item * n_rep + replicate
+                      // (item = local subject at the subject level, 0 at the phi level)
+    int pop_id_base;  // global id of local item 0 (subject_begin), phi: unused
     int is_phi;       // population id is kPopPhi
     double gamma, rp, mig_prob;
     // state
@@ -69,13 +70,13 @@ struct Level {
 
 __device__ __forceinline__ uint32_t pop_global_id(const Level &L, int p)
 {
-    return L.is_phi ? kPopPhi : (uint32_t)(L.pop_id_base + (p % L.pops_per_rep));
+    return L.is_phi ? kPopPhi : (uint32_t)(L.pop_id_base + p / L.n_rep);
 }
 
 __device__ __forceinline__ DrawAddr make_addr(const Level &L, int p, uint32_t iter, int sweep, int chain)
 {
     DrawAddr a;
-    a.seed = L.seed[p / L.pops_per_rep];
+    a.seed = L.seed[p % L.n_rep];
     a.pop = pop_global_id(L, p);
     a.iter = iter;
     a.sweep = sweep < 0 ? 0u : (uint32_t)sweep;
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t 
         const double *t0 = L.theta + ((size_t)p * C + c0) * D;
         const double *t1 = L.theta + ((size_t)p * C + c1) * D;
         double *pr = L.prop + ((size_t)p * C + src) * D;
-        const double *ovr = L.prior_ovr ? L.prior_ovr + ((size_t)(p / L.pops_per_rep) * C + src) * 2 * D : nullptr;
+        const double *ovr = L.prior_ovr ? L.prior_ovr + ((size_t)(p % L.n_rep) * C + src) * 2 * D : nullptr;
         for (int d = lane; d < D; d += 32) {
             double x = th[d];
             const bool moved = para_idx >= 0 ? (d == para_idx) : (d < L.nmove);
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(BLOCK) k_like(Level L, DevModel M, TrialData T
     }
     if (L.target[p * C + chain] < 0) return;
     const int split = blockIdx.y;
-    const int s = p % L.pops_per_rep;
+    const int s = p / L.n_rep;
     const int ntr = T.count[s];
     const int t_begin = split * T.chunk;
     double *part = ll_part + ((size_t)p * C + chain) * T.nsplit + split;

@@ -10,6 +10,7 @@
 // clamp of the survivor CDF to [1e-10, 1] and the NaN -> 1e-10 rules are the reference's.
 #pragma once
 #include "gg_math.cuh"
+#include "gg_fastmath.cuh"
 
 namespace gg {
 
@@ -36,15 +37,17 @@ GG_HD bool cellacc_build(CellAcc &e, double A, double B, double mean_v, double s
     return (A < 0.0) || (b < 0.0) || (b < A) || (sd_v < 0.0) || (st0 < 0.0) || (t0 < 0.0);
 }
 
-struct PhiPair { double cdf, pdf; };
+typedef fm::Pair PhiPair;
 
-// Phi(z) and phi(z) of the standard normal (Rf_pnorm5(z,0,1,1,0), Rf_dnorm4(z,0,1,0)).
-GG_HD PhiPair norm_both(double z)
+// Phi(z) and phi(z) of the standard normal (Rf_pnorm5(z,0,1,1,0), Rf_dnorm4(z,0,1,0)): one shared
+// exponential, coefficients in constant memory, no branches (gg_fastmath.cuh).
+GG_HD PhiPair norm_both(double z) { return fm::norm_pair(z); }
+
+// 1 / dt for the trial loop: dt == 0 must give +inf like the reference's x / (sd_v * 0)
+GG_HD double rcp_time(double dt)
 {
-    PhiPair r;
-    r.cdf = pnorm_std(z);
-    r.pdf = dnorm_std(z);
-    return r;
+    double r = fm::rcp_pos(dt);
+    return dt == 0.0 ? INFINITY : r;
 }
 
 // density of one trial whose cell's table row is e[0 .. n_acc)
@@ -54,7 +57,7 @@ GG_HD double n1pdf(double rt, const CellAcc *e, int n_acc_rt)
     const int n_acc = NACC > 0 ? NACC : n_acc_rt;
     double t0a = e[0].t0a;
     double dt = rt - t0a;
-    double rdt = 1.0 / dt;
+    double rdt = rcp_time(dt);
     double pdf;
     {
         const double b = e[0].b, A = e[0].A, mv = e[0].mean_v, sv = e[0].sd_v;
@@ -78,7 +81,7 @@ GG_HD double n1pdf(double rt, const CellAcc *e, int n_acc_rt)
         if (e[j].t0a != t0a) {
             t0a = e[j].t0a;
             dt = rt - t0a;
-            rdt = 1.0 / dt;
+            rdt = rcp_time(dt);
         }
         double cdf;
         if (0.0 > dt) { // :310-312

@@ -12,7 +12,7 @@
 #include <float.h>
 
 #ifdef __CUDACC__
-#define GG_HD __host__ __device__ __forceinline__
+#define GG_HD __device__ __forceinline__
 #else
 #define GG_HD inline
 #endif

@@ -16,7 +16,7 @@
 #include <stdint.h>
 
 #ifdef __CUDACC__
-#define GG_HD2 __host__ __device__ __forceinline__
+#define GG_HD2 __device__ __forceinline__
 #else
 #define GG_HD2 inline
 #endif

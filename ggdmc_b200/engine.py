@@ -154,7 +154,10 @@ def run_hier(ct: CellTable, trials: Sequence[Trials], p_prior: PriorTable, h_pri
     m, t, p, h, cfg = _model(ct), _trials(trials), _prior(p_prior), _prior(h_prior), _config(tuning)
     R, S = len(tuning.seeds), len(trials)
     phi_out = PopSamples.empty(R, tuning.nmc, tuning.nchain, h_prior.npar)
-    subj_out = [PopSamples.empty(R, tuning.nmc, tuning.nchain, ct.npar) for _ in range(S)]
+    # one allocation for all subjects: adjacent per-subject arrays come back in a single device->host copy
+    big_t = np.empty((S, R, tuning.nmc, tuning.nchain, ct.npar))
+    big_lp, big_ll = np.empty((S, R, tuning.nmc, tuning.nchain)), np.empty((S, R, tuning.nmc, tuning.nchain))
+    subj_out = [PopSamples(big_t[s], big_lp[s], big_ll[s]) for s in range(S)]
     starts = (B.StartT * S)(*[s.c() for s in subj_start])
     outs = (B.SamplesT * S)(*[o.c() for o in subj_out])
     pc, poc, err, cb = phi_start.c(), phi_out.c(), B.errbuf(), _progress(progress)
@@ -276,7 +279,7 @@ class Engine:
 
     def state(self):
         R, S, C_, D = self.R, self.S, self.C, self.D
-        st = np.empty((R, S, C_, D)); slp = np.empty((R, S, C_)); sll = np.empty((R, S, C_))
+        st = np.empty((S, R, C_, D)); slp = np.empty((S, R, C_)); sll = np.empty((S, R, C_))
         if self.hier:
             pt = np.empty((R, C_, 2 * D)); plp = np.empty((R, C_)); pll = np.empty((R, C_))
         else:

@@ -99,10 +99,9 @@ def hierarchical(name: str, model_k: int, n_subject: int, n_trial: int, n_replic
     # log prior / log likelihood of the start states, on the GPU
     S = len(trials)
     ll = E.sumloglike(ct, trials, subj0.reshape(S, R * C, D)).reshape(S, R, C)
-    lp = np.empty((S, R, C))
-    for i in range(S):
-        x = subj0[i].reshape(R * C, D)
-        lp[i] = E.sumlogprior(spec.p_prior, x, phi0.reshape(R * C, 2 * D)[:, :D], phi0.reshape(R * C, 2 * D)[:, D:]).reshape(R, C)
+    ph = np.broadcast_to(phi0.reshape(1, R * C, 2 * D), (S, R * C, 2 * D)).reshape(S * R * C, 2 * D)
+    lp = E.sumlogprior(spec.p_prior, subj0.reshape(S * R * C, D), np.ascontiguousarray(ph[:, :D]),
+                       np.ascontiguousarray(ph[:, D:])).reshape(S, R, C)
     phi_lp = E.sumlogprior(spec.h_prior, phi0.reshape(R * C, 2 * D)).reshape(R, C)
     phi_ll = lp.sum(axis=0)  # local subjects only; refreshed (and all-reduced) by the first phi step anyway
     return HierWorkload(name, spec, thetas, trials, C, E.PopState(phi0, phi_lp, phi_ll),

@@ -190,7 +190,8 @@ int ggdmc_b200_engine_iterate_flushed(ggdmc_engine_t *engine, int32_t n_iter, in
  * *elapsed_ms = mean CUDA-event time of one launch; *n_trial_lik = trial-likelihoods per launch. */
 int ggdmc_b200_engine_time_likelihood(ggdmc_engine_t *engine, int32_t reps, float *elapsed_ms, int64_t *n_trial_lik,
                                       char err[256]);
-/* Copy the current state of the local populations back: theta [n_replicate][n_subject][nchain][npar] etc.
+/* Copy the current state of the local populations back: subject theta [n_subject][n_replicate][nchain][npar],
+ * phi theta [n_replicate][nchain][2 npar] etc.
  * Any pointer may be NULL. */
 int ggdmc_b200_engine_state(ggdmc_engine_t *engine, double *phi_theta, double *phi_lp, double *phi_ll,
                             double *subj_theta, double *subj_lp, double *subj_ll, char err[256]);

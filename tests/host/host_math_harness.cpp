@@ -38,3 +38,16 @@ double hm_draw_uniform(unsigned long long seed, unsigned pop, unsigned iter, uns
     return gg::draw_uniform(a, purpose, slot);
 }
 }
+
+#include "../../ggdmc_b200/csrc/gg_fastmath.cuh"
+extern "C" {
+void hm_norm_pair(const double *z, int n, double *cdf, double *pdf)
+{
+    for (int i = 0; i < n; ++i) {
+        gg::fm::Pair p = gg::fm::norm_pair(z[i]);
+        cdf[i] = p.cdf;
+        pdf[i] = p.pdf;
+    }
+}
+double hm_rcp_pos(double d) { return gg::fm::rcp_pos(d); }
+}

@@ -196,6 +196,28 @@ def test_device_math_on_host_matches_oracle(hostmath):
         assert worst <= 1e-10
 
 
+def test_fast_norm_pair_accuracy(hostmath):
+    """gg_fastmath.cuh norm_pair (host build) against 50-digit mpmath: Phi and phi to a few ulp,
+    relative accuracy kept in the lower tail, special values like R's pnorm / dnorm."""
+    import mpmath as mp
+    mp.mp.dps = 50
+    H = hostmath
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(0)
+    z = np.concatenate([rng.uniform(-37.5, 9, 3000), rng.uniform(-6, 6, 3000), rng.uniform(-1, 1, 1000)])
+    cdf, pdf = np.zeros_like(z), np.zeros_like(z)
+    H.hm_norm_pair(z.ctypes.data_as(dp), len(z), cdf.ctypes.data_as(dp), pdf.ctypes.data_as(dp))
+    for zi, c, p in zip(z, cdf, pdf):
+        rc, rp = mp.ncdf(mp.mpf(float(zi))), mp.npdf(mp.mpf(float(zi)))
+        assert abs((mp.mpf(float(c)) - rc) / rc) < 8e-16, (zi, c)
+        assert abs((mp.mpf(float(p)) - rp) / rp) < 6e-16, (zi, p)
+    zs = np.array([0.0, np.inf, -np.inf, 40.0, -40.0, 1e300, np.nan])
+    cdf, pdf = np.zeros_like(zs), np.zeros_like(zs)
+    H.hm_norm_pair(zs.ctypes.data_as(dp), len(zs), cdf.ctypes.data_as(dp), pdf.ctypes.data_as(dp))
+    assert list(cdf[:6]) == [0.5, 1.0, 0.0, 1.0, 0.0, 1.0] and np.isnan(cdf[6]) and np.isnan(pdf[6])
+    assert pdf[0] == 0.3989422804014327 and list(pdf[1:6]) == [0.0] * 5
+
+
 def test_device_prior_math_on_host_matches_oracle(hostmath):
     H, L = hostmath, ob.lib()
     rng = np.random.default_rng(0)
