@@ -255,40 +255,63 @@ void allow_smem(K kernel, size_t bytes)
     if (bytes > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
-constexpr int kLikeBlock = 128;
 constexpr int kHyperBlock = 256;
 constexpr int kProposeWarps = 4;
 
-size_t like_smem(const DevModel &M, int D)
+// Launch shape of the likelihood kernel: (threads per block, minimum resident blocks per SM).
+// The default was picked by measurement on B200 (profiles/); GGDMC_B200_LIKE_VARIANT overrides it
+// for experiments.
+struct LikeVariant { int block, minb; };
+const LikeVariant kLikeVariants[] = {{128, 6}, {128, 8}, {64, 12}, {64, 16}};
+int like_variant()
 {
-    size_t b = (size_t)M.n_cell * M.n_acc * sizeof(CellAcc) + (size_t)D * 8 + (kLikeBlock / 32) * 8 + (size_t)M.n_cell * M.n_acc;
+    static int v = [] {
+        const char *e = std::getenv("GGDMC_B200_LIKE_VARIANT");
+        int x = e ? std::atoi(e) : 1;
+        return (x < 0 || x > 3) ? 1 : x;
+    }();
+    return v;
+}
+
+size_t like_smem(const DevModel &M, int block)
+{
+    size_t b = (size_t)M.n_cell * M.n_acc * sizeof(CellAcc) + (size_t)(block / 32) * 8 + (size_t)M.n_cell;
     return (b + 15) & ~(size_t)15;
+}
+
+template <int NACC, int BLOCK, int MINB>
+void launch_like_t(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step,
+                   double *ll_part, cudaStream_t st)
+{
+    dim3 grid(step < 0 ? L.npop * L.nchain : L.npop, T.nsplit);
+    const size_t sm = like_smem(M, BLOCK);
+    require(sm <= 220 * 1024, "cell table does not fit in shared memory");
+    allow_smem(k_like<NACC, BLOCK, MINB>, sm);
+    k_like<NACC, BLOCK, MINB><<<grid, BLOCK, sm, st>>>(L, M, T, d_iter, sweep, step, ll_part);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+template <int NACC>
+void launch_like_n(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step,
+                   double *ll_part, cudaStream_t st)
+{
+    switch (like_variant()) {
+    case 0: launch_like_t<NACC, 128, 6>(L, M, T, d_iter, sweep, step, ll_part, st); break;
+    case 2: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, ll_part, st); break;
+    case 3: launch_like_t<NACC, 64, 16>(L, M, T, d_iter, sweep, step, ll_part, st); break;
+    default: launch_like_t<NACC, 128, 8>(L, M, T, d_iter, sweep, step, ll_part, st);
+    }
 }
 
 void launch_like(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step,
                  double *ll_part, cudaStream_t st)
 {
-    dim3 grid(step < 0 ? L.npop * L.nchain : L.npop, T.nsplit);
-    const size_t sm = like_smem(M, L.npar);
-    require(sm <= 220 * 1024, "cell table does not fit in shared memory");
     switch (M.n_acc) {
-    case 2:
-        allow_smem(k_like<2, kLikeBlock>, sm);
-        k_like<2, kLikeBlock><<<grid, kLikeBlock, sm, st>>>(L, M, T, d_iter, sweep, step, ll_part);
-        break;
-    case 3:
-        allow_smem(k_like<3, kLikeBlock>, sm);
-        k_like<3, kLikeBlock><<<grid, kLikeBlock, sm, st>>>(L, M, T, d_iter, sweep, step, ll_part);
-        break;
-    case 4:
-        allow_smem(k_like<4, kLikeBlock>, sm);
-        k_like<4, kLikeBlock><<<grid, kLikeBlock, sm, st>>>(L, M, T, d_iter, sweep, step, ll_part);
-        break;
-    default:
-        allow_smem(k_like<0, kLikeBlock>, sm);
-        k_like<0, kLikeBlock><<<grid, kLikeBlock, sm, st>>>(L, M, T, d_iter, sweep, step, ll_part);
+    case 2: launch_like_n<2>(L, M, T, d_iter, sweep, step, ll_part, st); break;
+    case 3: launch_like_n<3>(L, M, T, d_iter, sweep, step, ll_part, st); break;
+    case 4: launch_like_n<4>(L, M, T, d_iter, sweep, step, ll_part, st); break;
+    default: launch_like_n<0>(L, M, T, d_iter, sweep, step, ll_part, st);
     }
-    CUDA_CHECK(cudaGetLastError());
 }
 
 } // namespace
@@ -321,7 +344,7 @@ struct ggdmc_engine {
     LevelDev subj, phi;
     DBuf<uint64_t> seeds;
     DBuf<uint32_t> d_iter;
-    DBuf<double> ll_part, hpart, hsum, hyper_data;
+    DBuf<double> ll_part, hpart, hsum, hyper_data, phi_consts;
     HyperArgs H{};
 
     ~ggdmc_engine()
@@ -407,6 +430,8 @@ struct ggdmc_engine {
             P.nmove = std::min(D2, cfg->nparameter);
             init_level_state(phi, phi_start, 1, D2);
             L.prior_ovr = phi.theta.p; // src/de.cpp:599-600, 646-649
+            phi_consts.alloc((size_t)R * C * D * 2);
+            L.ovr_consts = phi_consts.p;
             setup_hyper(subj.theta.p, C * D, R * C * D, D, 1);
         }
     }
@@ -487,14 +512,14 @@ struct ggdmc_engine {
         k_sweep_begin<<<L.npop, 128, (size_t)2 * C * sizeof(int), stream>>>(L, d_iter.p, sweep, decide_once, para_idx);
         ++launches;
         if (schedule == GGDMC_SCHEDULE_PARALLEL) {
-            k_propose<kProposeWarps><<<L.npop, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1);
+            k_propose<kProposeWarps><<<(L.npop * C + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1);
             timed_like(L, sweep, -1);
             const int n = L.npop * C;
             k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, ll_part.p, trials.d.nsplit);
             launches += 3;
         } else {
             for (int step = 0; step < C; ++step) {
-                k_propose<kProposeWarps><<<L.npop, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step);
+                k_propose<kProposeWarps><<<(L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step);
                 timed_like(L, sweep, step);
                 k_accept<<<(L.npop + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, step, ll_part.p, trials.d.nsplit);
                 launches += 3;
@@ -506,7 +531,7 @@ struct ggdmc_engine {
     void hyper_eval(int step)
     {
         Level &P = phi.L;
-        const size_t sm = (size_t)(6 * D + kHyperBlock / 32) * 8;
+        const size_t sm = (size_t)(6 * D + 2 * (kHyperBlock / 32)) * 8;
         dim3 grid(step < 0 ? R * C : R, H.nsplit, step < 0 ? 1 : 2);
         k_hyper<kHyperBlock><<<grid, kHyperBlock, sm, stream>>>(P, H, step, hpart.p);
         const int n = R * C * 2;
@@ -527,20 +552,27 @@ struct ggdmc_engine {
         k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), stream>>>(P, d_iter.p, sweep, decide_once, para_idx);
         ++launches;
         if (schedule == GGDMC_SCHEDULE_PARALLEL) {
-            k_propose<kProposeWarps><<<R, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, -1);
+            k_propose<kProposeWarps><<<(R * C + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, -1);
             hyper_eval(-1);
             const int n = R * C;
             k_phi_accept<<<(n + 127) / 128, 128, 0, stream>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur);
             launches += 2;
         } else {
             for (int step = 0; step < C; ++step) {
-                k_propose<kProposeWarps><<<R, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, step);
+                k_propose<kProposeWarps><<<(R + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, step);
                 hyper_eval(step);
                 k_phi_accept<<<(R + 127) / 128, 128, 0, stream>>>(P, d_iter.p, sweep, step, hsum.p, need_cur);
                 launches += 2;
             }
         }
         CUDA_CHECK(cudaGetLastError());
+    }
+
+    void phi_constants()
+    {
+        const int n = R * C * D;
+        k_phi_consts<<<(n + 127) / 128, 128, 0, stream>>>(phi.L, p_prior.d, D, phi_consts.p);
+        ++launches;
     }
 
     void store(LevelDev &lv)
@@ -562,6 +594,7 @@ struct ggdmc_engine {
                 for (int p = 0; p < D2; ++p) sweep_phi(p, 0, p);
             else
                 sweep_phi(0, 0, -1);
+            phi_constants();
             if (is_pblocked)
                 for (int p = 0; p < D; ++p) sweep_lba(p, 0, p);
             else
@@ -749,7 +782,7 @@ int ggdmc_b200_engine_time_likelihood(ggdmc_engine_t *engine, int32_t reps, floa
     const double saved = L.mig_prob;
     L.mig_prob = 0.0;
     k_sweep_begin<<<L.npop, 128, (size_t)2 * e.C * sizeof(int), e.stream>>>(L, e.d_iter.p, 0, 1, -1);
-    k_propose<kProposeWarps><<<L.npop, kProposeWarps * 32, (size_t)kProposeWarps * e.D * 8, e.stream>>>(L, e.d_iter.p, 0, -1);
+    k_propose<kProposeWarps><<<(L.npop * e.C + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, (size_t)kProposeWarps * e.D * 8, e.stream>>>(L, e.d_iter.p, 0, -1);
     L.mig_prob = saved;
     launch_like(L, e.model.d, e.trials.d, e.d_iter.p, 0, -1, e.ll_part.p, e.stream); // warm-up
     CUDA_CHECK(cudaEventRecord(e.ev0, e.stream));
@@ -881,7 +914,7 @@ int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *t
     DBuf<double> d_theta, d_out;
     d_theta.upload(theta, (size_t)n_theta * model->npar);
     d_out.alloc((size_t)n_theta * std::max(ntr, 1));
-    const size_t sm = ((size_t)M.d.n_cell * M.d.n_acc * sizeof(CellAcc) + (size_t)model->npar * 8 + (size_t)M.d.n_cell * M.d.n_acc + 15) & ~(size_t)15;
+    const size_t sm = ((size_t)M.d.n_cell * M.d.n_acc * sizeof(CellAcc) + (size_t)M.d.n_cell + 15) & ~(size_t)15;
     allow_smem(k_trial_logdens<128>, sm);
     if (ntr > 0) {
         dim3 grid(n_theta, std::min(64, (ntr + 127) / 128));

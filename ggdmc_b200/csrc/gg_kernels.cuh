@@ -63,6 +63,7 @@ struct Level {
     // prior of the moved vector
     DevPrior prior;
     const double *prior_ovr;          // phi state [n_rep][C][2*npar] when the prior's p0/p1 come from phi chain (src/de.cpp:599-600), else null
+    const double *ovr_consts;         // [n_rep][C][npar][2] = (1/sd, ln sqrt(2 pi) + ln sd + ln denom) of that phi state (k_phi_consts), or null
     // storage
     double *out_theta, *out_lp, *out_ll; // [npop][nmc][C][npar], [npop][nmc][C]
     int nmc, thin;
@@ -95,19 +96,17 @@ __device__ __forceinline__ double runif_from(double lo, double hi, double u)
 // block-wide sum of one double per thread (warp shuffles, then one shared-memory pass)
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK>
-__device__ __forceinline__ double block_sum(double v, double *scratch /* [BLOCK/32] */)
+__device__ __forceinline__ double block_sum(double v, double *scratch /* [BLOCK/32], not otherwise in use */)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
     if (lane == 0) scratch[w] = v;
     __syncthreads();
     double r = 0.0;
-    if (w == 0) {
-        r = (lane < BLOCK / 32) ? scratch[lane] : 0.0;
+    if (threadIdx.x == 0) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+        for (int i = 0; i < BLOCK / 32; ++i) r += scratch[i];
     }
     return r; // valid in thread 0
 }
@@ -238,55 +237,93 @@ __device__ __forceinline__ double sum_arma_order(const double *v, int n)
     return a1 + a2;
 }
 
+// Per (replicate, phi chain, parameter) constants of the phi-driven truncated-normal prior, so the
+// subject level does not redo 2 Phi + 2 log per parameter per subject (the reference re-runs
+// tnorm_class::set_parameters for every element, @hdr/prior.h:349).  NaN marks "use the generic path".
+__global__ void k_phi_consts(Level P, DevPrior like, int D, double *consts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = P.npop * P.nchain * D;
+    if (i >= n) return;
+    const int d = i % D, rc = i / D;
+    const double *phi = P.theta + (size_t)rc * 2 * D;
+    const double m = phi[d], sd = phi[D + d];
+    double inv = 0.0, K = NAN;
+    if (like.dist[d] == 1 && like.log_p[d] != 0 && sd > 0.0 && isfinite(sd) && isfinite(m)) {
+        const double den = pnorm5(like.upper[d], m, sd, true) - pnorm5(like.lower[d], m, sd, true);
+        inv = 1.0 / sd;
+        K = kLnSqrt2Pi + log(sd) + log(den);
+    }
+    consts[2 * (size_t)i] = inv;
+    consts[2 * (size_t)i + 1] = K;
+}
+
+// One warp per (population, sweep position).
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t *d_iter, int sweep, int step)
 {
     extern __shared__ double sm_prop[]; // [WARPS][npar] prior terms scratch
-    const int p = blockIdx.x, C = L.nchain, D = L.npar;
+    const int C = L.nchain, D = L.npar;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS + w;
+    int p, k;
+    if (step < 0) {
+        p = g / C;
+        k = g - p * C;
+    } else {
+        p = g;
+        k = step;
+    }
+    if (p >= L.npop) return;
     const uint32_t iter = *d_iter;
     const int mode = L.mode[p];
     const int para_idx = L.para[p];
     const int nsteps = mode ? L.mig_n[p] : C;
+    if (k >= nsteps) return;
     double *scratch = sm_prop + w * D;
-    const int k_begin = step < 0 ? w : step, k_end = step < 0 ? nsteps : (step < nsteps ? step + 1 : 0);
-    const int k_stride = step < 0 ? WARPS : 1;
-    if (step >= 0 && w != 0) return;
-    for (int k = k_begin; k < k_end; k += k_stride) {
-        int src, tgt, c0 = 0, c1 = 0;
-        if (mode) {
-            src = L.mig_list[p * C + k];
-            tgt = L.mig_list[p * C + ((k + 1 == nsteps) ? 0 : k + 1)];
+    int src, tgt, c0 = 0, c1 = 0;
+    if (mode) {
+        src = L.mig_list[p * C + k];
+        tgt = L.mig_list[p * C + ((k + 1 == nsteps) ? 0 : k + 1)];
+    } else {
+        src = k;
+        tgt = k;
+    }
+    DrawAddr a = make_addr(L, p, iter, sweep, src);
+    if (!mode) pick_partners(a, C, src, lane, c0, c1);
+    const double *th = L.theta + ((size_t)p * C + src) * D;
+    const double *t0 = L.theta + ((size_t)p * C + c0) * D;
+    const double *t1 = L.theta + ((size_t)p * C + c1) * D;
+    double *pr = L.prop + ((size_t)p * C + src) * D;
+    const size_t rc = (size_t)(p % L.n_rep) * C + src;
+    const double *ovr = L.prior_ovr ? L.prior_ovr + rc * 2 * D : nullptr;
+    const double *oc = (ovr && L.ovr_consts) ? L.ovr_consts + rc * 2 * D : nullptr;
+    for (int d = lane; d < D; d += 32) {
+        double x = th[d];
+        const bool moved = para_idx >= 0 ? (d == para_idx) : (d < L.nmove);
+        if (moved) {
+            double u = draw_uniform(a, U_NOISE, (uint32_t)d);
+            double noise = runif_from(-L.rp, L.rp, u);
+            double inc = mode ? noise : __dadd_rn(noise, __dmul_rn(L.gamma, __dsub_rn(t0[d], t1[d])));
+            x = __dadd_rn(x, inc);
+        }
+        pr[d] = x;
+        const double lo = L.prior.lower[d], up = L.prior.upper[d];
+        double v;
+        const double K = oc ? oc[2 * d + 1] : NAN;
+        if (K == K) { // phi-driven truncated normal, log scale: -(ln sqrt(2 pi) + z^2/2 + ln sd) - ln denom
+            const double z = (x - ovr[d]) * oc[2 * d];
+            v = (x < lo || x > up) ? -INFINITY : -(0.5 * z * z + K);
         } else {
-            src = k;
-            tgt = k;
-        }
-        DrawAddr a = make_addr(L, p, iter, sweep, src);
-        if (!mode) pick_partners(a, C, src, lane, c0, c1);
-        const double *th = L.theta + ((size_t)p * C + src) * D;
-        const double *t0 = L.theta + ((size_t)p * C + c0) * D;
-        const double *t1 = L.theta + ((size_t)p * C + c1) * D;
-        double *pr = L.prop + ((size_t)p * C + src) * D;
-        const double *ovr = L.prior_ovr ? L.prior_ovr + ((size_t)(p % L.n_rep) * C + src) * 2 * D : nullptr;
-        for (int d = lane; d < D; d += 32) {
-            double x = th[d];
-            const bool moved = para_idx >= 0 ? (d == para_idx) : (d < L.nmove);
-            if (moved) {
-                double u = draw_uniform(a, U_NOISE, (uint32_t)d);
-                double noise = runif_from(-L.rp, L.rp, u);
-                double inc = mode ? noise : __dadd_rn(noise, __dmul_rn(L.gamma, __dsub_rn(t0[d], t1[d])));
-                x = __dadd_rn(x, inc);
-            }
-            pr[d] = x;
             const double q0 = ovr ? ovr[d] : L.prior.p0[d], q1 = ovr ? ovr[D + d] : L.prior.p1[d];
-            scratch[d] = dprior1(L.prior.dist[d], x, q0, q1, L.prior.lower[d], L.prior.upper[d], L.prior.log_p[d] != 0);
+            v = dprior1(L.prior.dist[d], x, q0, q1, lo, up, L.prior.log_p[d] != 0);
         }
-        __syncwarp();
-        if (lane == 0) {
-            L.prop_lp[p * C + src] = sum_arma_order(scratch, D);
-            L.target[p * C + src] = tgt;
-        }
-        __syncwarp();
+        scratch[d] = v;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        L.prop_lp[p * C + src] = sum_arma_order(scratch, D);
+        L.target[p * C + src] = tgt;
     }
 }
 
@@ -328,37 +365,46 @@ struct LogProd {
     __device__ __forceinline__ double value() const { return fma((double)e, kLn2Hi, fma((double)e, kLn2Lo, log(m))) + extra; }
 };
 
-// Builds the (cell, accumulator) table of one parameter vector in shared memory.
+// Builds the (cell, accumulator) table of one parameter vector in shared memory: thread k fills
+// entry (cell, column) = (k / n_acc, k % n_acc); the thread of column 0 also decides the cell's
+// validity (@hdr/lba.h:121-146: invalid when ANY accumulator has A, b, sd_v, st0 or t0 < 0 or
+// b < A).  One barrier at the end.
 template <int BLOCK>
-__device__ __forceinline__ void build_cell_table(const DevModel &M, const double *theta_s, CellAcc *ent, uint8_t *bad,
-                                                 const DrawAddr &addr)
+__device__ __forceinline__ void build_cell_table(const DevModel &M, const double *__restrict__ theta, CellAcc *ent,
+                                                 uint8_t *cell_bad, const DrawAddr &addr)
 {
     const int n = M.n_cell * M.n_acc, na = M.n_acc;
     for (int k = threadIdx.x; k < n; k += BLOCK) {
         const int c = k / na, j = k - c * na;
-        const int *src = M.param_src + (size_t)c * 6 * na + j;
+        const int *src = M.param_src + (size_t)c * 6 * na;
         double v[6];
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
-            int s = src[r * na];
-            v[r] = s >= 0 ? theta_s[s] : M.const_val[-1 - s];
+            const int s = src[r * na + j];
+            v[r] = s >= 0 ? theta[s] : M.const_val[-1 - s];
         }
         double u = 0.0;
         if (v[4] != 0.0) u = draw_uniform(addr, U_ST0, (uint32_t)k);
-        bad[k] = cellacc_build(ent[k], v[0], v[1], v[2], v[3], v[4], v[5], M.posdrift[j] != 0, u) ? 1 : 0;
-    }
-    __syncthreads();
-    // a cell is invalid when any of its accumulators is (@hdr/lba.h:121-146); fold into bad[c*na]
-    for (int c = threadIdx.x; c < M.n_cell; c += BLOCK) {
-        uint8_t b = 0;
-        for (int j = 0; j < na; ++j) b |= bad[c * na + j];
-        bad[c * na] = b;
+        bool bad = cellacc_build(ent[k], v[0], v[1], v[2], v[3], v[4], v[5], M.posdrift[j] != 0, u);
+        if (j == 0) {
+            for (int jj = 1; jj < na; ++jj) {
+                double w[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const int s = src[r * na + jj];
+                    w[r] = s >= 0 ? theta[s] : M.const_val[-1 - s];
+                }
+                const double b = w[0] + w[1];
+                bad |= (w[0] < 0.0) || (b < 0.0) || (b < w[0]) || (w[3] < 0.0) || (w[4] < 0.0) || (w[5] < 0.0);
+            }
+            cell_bad[c] = bad ? 1 : 0;
+        }
     }
     __syncthreads();
 }
 
-template <int NACC, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_like(Level L, DevModel M, TrialData T, const uint32_t *d_iter, int sweep, int step,
+template <int NACC, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, TrialData T, const uint32_t *d_iter, int sweep, int step,
                                                 double *ll_part /* [npop][C][nsplit] */)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -387,14 +433,11 @@ __global__ void __launch_bounds__(BLOCK) k_like(Level L, DevModel M, TrialData T
         return;
     }
     CellAcc *ent = reinterpret_cast<CellAcc *>(sm_raw);
-    double *theta_s = reinterpret_cast<double *>(ent + M.n_cell * na);
-    double *red = theta_s + D;
+    double *red = reinterpret_cast<double *>(ent + M.n_cell * na);
     uint8_t *bad = reinterpret_cast<uint8_t *>(red + BLOCK / 32);
     const double *th = L.prop + ((size_t)p * C + chain) * D;
-    for (int d = threadIdx.x; d < D; d += BLOCK) theta_s[d] = th[d];
-    __syncthreads();
     DrawAddr addr = make_addr(L, p, *d_iter, sweep, chain);
-    build_cell_table<BLOCK>(M, theta_s, ent, bad, addr);
+    build_cell_table<BLOCK>(M, th, ent, bad, addr);
 
     const int t_end = min(ntr, t_begin + T.chunk);
     const double *rt = T.rt + T.offset[s];
@@ -402,18 +445,17 @@ __global__ void __launch_bounds__(BLOCK) k_like(Level L, DevModel M, TrialData T
     LogProd acc;
     acc.init();
     // two trials per thread per pass: one 16-byte RT load + one 4-byte cell load (subjects are padded
-    // to a multiple of 8 trials with cell = 0xFFFF)
+    // to a multiple of 8 trials with cell = 0xFFFF); the pair is processed by a rolled loop so the
+    // hot loop body stays small enough for the instruction cache
     for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
         const double2 r2 = __ldg(reinterpret_cast<const double2 *>(rt + t));
         const ushort2 c2 = __ldg(reinterpret_cast<const ushort2 *>(cl + t));
-        {
-            const int c = c2.x;
-            double pdf = bad[c * na] ? kFloor : n1pdf<NACC>(r2.x, ent + c * na, na);
-            acc.mul(pdf);
-        }
-        if (t + 1 < t_end) {
-            const int c = c2.y;
-            double pdf = bad[c * na] ? kFloor : n1pdf<NACC>(r2.y, ent + c * na, na);
+        const int nh = (t + 1 < t_end) ? 2 : 1;
+#pragma unroll 1
+        for (int h = 0; h < nh; ++h) {
+            const int c = h ? c2.y : c2.x;
+            const double r = h ? r2.y : r2.x;
+            double pdf = bad[c] ? kFloor : n1pdf<NACC>(r, ent + c * na, na);
             acc.mul(pdf);
         }
     }
@@ -432,15 +474,12 @@ __global__ void __launch_bounds__(BLOCK) k_trial_logdens(DevModel M, const doubl
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int na = M.n_acc, D = M.npar, k = blockIdx.x;
     CellAcc *ent = reinterpret_cast<CellAcc *>(sm_raw);
-    double *theta_s = reinterpret_cast<double *>(ent + M.n_cell * na);
-    uint8_t *bad = reinterpret_cast<uint8_t *>(theta_s + D);
-    for (int d = threadIdx.x; d < D; d += BLOCK) theta_s[d] = theta[(size_t)k * D + d];
-    __syncthreads();
+    uint8_t *bad = reinterpret_cast<uint8_t *>(ent + M.n_cell * na);
     DrawAddr addr = {0, 0, 0, 0, 0};
-    build_cell_table<BLOCK>(M, theta_s, ent, bad, addr);
+    build_cell_table<BLOCK>(M, theta + (size_t)k * D, ent, bad, addr);
     for (int t = blockIdx.y * BLOCK + threadIdx.x; t < ntr; t += gridDim.y * BLOCK) {
         const int c = cl[t];
-        double pdf = bad[c * na] ? kFloor : n1pdf<0>(rt[t], ent + c * na, na);
+        double pdf = bad[c] ? kFloor : n1pdf<0>(rt[t], ent + c * na, na);
         out[(size_t)k * ntr + t] = log(pdf);
     }
 }
@@ -559,7 +598,7 @@ __global__ void __launch_bounds__(BLOCK) k_hyper(Level L, HyperArgs H, int step,
         }
     }
     double vc = block_sum<BLOCK>(sum_c, red);
-    double vp = block_sum<BLOCK>(sum_p, red);
+    double vp = block_sum<BLOCK>(sum_p, red + BLOCK / 32);
     if (threadIdx.x == 0) {
         double *o = hpart + (((size_t)r * C + c) * 2) * H.nsplit + split;
         o[0] = vc;

@@ -148,16 +148,25 @@ def run_hyper(p_prior: PriorTable, h_prior: PriorTable, data_theta: np.ndarray, 
     return out
 
 
+def alloc_hier_outputs(S: int, R: int, nmc: int, nchain: int, npar: int, touch: bool = False):
+    """Output arrays for :func:`run_hier`: (phi PopSamples, [subject PopSamples]).  All subjects live in
+    one allocation, so the engine returns them with a single device->host copy per array."""
+    mk = np.zeros if touch else np.empty
+    phi_out = PopSamples(mk((R, nmc, nchain, 2 * npar)), mk((R, nmc, nchain)), mk((R, nmc, nchain)))
+    big_t, big_lp, big_ll = mk((S, R, nmc, nchain, npar)), mk((S, R, nmc, nchain)), mk((S, R, nmc, nchain))
+    if touch:
+        for a in (big_t, big_lp, big_ll):
+            a.fill(0.0)
+    return phi_out, [PopSamples(big_t[s], big_lp[s], big_ll[s]) for s in range(S)]
+
+
 def run_hier(ct: CellTable, trials: Sequence[Trials], p_prior: PriorTable, h_prior: PriorTable, tuning: Tuning,
-             phi_start: PopState, subj_start: Sequence[PopState], progress=None):
-    """`run` of the reference: returns (phi PopSamples, [subject PopSamples])."""
+             phi_start: PopState, subj_start: Sequence[PopState], progress=None, out=None):
+    """`run` of the reference: returns (phi PopSamples, [subject PopSamples]).  `out` may carry
+    preallocated outputs from :func:`alloc_hier_outputs`."""
     m, t, p, h, cfg = _model(ct), _trials(trials), _prior(p_prior), _prior(h_prior), _config(tuning)
     R, S = len(tuning.seeds), len(trials)
-    phi_out = PopSamples.empty(R, tuning.nmc, tuning.nchain, h_prior.npar)
-    # one allocation for all subjects: adjacent per-subject arrays come back in a single device->host copy
-    big_t = np.empty((S, R, tuning.nmc, tuning.nchain, ct.npar))
-    big_lp, big_ll = np.empty((S, R, tuning.nmc, tuning.nchain)), np.empty((S, R, tuning.nmc, tuning.nchain))
-    subj_out = [PopSamples(big_t[s], big_lp[s], big_ll[s]) for s in range(S)]
+    phi_out, subj_out = out if out is not None else alloc_hier_outputs(S, R, tuning.nmc, tuning.nchain, ct.npar)
     starts = (B.StartT * S)(*[s.c() for s in subj_start])
     outs = (B.SamplesT * S)(*[o.c() for o in subj_out])
     pc, poc, err, cb = phi_start.c(), phi_out.c(), B.errbuf(), _progress(progress)
