@@ -267,8 +267,8 @@ int like_variant()
 {
     static int v = [] {
         const char *e = std::getenv("GGDMC_B200_LIKE_VARIANT");
-        int x = e ? std::atoi(e) : 1;
-        return (x < 0 || x > 3) ? 1 : x;
+        int x = e ? std::atoi(e) : 2;
+        return (x < 0 || x > 3) ? 2 : x;
     }();
     return v;
 }
@@ -299,7 +299,8 @@ void launch_like_n(const Level &L, const DevModel &M, const TrialData &T, const 
     case 0: launch_like_t<NACC, 128, 6>(L, M, T, d_iter, sweep, step, ll_part, st); break;
     case 2: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, ll_part, st); break;
     case 3: launch_like_t<NACC, 64, 16>(L, M, T, d_iter, sweep, step, ll_part, st); break;
-    default: launch_like_t<NACC, 128, 8>(L, M, T, d_iter, sweep, step, ll_part, st);
+    case 1: launch_like_t<NACC, 128, 8>(L, M, T, d_iter, sweep, step, ll_part, st); break;
+    default: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, ll_part, st);
     }
 }
 
