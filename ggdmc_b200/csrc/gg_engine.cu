@@ -333,6 +333,12 @@ struct ggdmc_engine {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // optional per-launch timing of the likelihood kernel (bench.py roofline)
+    // one DE-MCMC iteration captured as a CUDA graph (fixed launch sequence: every data-dependent
+    // decision is taken on the device); GGDMC_B200_NO_GRAPH=1 falls back to plain stream launches
+    bool use_graph = std::getenv("GGDMC_B200_NO_GRAPH") == nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t launches_per_iter = 0;
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
@@ -350,6 +356,8 @@ struct ggdmc_engine {
 
     ~ggdmc_engine()
     {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (graph) cudaGraphDestroy(graph);
         for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -617,12 +625,35 @@ struct ggdmc_engine {
         }
     }
 
+    // iteration() either as plain launches or as one graph launch
+    void step_once()
+    {
+        if (!use_graph || profile || h_iter == 0) { // the very first iteration runs uncaptured (one-off kernel attribute calls)
+            iteration();
+            return;
+        }
+        if (!graph_exec) {
+            const int64_t l0 = launches;
+            const uint32_t h0 = h_iter;
+            CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            iteration();
+            CUDA_CHECK(cudaStreamEndCapture(stream, &graph));
+            CUDA_CHECK(cudaGraphInstantiate(&graph_exec, graph, 0));
+            launches_per_iter = launches - l0;
+            launches = l0;
+            h_iter = h0;
+        }
+        CUDA_CHECK(cudaGraphLaunch(graph_exec, stream));
+        launches += launches_per_iter;
+        ++h_iter;
+    }
+
     void iterate(int n_iter, float *elapsed_ms, ggdmc_progress_fn progress, void *user, int report_length)
     {
         CUDA_CHECK(cudaSetDevice(device));
         CUDA_CHECK(cudaEventRecord(ev0, stream));
         for (int i = 0; i < n_iter; ++i) {
-            iteration();
+            step_once();
             if (progress && report_length > 0 && h_iter % (uint32_t)thin == 0) {
                 uint32_t stored = h_iter / (uint32_t)thin; // theta_phi::print_progress, @hdr/theta.h:76-85
                 if ((stored + 1) % (uint32_t)report_length == 0) progress((int32_t)(stored + 1), user);
@@ -647,7 +678,7 @@ struct ggdmc_engine {
         for (int i = 0; i < n_iter; ++i) {
             CUDA_CHECK(cudaMemsetAsync(flush.p, i & 0xff, flush_bytes, stream));
             CUDA_CHECK(cudaEventRecord(ev[2 * i], stream));
-            iteration();
+            step_once();
             CUDA_CHECK(cudaEventRecord(ev[2 * i + 1], stream));
         }
         CUDA_CHECK(cudaStreamSynchronize(stream));

@@ -68,13 +68,30 @@ class HierWorkload:
         return int(sum(len(t.rt) for t in self.trials))
 
 
-def hierarchical(name: str, model_k: int, n_subject: int, n_trial: int, n_replicate: int = 1, data_seed: int = 20260101,
-                 subject_begin: int = 0, subject_end: Optional[int] = None, start_seed: int = 1234) -> HierWorkload:
-    """Build subjects [subject_begin, subject_end) of an n_subject-subject hierarchical workload.
+def shard_bounds(n_subject: int, rank: int, world: int):
+    """Subjects [begin, end) owned by `rank`: contiguous, sizes differ by at most one."""
+    return rank * n_subject // world, (rank + 1) * n_subject // world
 
-    Data and start states of a subject depend only on (data_seed, global subject index), so every
-    rank of a sharded run builds exactly its slice of the same global problem.
-    """
+
+@dataclass
+class PopulationShard:
+    """CPU-side description of subjects [subject_begin, subject_end) of a hierarchical problem."""
+
+    spec: ModelSpec
+    subject_begin: int
+    subject_end: int
+    true_theta: np.ndarray  # [S_local, npar]
+    trials: List[Trials]
+    nchain: int
+    phi0: np.ndarray  # [R, C, 2 npar]  (identical on every shard)
+    subj0: np.ndarray  # [S_local, R, C, npar]
+
+
+def build_population(model_k: int, n_subject: int, n_trial: int, n_replicate: int = 1, data_seed: int = 20260101,
+                     subject_begin: int = 0, subject_end: Optional[int] = None, start_seed: int = 1234) -> PopulationShard:
+    """Synthetic data + start values (no GPU).  Everything about a subject depends only on
+    (seed, GLOBAL subject index) and the phi start only on the seed, so the shards built by the
+    ranks of a multi-GPU run are exactly the slices of the single-GPU problem."""
     spec = load_model(model_k)
     ct = spec.ct
     subject_end = n_subject if subject_end is None else subject_end
@@ -86,25 +103,30 @@ def hierarchical(name: str, model_k: int, n_subject: int, n_trial: int, n_replic
         th = synth.rtnorm(spec.pop_mean, spec.pop_scale, 0.0, rng)
         thetas.append(th)
         trials.append(synth.simulate_subject(ct, spec.node_1_index, th, n_trial, rng))
-    thetas = np.stack(thetas)
-    # phi start: replicated on every rank -> seeded without the rank
+    thetas = np.stack(thetas) if thetas else np.zeros((0, D))
     prng = np.random.default_rng([start_seed, 0xF1])
     center = np.concatenate([spec.pop_mean, spec.pop_scale])
-    phi0 = center[None, None, :] * (1.0 + 0.05 * prng.standard_normal((R, C, 2 * D)))
-    phi0 = np.abs(phi0)
+    phi0 = np.abs(center[None, None, :] * (1.0 + 0.05 * prng.standard_normal((R, C, 2 * D))))
     subj0 = np.empty((len(trials), R, C, D))
     for i, s in enumerate(range(subject_begin, subject_end)):
         srng = np.random.default_rng([start_seed, s])
         subj0[i] = np.abs(thetas[i][None, None, :] * (1.0 + 0.05 * srng.standard_normal((R, C, D))))
-    # log prior / log likelihood of the start states, on the GPU
-    S = len(trials)
+    return PopulationShard(spec, subject_begin, subject_end, thetas, trials, C, phi0, subj0)
+
+
+def hierarchical(name: str, model_k: int, n_subject: int, n_trial: int, n_replicate: int = 1, data_seed: int = 20260101,
+                 subject_begin: int = 0, subject_end: Optional[int] = None, start_seed: int = 1234) -> HierWorkload:
+    """build_population + log prior / log likelihood of the start states, evaluated on the GPU."""
+    sh = build_population(model_k, n_subject, n_trial, n_replicate, data_seed, subject_begin, subject_end, start_seed)
+    spec, ct, trials, phi0, subj0, C = sh.spec, sh.spec.ct, sh.trials, sh.phi0, sh.subj0, sh.nchain
+    R, D, S = n_replicate, ct.npar, len(sh.trials)
     ll = E.sumloglike(ct, trials, subj0.reshape(S, R * C, D)).reshape(S, R, C)
     ph = np.broadcast_to(phi0.reshape(1, R * C, 2 * D), (S, R * C, 2 * D)).reshape(S * R * C, 2 * D)
     lp = E.sumlogprior(spec.p_prior, subj0.reshape(S * R * C, D), np.ascontiguousarray(ph[:, :D]),
                        np.ascontiguousarray(ph[:, D:])).reshape(S, R, C)
     phi_lp = E.sumlogprior(spec.h_prior, phi0.reshape(R * C, 2 * D)).reshape(R, C)
     phi_ll = lp.sum(axis=0)  # local subjects only; refreshed (and all-reduced) by the first phi step anyway
-    return HierWorkload(name, spec, thetas, trials, C, E.PopState(phi0, phi_lp, phi_ll),
+    return HierWorkload(name, spec, sh.true_theta, trials, C, E.PopState(phi0, phi_lp, phi_ll),
                         [E.PopState(subj0[i], lp[i], ll[i]) for i in range(S)])
 
 
