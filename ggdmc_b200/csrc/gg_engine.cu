@@ -39,6 +39,23 @@ void require(bool ok, const char *msg)
     if (!ok) throw Error(GGDMC_ERR_ARG, msg);
 }
 
+// Device buffers come from the device's default stream-ordered memory pool with an unlimited release
+// threshold: the first run* call pays for the allocations, later calls in the same process reuse the
+// pooled memory (the reference re-creates all of its C++ objects on every .Call as well, but malloc is
+// cheap there; cudaMalloc / cudaFree are not).  All pool operations are ordered on the legacy default
+// stream; engines synchronise it once after construction.
+inline void pool_setup(int device)
+{
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[device] = true;
+}
+
 template <class T>
 struct DBuf { // device buffer
     T *p = nullptr;
@@ -46,20 +63,29 @@ struct DBuf { // device buffer
     DBuf() = default;
     DBuf(const DBuf &) = delete;
     DBuf &operator=(const DBuf &) = delete;
-    ~DBuf() { if (p) cudaFree(p); }
+    ~DBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFreeAsync(p, 0);
+        p = nullptr;
+    }
     void alloc(size_t count)
     {
-        if (p) { cudaFree(p); p = nullptr; }
+        release();
         n = count;
-        if (count) CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+        if (count) CUDA_CHECK(cudaMallocAsync(&p, count * sizeof(T), 0));
     }
-    void zero() { if (n) CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T))); }
+    void zero() { if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), 0)); }
     void upload(const T *h, size_t count)
     {
         alloc(count);
-        if (count) CUDA_CHECK(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+        if (count) CUDA_CHECK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, 0));
     }
-    void upload(const std::vector<T> &h) { upload(h.data(), h.size()); }
+    void upload(const std::vector<T> &h)
+    {
+        upload(h.data(), h.size());
+        CUDA_CHECK(cudaStreamSynchronize(0)); // the vector may die right after this call
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -172,10 +198,14 @@ struct TrialsDev {
             const int64_t b = t->subject_offset[s], e = t->subject_offset[s + 1];
             require(e >= b && e - b < (int64_t)1 << 31, "bad subject_offset");
             const int n = (int)(e - b);
-            std::vector<int> idx(n);
-            std::iota(idx.begin(), idx.end(), 0);
-            for (int i = 0; i < n; ++i) require(t->cell[b + i] < n_cell, "cell index out of range");
-            std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return t->cell[b + x] < t->cell[b + y]; });
+            // stable counting sort by cell (dmi@data usually arrives grouped by cell already)
+            std::vector<int> idx(n), start((size_t)n_cell + 1, 0);
+            for (int i = 0; i < n; ++i) {
+                require(t->cell[b + i] < n_cell, "cell index out of range");
+                ++start[t->cell[b + i] + 1];
+            }
+            for (int c = 0; c < n_cell; ++c) start[c + 1] += start[c];
+            for (int i = 0; i < n; ++i) idx[start[t->cell[b + i]]++] = i;
             off[s] = pos;
             h_count[s] = n;
             max_count = std::max(max_count, n);
@@ -239,13 +269,14 @@ int pick_device(int requested)
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0)
         throw Error(GGDMC_ERR_CUDA, "no CUDA device: ggdmc_b200 has no CPU fallback");
+    int cur = requested;
     if (requested >= 0) {
         require(requested < n, "device ordinal out of range");
         CUDA_CHECK(cudaSetDevice(requested));
-        return requested;
+    } else {
+        CUDA_CHECK(cudaGetDevice(&cur));
     }
-    int cur = 0;
-    CUDA_CHECK(cudaGetDevice(&cur));
+    pool_setup(cur);
     return cur;
 }
 
@@ -356,6 +387,7 @@ struct ggdmc_engine {
 
     ~ggdmc_engine()
     {
+        if (stream) cudaStreamSynchronize(stream); // buffers go back to the pool right after this
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
         for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
@@ -390,6 +422,7 @@ struct ggdmc_engine {
         // starts[i] holds [R][C][D_] for item i (subject or phi); device population p = i * R + r,
         // so item i's block is one contiguous copy
         const size_t CD = (size_t)C * D_, blk = (size_t)R * CD, blk1 = (size_t)R * C;
+        CUDA_CHECK(cudaStreamSynchronize(0)); // pool allocations (ordered on the default stream) are now usable on `stream`
         std::vector<double> th((size_t)n_items * blk), lp((size_t)n_items * blk1), ll(lp.size());
         for (int i = 0; i < n_items; ++i) {
             require(starts[i].theta && starts[i].lp && starts[i].ll, "null start state");
@@ -443,6 +476,7 @@ struct ggdmc_engine {
             L.ovr_consts = phi_consts.p;
             setup_hyper(subj.theta.p, C * D, R * C * D, D, 1);
         }
+        CUDA_CHECK(cudaStreamSynchronize(0));
     }
 
     void create_hyper(const ggdmc_prior_t *pp, const ggdmc_prior_t *hp, const double *data_theta, int n_subject,
@@ -465,6 +499,7 @@ struct ggdmc_engine {
         P.nmove = std::min(D2, cfg->nparameter);
         init_level_state(phi, start, 1, D2);
         setup_hyper(hyper_data.p, 0, D, 0, 0);
+        CUDA_CHECK(cudaStreamSynchronize(0));
     }
 
     void setup_hyper(const double *x, int rep_stride, int subj_stride, int chain_stride, int need_cur)
@@ -673,6 +708,7 @@ struct ggdmc_engine {
         CUDA_CHECK(cudaSetDevice(device));
         DBuf<unsigned char> flush;
         flush.alloc(flush_bytes);
+        CUDA_CHECK(cudaStreamSynchronize(0));
         std::vector<cudaEvent_t> ev((size_t)2 * n_iter);
         for (auto &e : ev) CUDA_CHECK(cudaEventCreate(&e));
         for (int i = 0; i < n_iter; ++i) {

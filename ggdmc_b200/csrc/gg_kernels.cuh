@@ -349,18 +349,27 @@ struct LogProd {
     int e;
     double extra; // log of factors that are 0, subnormal, inf or NaN (rare)
     __device__ __forceinline__ void init() { m = 1.0; e = 0; extra = 0.0; }
+    // x finite and >= 0 (fast-path densities): a zero factor makes the product 0
+    __device__ __forceinline__ void mul_fast(double x)
+    {
+        const long long b = __double_as_longlong(x);
+        const int ex = (int)(b >> 52);
+        if (ex == 0) {
+            extra = -INFINITY;
+        } else {
+            m *= __longlong_as_double((b & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll);
+            const long long mb = __double_as_longlong(m);
+            e += ex - 1023 + (int)(mb >> 52) - 1023;
+            m = __longlong_as_double((mb & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll);
+        }
+    }
+    // any x
     __device__ __forceinline__ void mul(double x)
     {
-        long long b = __double_as_longlong(x);
-        int ex = (int)((b >> 52) & 0x7ff);
-        if ((unsigned)(ex - 1) < 0x7feu && b > 0) {
-            m *= __longlong_as_double((b & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll);
-            long long mb = __double_as_longlong(m);
-            e += ex - 1023 + (int)((mb >> 52) & 0x7ff) - 1023;
-            m = __longlong_as_double((mb & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll);
-        } else {
-            extra += log(x);
-        }
+        const long long b = __double_as_longlong(x);
+        const int ex = (int)((b >> 52) & 0x7ff);
+        if ((unsigned)(ex - 1) < 0x7feu && b > 0) mul_fast(x);
+        else extra += log(x);
     }
     __device__ __forceinline__ double value() const { return fma((double)e, kLn2Hi, fma((double)e, kLn2Lo, log(m))) + extra; }
 };
@@ -385,8 +394,9 @@ __device__ __forceinline__ void build_cell_table(const DevModel &M, const double
         }
         double u = 0.0;
         if (v[4] != 0.0) u = draw_uniform(addr, U_ST0, (uint32_t)k);
-        bool bad = cellacc_build(ent[k], v[0], v[1], v[2], v[3], v[4], v[5], M.posdrift[j] != 0, u);
-        if (j == 0) {
+        cellacc_build(ent[k], v[0], v[1], v[2], v[3], v[4], v[5], M.posdrift[j] != 0, u);
+        if (j == 0) { // this thread also classifies the cell from ALL of its accumulators
+            uint8_t cls = cell_class_update(kCellRegular, v[0], v[1], v[2], v[3], v[4], v[5]);
             for (int jj = 1; jj < na; ++jj) {
                 double w[6];
 #pragma unroll
@@ -394,10 +404,9 @@ __device__ __forceinline__ void build_cell_table(const DevModel &M, const double
                     const int s = src[r * na + jj];
                     w[r] = s >= 0 ? theta[s] : M.const_val[-1 - s];
                 }
-                const double b = w[0] + w[1];
-                bad |= (w[0] < 0.0) || (b < 0.0) || (b < w[0]) || (w[3] < 0.0) || (w[4] < 0.0) || (w[5] < 0.0);
+                cls = cell_class_update(cls, w[0], w[1], w[2], w[3], w[4], w[5]);
             }
-            cell_bad[c] = bad ? 1 : 0;
+            cell_bad[c] = cls;
         }
     }
     __syncthreads();
@@ -444,9 +453,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, Trial
     const uint16_t *cl = T.cell + T.offset[s];
     LogProd acc;
     acc.init();
-    // two trials per thread per pass: one 16-byte RT load + one 4-byte cell load (subjects are padded
-    // to a multiple of 8 trials with cell = 0xFFFF); the pair is processed by a rolled loop so the
-    // hot loop body stays small enough for the instruction cache
+    // Hot loop.  Two trials per thread per pass: one 16-byte RT load + one 4-byte cell load (subjects are
+    // padded to a multiple of 8 trials with cell = 0xFFFF); the pair is processed by a rolled loop so the
+    // loop body stays small.  Only fast-path trials (regular cell, rt > t0) are evaluated here; anything
+    // else is left to the cold loop below, which keeps every rare branch -- and its registers -- out of
+    // the code the FP64 pipe spends its time in.
+    bool leftovers = false;
     for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
         const double2 r2 = __ldg(reinterpret_cast<const double2 *>(rt + t));
         const ushort2 c2 = __ldg(reinterpret_cast<const ushort2 *>(cl + t));
@@ -455,8 +467,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, Trial
         for (int h = 0; h < nh; ++h) {
             const int c = h ? c2.y : c2.x;
             const double r = h ? r2.y : r2.x;
-            double pdf = bad[c] ? kFloor : n1pdf<NACC>(r, ent + c * na, na);
-            acc.mul(pdf);
+            const CellAcc *e = ent + c * na;
+            if (bad[c] == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) acc.mul_fast(n1pdf_fast<NACC>(r, e, na));
+            else leftovers = true;
+        }
+    }
+    if (leftovers) { // cold loop: invalid / generic cells and trials with rt <= t0
+        for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
+            const int nh = (t + 1 < t_end) ? 2 : 1;
+            for (int h = 0; h < nh; ++h) {
+                const int c = cl[t + h];
+                const double r = rt[t + h];
+                const CellAcc *e = ent + c * na;
+                const uint8_t cls = bad[c];
+                if (cls == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) continue; // done in the hot loop
+                acc.mul(cls == kCellInvalid ? kFloor : n1pdf_generic_body<NACC>(r, e, na));
+            }
         }
     }
     double v = block_sum<BLOCK>(acc.value(), red);
@@ -479,8 +505,7 @@ __global__ void __launch_bounds__(BLOCK) k_trial_logdens(DevModel M, const doubl
     build_cell_table<BLOCK>(M, theta + (size_t)k * D, ent, bad, addr);
     for (int t = blockIdx.y * BLOCK + threadIdx.x; t < ntr; t += gridDim.y * BLOCK) {
         const int c = cl[t];
-        double pdf = bad[c] ? kFloor : n1pdf<0>(rt[t], ent + c * na, na);
-        out[(size_t)k * ntr + t] = log(pdf);
+        out[(size_t)k * ntr + t] = log(n1pdf_any<0>(bad[c], rt[t], ent + c * na, na));
     }
 }
 

@@ -11,6 +11,7 @@
 #pragma once
 #include "gg_math.cuh"
 #include "gg_fastmath.cuh"
+#include <stdint.h>
 
 namespace gg {
 
@@ -50,9 +51,17 @@ GG_HD double rcp_time(double dt)
     return dt == 0.0 ? INFINITY : r;
 }
 
-// density of one trial whose cell's table row is e[0 .. n_acc)
+// Cell classes decided once per (chain, cell) when the table is built.
+enum : uint8_t {
+    kCellRegular = 0,  // all parameters finite, A >= 1e-10 and sd_v > 0 for every accumulator: fast path
+    kCellInvalid = 1,  // validate_parameters() fails: every trial has density 1e-10 (@hdr/likelihood.h:105)
+    kCellGeneric = 2   // anything else (A < 1e-10 point-mass branch, sd_v == 0, NaN / inf parameters)
+};
+
+// density of one trial whose cell's table row is e[0 .. n_acc): the reference's arithmetic with all of
+// its branches and NaN rules (lba_class::d / p, @hdr/lba.h:213-248, 286-345)
 template <int NACC>
-GG_HD double n1pdf(double rt, const CellAcc *e, int n_acc_rt)
+GG_HD double n1pdf_generic_body(double rt, const CellAcc *e, int n_acc_rt)
 {
     const int n_acc = NACC > 0 ? NACC : n_acc_rt;
     double t0a = e[0].t0a;
@@ -75,7 +84,6 @@ GG_HD double n1pdf(double rt, const CellAcc *e, int n_acc_rt)
         }
         if (isnan(pdf)) pdf = kFloor; // lba.h:247
     }
-#pragma unroll
     for (int j = 1; j < n_acc; ++j) { // p(), lba.h:286-345
         const double b = e[j].b, A = e[j].A, mv = e[j].mean_v, sv = e[j].sd_v;
         if (e[j].t0a != t0a) {
@@ -102,6 +110,77 @@ GG_HD double n1pdf(double rt, const CellAcc *e, int n_acc_rt)
         if (isnan(pdf)) pdf = kFloor; // :342
     }
     return pdf;
+}
+
+// Can the fast path take this trial?  Needs rt > t0 for every accumulator (then every z is finite).
+template <int NACC>
+GG_HD bool n1pdf_fast_ok(double rt, const CellAcc *e, int n_acc_rt)
+{
+    const int n_acc = NACC > 0 ? NACC : n_acc_rt;
+    bool ok = (rt - e[0].t0a) > 0.0;
+#pragma unroll
+    for (int j = 1; j < n_acc; ++j) ok = ok && ((rt - e[j].t0a) > 0.0);
+    return ok;
+}
+
+// Fast path for a trial of a REGULAR cell with n1pdf_fast_ok(): same formulas as the generic body,
+// but with finite parameters, A >= 1e-10, sd_v > 0 and rt > t0 the point-mass branches and every NaN
+// rule are dead code and every z is finite.
+template <int NACC>
+GG_HD double n1pdf_fast(double rt, const CellAcc *e, int n_acc_rt)
+{
+    const int n_acc = NACC > 0 ? NACC : n_acc_rt;
+    double t0a = e[0].t0a;
+    double dt = rt - t0a;
+    double rdt = fm::rcp_pos(dt);
+    double pdf;
+    {
+        const double b = e[0].b, A = e[0].A, mv = e[0].mean_v, sv = e[0].sd_v;
+        const double rts = e[0].inv_sdv * rdt, tv = mv * dt;
+        const PhiPair n1 = fm::norm_pair_finite((b - tv) * rts);
+        const PhiPair n2 = fm::norm_pair_finite(((b - A) - tv) * rts);
+        const double t1 = mv * (n1.cdf - n2.cdf);
+        const double t2 = sv * (n2.pdf - n1.pdf);
+        pdf = fmax((t1 + t2) * (e[0].inv_A * e[0].inv_denom), kFloor);
+    }
+#pragma unroll
+    for (int j = 1; j < n_acc; ++j) {
+        const double b = e[j].b, A = e[j].A, mv = e[j].mean_v, sv = e[j].sd_v;
+        if (e[j].t0a != t0a) {
+            t0a = e[j].t0a;
+            dt = rt - t0a;
+            rdt = fm::rcp_pos(dt);
+        }
+        const double ts = sv * dt, rts = e[j].inv_sdv * rdt, tv = mv * dt;
+        const double x1 = b - tv, x2 = x1 - A;
+        const PhiPair n1 = fm::norm_pair_finite(x1 * rts);
+        const PhiPair n2 = fm::norm_pair_finite(x2 * rts);
+        const double s = x2 * n2.cdf - x1 * n1.cdf + ts * (n2.pdf - n1.pdf);
+        double cdf = (1.0 + s * e[j].inv_A) * e[j].inv_denom;
+        cdf = cdf < kFloor ? kFloor : (1.0 < cdf ? 1.0 : cdf);
+        pdf = pdf * (1.0 - cdf);
+    }
+    return pdf;
+}
+
+// density of any trial of any cell class (used outside the hot loop)
+template <int NACC>
+GG_HD double n1pdf_any(uint8_t cls, double rt, const CellAcc *e, int n_acc)
+{
+    if (cls == kCellInvalid) return kFloor;
+    if (cls == kCellRegular && n1pdf_fast_ok<NACC>(rt, e, n_acc)) return n1pdf_fast<NACC>(rt, e, n_acc);
+    return n1pdf_generic_body<NACC>(rt, e, n_acc);
+}
+
+// class of a cell from the raw parameters of all its accumulators (v = A, B, mean_v, sd_v, st0, t0)
+GG_HD uint8_t cell_class_update(uint8_t cls, double A, double B, double mean_v, double sd_v, double st0, double t0)
+{
+    const double b = A + B;
+    if ((A < 0.0) || (b < 0.0) || (b < A) || (sd_v < 0.0) || (st0 < 0.0) || (t0 < 0.0)) return kCellInvalid;
+    if (cls == kCellInvalid) return cls;
+    const bool regular = (A >= kFloor) && (sd_v > 0.0) && isfinite(A) && isfinite(b) && isfinite(mean_v) && isfinite(sd_v) &&
+                         isfinite(st0) && isfinite(t0);
+    return regular ? cls : (uint8_t)kCellGeneric;
 }
 
 } // namespace gg

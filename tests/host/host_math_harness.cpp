@@ -10,12 +10,15 @@ extern "C" {
 int hm_lba_cell(const double *P, int n_acc, const unsigned char *posdrift, const double *rt, int n, double *out)
 {
     gg::CellAcc e[16];
-    bool bad = false;
-    for (int j = 0; j < n_acc; ++j)
-        bad |= gg::cellacc_build(e[j], P[0 * n_acc + j], P[1 * n_acc + j], P[2 * n_acc + j], P[3 * n_acc + j],
-                                 P[4 * n_acc + j], P[5 * n_acc + j], posdrift[j] != 0, 0.0);
-    for (int i = 0; i < n; ++i) out[i] = bad ? gg::kFloor : gg::n1pdf<0>(rt[i], e, n_acc);
-    return bad ? 0 : 1;
+    uint8_t cls = gg::kCellRegular;
+    for (int j = 0; j < n_acc; ++j) {
+        gg::cellacc_build(e[j], P[0 * n_acc + j], P[1 * n_acc + j], P[2 * n_acc + j], P[3 * n_acc + j], P[4 * n_acc + j],
+                          P[5 * n_acc + j], posdrift[j] != 0, 0.0);
+        cls = gg::cell_class_update(cls, P[0 * n_acc + j], P[1 * n_acc + j], P[2 * n_acc + j], P[3 * n_acc + j], P[4 * n_acc + j],
+                                    P[5 * n_acc + j]);
+    }
+    for (int i = 0; i < n; ++i) out[i] = gg::n1pdf_any<0>(cls, rt[i], e, n_acc);
+    return cls;
 }
 double hm_pnorm_std(double z) { return gg::pnorm_std(z); }
 double hm_dnorm_std(double z) { return gg::dnorm_std(z); }
