@@ -22,11 +22,11 @@ struct CellAcc {
 // Entry (cell, column j) of the table.  P* are the raw core parameters of that column
 // (A, B, mean_v, sd_v, st0, t0); u_st0 is the uniform of `t0 + st0 * U` (@hdr/lba.h:117).
 // Returns true when this accumulator makes the cell INVALID (@hdr/lba.h:121-146).
-GG_HD bool cellacc_build(CellAcc &e, double A, double B, double mean_v, double sd_v, double st0, double t0,
+GG_HD void cellacc_build(CellAcc &e, double A, double B, double mean_v, double sd_v, double st0, double t0,
                          bool posdrift, double u_st0)
 {
     double b = A + B; // design_light.h:336-340: row B += row A
-    double denom = posdrift ? fmax(pnorm_std(mean_v / sd_v), kFloor) : 1.0; // lba.h:112-115
+    double denom = posdrift ? fmax(fm::norm_pair(mean_v / sd_v).cdf, kFloor) : 1.0; // lba.h:112-115
     e.b = b;
     e.A = A;
     e.mean_v = mean_v;
@@ -35,7 +35,6 @@ GG_HD bool cellacc_build(CellAcc &e, double A, double B, double mean_v, double s
     e.inv_sdv = 1.0 / sd_v;
     e.inv_A = 1.0 / A;
     e.inv_denom = 1.0 / denom;
-    return (A < 0.0) || (b < 0.0) || (b < A) || (sd_v < 0.0) || (st0 < 0.0) || (t0 < 0.0);
 }
 
 typedef fm::Pair PhiPair;
