@@ -1,0 +1,253 @@
+// ggdmc_b200 -- R glue: the three .Call routines of ggdmc, re-implemented on top of the C ABI.
+//
+// Drop this file into ggdmc's src/ in place of de.cpp / de2R.cpp (keep RcppExports.cpp and
+// type_casting.h's new_posterior), add `PKG_LIBS += -L<repo>/ggdmc_b200 -lggdmc_b200` to
+// src/Makevars and -I<repo>/include to PKG_CPPFLAGS.  It exports the same three functions
+//     run_subject(config_r, dmi, samples), run_hyper(config_r, dmi, samples), run(config_r, dmis, samples)
+// (src/de2R.cpp:8-171), so R/RcppExports.R, R/sampling.R and every user script stay unchanged.
+//
+// This file cannot be compiled in the build image (no R, Rcpp or Armadillo there); the same
+// flattening rules are implemented and tested in Python (ggdmc_b200/model.py, api.py), which is the
+// executable specification of what this file does.
+//
+// [[Rcpp::depends(Rcpp)]]
+#include <Rcpp.h>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "ggdmc_b200.h"
+
+namespace {
+
+const char *kCore[6] = {"A", "B", "mean_v", "sd_v", "st0", "t0"}; // @hdr/design_light.h:314-344 row order
+
+struct FlatModel {
+    std::vector<int32_t> param_src;
+    std::vector<double> const_val;
+    std::vector<uint8_t> posdrift;
+    std::vector<std::string> cell_names, pnames;
+    ggdmc_model_t c{};
+};
+
+// model_boolean + node_1_index + constants + pnames -> param_src
+FlatModel flatten_model(const Rcpp::S4 &dmi)
+{
+    Rcpp::S4 model = dmi.slot("model");
+    if (Rcpp::as<std::string>(model.slot("type")) != "lba") Rcpp::stop("Undefined model type");
+    FlatModel m;
+    std::vector<std::string> pxc = Rcpp::as<std::vector<std::string>>(model.slot("parameter_x_condition_names"));
+    m.pnames = Rcpp::as<std::vector<std::string>>(model.slot("pnames"));
+    m.cell_names = Rcpp::as<std::vector<std::string>>(model.slot("cell_names"));
+    Rcpp::NumericVector constants = model.slot("constants");
+    std::vector<std::string> cnames = Rcpp::as<std::vector<std::string>>(constants.names());
+    m.const_val.assign(constants.begin(), constants.end());
+    Rcpp::LogicalVector mb = model.slot("model_boolean");
+    Rcpp::IntegerVector dim = mb.attr("dim");
+    const int n_cell = dim[0], n_pxc = dim[1], n_acc = dim[2];
+    Rcpp::IntegerMatrix n1 = dmi.slot("node_1_index");
+    Rcpp::LogicalVector pd = dmi.slot("is_positive_drift");
+    m.param_src.assign((size_t)n_cell * 6 * n_acc, 0);
+    for (int c = 0; c < n_cell; ++c)
+        for (int j = 0; j < n_acc; ++j) {
+            const int acc = n1(c, j);
+            for (int r = 0; r < 6; ++r) {
+                int found = -1;
+                for (int k = 0; k < n_pxc; ++k) {
+                    const std::string core = pxc[k].substr(0, pxc[k].find('.'));
+                    if (core == kCore[r] && mb[c + n_cell * (k + (size_t)n_pxc * acc)]) found = k;
+                }
+                if (found < 0) Rcpp::stop("model_boolean has no source for a core parameter");
+                int src = -1;
+                for (size_t q = 0; q < m.pnames.size(); ++q)
+                    if (m.pnames[q] == pxc[found]) src = (int)q;
+                if (src < 0)
+                    for (size_t q = 0; q < cnames.size(); ++q)
+                        if (cnames[q] == pxc[found]) src = -1 - (int)q;
+                m.param_src[((size_t)c * 6 + r) * n_acc + j] = src;
+            }
+        }
+    for (int j = 0; j < n_acc; ++j) m.posdrift.push_back(pd[j] ? 1 : 0);
+    m.c.n_acc = n_acc; m.c.n_cell = n_cell; m.c.npar = (int)m.pnames.size(); m.c.n_const = (int)m.const_val.size();
+    m.c.param_src = m.param_src.data(); m.c.const_val = m.const_val.data(); m.c.posdrift = m.posdrift.data();
+    return m;
+}
+
+struct FlatTrials {
+    std::vector<int64_t> offset{0};
+    std::vector<double> rt;
+    std::vector<uint16_t> cell;
+    ggdmc_trials_t c{};
+    void add(const Rcpp::S4 &dmi, const std::vector<std::string> &cell_names)
+    {
+        Rcpp::List data = dmi.slot("data"); // named list cell_name -> RT vector, empty cells omitted
+        std::vector<std::string> names = Rcpp::as<std::vector<std::string>>(data.names());
+        for (size_t i = 0; i < names.size(); ++i) {
+            size_t c = 0;
+            while (c < cell_names.size() && cell_names[c] != names[i]) ++c;
+            Rcpp::NumericVector v = data[i];
+            for (double x : v) { rt.push_back(x); cell.push_back((uint16_t)c); }
+        }
+        offset.push_back((int64_t)rt.size());
+    }
+    void finish()
+    {
+        c.n_subject = (int32_t)offset.size() - 1;
+        c.subject_offset = offset.data(); c.rt = rt.data(); c.cell = cell.data();
+    }
+};
+
+struct FlatPrior {
+    std::vector<double> p0, p1, lower, upper;
+    std::vector<int32_t> dist;
+    std::vector<uint8_t> log_p;
+    ggdmc_prior_t c{};
+    explicit FlatPrior(const Rcpp::List &pl)
+    {
+        for (R_xlen_t i = 0; i < pl.size(); ++i) {
+            Rcpp::List e = pl[i];
+            p0.push_back(Rcpp::as<double>(e["p0"])); p1.push_back(Rcpp::as<double>(e["p1"]));
+            lower.push_back(Rcpp::as<double>(e["lower"])); upper.push_back(Rcpp::as<double>(e["upper"]));
+            dist.push_back((int32_t)Rcpp::as<double>(e["dist_id"])); log_p.push_back(Rcpp::as<bool>(e["log_p"]) ? 1 : 0);
+        }
+        c.npar = (int32_t)p0.size(); c.p0 = p0.data(); c.p1 = p1.data(); c.lower = lower.data(); c.upper = upper.data();
+        c.dist = dist.data(); c.log_p = log_p.data();
+    }
+};
+
+struct FlatConfig {
+    uint64_t seed;
+    ggdmc_config_t c{};
+    explicit FlatConfig(const Rcpp::S4 &config_r)
+    {
+        Rcpp::S4 ti = config_r.slot("theta_input"), de = config_r.slot("de_input");
+        c.nmc = ti.slot("nmc"); c.nchain = ti.slot("nchain"); c.thin = ti.slot("thin");
+        c.report_length = Rcpp::as<bool>(ti.slot("is_print")) ? Rcpp::as<int>(ti.slot("report_length")) : 0;
+        c.pop_migration_prob = de.slot("pop_migration_prob"); c.sub_migration_prob = de.slot("sub_migration_prob");
+        c.gamma_precursor = de.slot("gamma_precursor"); c.rp = de.slot("rp");
+        c.is_hblocked = Rcpp::as<bool>(de.slot("is_hblocked")); c.is_pblocked = Rcpp::as<bool>(de.slot("is_pblocked"));
+        c.nparameter = de.slot("nparameter");
+        c.schedule = GGDMC_SCHEDULE_PARALLEL; // options(ggdmc.schedule = "reference") could select the other
+        c.n_replicate = 1; c.device = -1;
+        seed = (uint64_t)Rcpp::as<double>(config_r.slot("seed")); // config@seed -> Philox key (R/model-class.R:1514-1515)
+        c.seed = &seed;
+    }
+};
+
+// start state = last fully finite slice of the incoming `posterior` (fresh init: slice 1 only)
+struct StartState {
+    std::vector<double> theta, lp, ll;
+    ggdmc_start_t c{};
+    StartState(const Rcpp::S4 &samples)
+    {
+        Rcpp::NumericVector th = samples.slot("theta");
+        Rcpp::IntegerVector d = th.attr("dim");
+        const size_t npar = d[0], nchain = d[1], nmc = d[2], blk = npar * nchain;
+        size_t s = nmc;
+        while (s-- > 0) {
+            bool ok = true;
+            for (size_t i = 0; i < blk && ok; ++i) ok = R_finite(th[s * blk + i]);
+            if (ok) break;
+        }
+        Rcpp::NumericMatrix lpm = samples.slot("summed_log_prior"), llm = samples.slot("log_likelihoods");
+        theta.assign(th.begin() + s * blk, th.begin() + (s + 1) * blk); // npar x nchain col-major == [nchain][npar]
+        for (size_t k = 0; k < nchain; ++k) { lp.push_back(lpm(k, s)); ll.push_back(llm(k, s)); }
+        c.theta = theta.data(); c.lp = lp.data(); c.ll = ll.data();
+    }
+};
+
+void progress_cb(int32_t i, void *) { Rcpp::Rcout << i << " "; } // theta_phi::print_progress, @hdr/theta.h:76-85
+
+Rcpp::S4 make_posterior(const ggdmc_samples_t &s, const std::vector<std::string> &pnames, int thin)
+{
+    Rcpp::S4 out("posterior"); // src/type_casting.h:10-26
+    Rcpp::NumericVector th(s.theta, s.theta + (size_t)s.npar * s.nchain * s.nmc);
+    th.attr("dim") = Rcpp::IntegerVector::create(s.npar, s.nchain, s.nmc);
+    Rcpp::NumericMatrix lp(s.nchain, s.nmc, s.lp), ll(s.nchain, s.nmc, s.ll);
+    out.slot("theta") = th; out.slot("summed_log_prior") = lp; out.slot("log_likelihoods") = ll;
+    out.slot("start") = 1; out.slot("npar") = s.npar; out.slot("pnames") = pnames;
+    out.slot("nmc") = s.nmc; out.slot("thin") = thin; out.slot("nchain") = s.nchain;
+    return out;
+}
+
+struct OutBuf {
+    std::vector<double> theta, lp, ll;
+    ggdmc_samples_t c{};
+    OutBuf(int npar, int nchain, int nmc) : theta((size_t)npar * nchain * nmc), lp((size_t)nchain * nmc), ll((size_t)nchain * nmc)
+    {
+        c.npar = npar; c.nchain = nchain; c.nmc = nmc; c.theta = theta.data(); c.lp = lp.data(); c.ll = ll.data();
+    }
+};
+
+} // namespace
+
+// [[Rcpp::export]]
+Rcpp::S4 run_subject(const Rcpp::S4 &config_r, const Rcpp::S4 &dmi, const Rcpp::S4 &samples)
+{
+    Rcpp::S4 priors = config_r.slot("prior");
+    FlatModel m = flatten_model(dmi);
+    FlatTrials t; t.add(dmi, m.cell_names); t.finish();
+    FlatPrior pp(priors.slot("p_prior"));
+    FlatConfig cfg(config_r);
+    StartState st(samples);
+    OutBuf out(m.c.npar, cfg.c.nchain, cfg.c.nmc);
+    char err[256] = {0};
+    if (ggdmc_b200_run_subject(&m.c, &t.c, &pp.c, &cfg.c, &st.c, &out.c, progress_cb, nullptr, err)) Rcpp::stop(err);
+    Rcpp::Rcout << std::endl;
+    return make_posterior(out.c, m.pnames, cfg.c.thin);
+}
+
+// [[Rcpp::export]]
+Rcpp::S4 run_hyper(const Rcpp::S4 &config_r, const Rcpp::S4 &dmi, const Rcpp::S4 &samples)
+{
+    Rcpp::S4 priors = config_r.slot("prior");
+    FlatPrior pp(priors.slot("p_prior")), hp(priors.slot("h_prior"));
+    Rcpp::NumericMatrix data = dmi.slot("data"); // nsubject x npar
+    std::vector<double> x((size_t)data.nrow() * data.ncol());
+    for (int s = 0; s < data.nrow(); ++s)
+        for (int p = 0; p < data.ncol(); ++p) x[(size_t)s * data.ncol() + p] = data(s, p);
+    FlatConfig cfg(config_r);
+    StartState st(samples);
+    OutBuf out(hp.c.npar, cfg.c.nchain, cfg.c.nmc);
+    char err[256] = {0};
+    if (ggdmc_b200_run_hyper(&pp.c, &hp.c, x.data(), data.nrow(), &cfg.c, &st.c, &out.c, progress_cb, nullptr, err)) Rcpp::stop(err);
+    Rcpp::Rcout << std::endl;
+    Rcpp::S4 ti = config_r.slot("theta_input");
+    return make_posterior(out.c, Rcpp::as<std::vector<std::string>>(ti.slot("pnames")), cfg.c.thin);
+}
+
+// [[Rcpp::export]]
+Rcpp::List run(const Rcpp::S4 &config_r, const Rcpp::List &dmis, const Rcpp::List &samples)
+{
+    Rcpp::S4 priors = config_r.slot("prior");
+    FlatPrior pp(priors.slot("p_prior")), hp(priors.slot("h_prior"));
+    const int S = dmis.size();
+    FlatModel m = flatten_model(Rcpp::as<Rcpp::S4>(dmis[0]));
+    FlatTrials t;
+    for (int s = 0; s < S; ++s) t.add(Rcpp::as<Rcpp::S4>(dmis[s]), m.cell_names);
+    t.finish();
+    FlatConfig cfg(config_r);
+    Rcpp::List subj_r = samples["subject_theta"];
+    std::vector<StartState> starts;
+    std::vector<ggdmc_start_t> starts_c;
+    for (int s = 0; s < S; ++s) starts.emplace_back(Rcpp::as<Rcpp::S4>(subj_r[s]));
+    for (auto &s : starts) starts_c.push_back(s.c);
+    StartState phi_start(Rcpp::as<Rcpp::S4>(samples["phi"]));
+    // one allocation for all subjects: the engine then returns them in a single device->host copy
+    const size_t blk = (size_t)m.c.npar * cfg.c.nchain * cfg.c.nmc, blk1 = (size_t)cfg.c.nchain * cfg.c.nmc;
+    std::vector<double> big_t(blk * S), big_lp(blk1 * S), big_ll(blk1 * S);
+    std::vector<ggdmc_samples_t> outs(S);
+    for (int s = 0; s < S; ++s) {
+        outs[s].npar = m.c.npar; outs[s].nchain = cfg.c.nchain; outs[s].nmc = cfg.c.nmc;
+        outs[s].theta = big_t.data() + s * blk; outs[s].lp = big_lp.data() + s * blk1; outs[s].ll = big_ll.data() + s * blk1;
+    }
+    OutBuf phi_out(hp.c.npar, cfg.c.nchain, cfg.c.nmc);
+    char err[256] = {0};
+    if (ggdmc_b200_run(&m.c, &t.c, &pp.c, &hp.c, &cfg.c, &phi_start.c, starts_c.data(), &phi_out.c, outs.data(), progress_cb, nullptr, err))
+        Rcpp::stop(err);
+    Rcpp::Rcout << std::endl;
+    Rcpp::List theta_out(S);
+    for (int s = 0; s < S; ++s) theta_out[s] = make_posterior(outs[s], m.pnames, cfg.c.thin);
+    Rcpp::S4 ti = config_r.slot("theta_input");
+    return Rcpp::List::create(Rcpp::Named("phi") = make_posterior(phi_out.c, Rcpp::as<std::vector<std::string>>(ti.slot("pnames")), cfg.c.thin),
+                              Rcpp::Named("subject_theta") = theta_out);
+}

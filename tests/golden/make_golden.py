@@ -41,6 +41,12 @@ def main():
         ct = build_cell_table(dmi["model"], dmi["node_1_index"], dmi["is_positive_drift"])
         out.update(param_src=ct.param_src, const_val=ct.const_val, posdrift=ct.posdrift, pnames=np.array(ct.pnames),
                    cell_names=np.array(ct.cell_names))
+        # raw model slots, so the S4 -> cell-table flattening itself can be tested where /root/reference is absent
+        mdl = dmi["model"]
+        out["model_boolean"] = np.asarray(mdl["model_boolean"]).astype(bool)
+        out["pxc_names"] = np.array([str(s) for s in mdl["parameter_x_condition_names"]])
+        out["const_names"] = np.array([str(s) for s in mdl["constants"].attrs["names"]])
+        out["is_positive_drift"] = np.asarray(dmi["is_positive_drift"]).astype(bool)
         out["node_1_index"] = np.asarray(dmi["node_1_index"]).astype(np.int32)
         out["accumulators"] = np.array([str(a) for a in dmi["model"]["accumulators"]])
         # single subject
