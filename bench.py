@@ -130,7 +130,7 @@ def oracle_hier_sample(model_k: int, n_subject: int, n_trial: int, n_iter: int, 
         datas.append(od)
         pops.append(ob.OPop(x0, lp, ll, 2, 1 << 30))
     phi = ob.OPop(phi0, np.array([ob.sumlogprior(ohp, phi0[c]) for c in range(C)]), np.zeros(C), 2, 1 << 30)
-    de = ob.make_de(2 * D, C, pop_migration_prob=0.05, sub_migration_prob=0.05, jacobi=False)
+    de = ob.make_de(2 * D, C, pop_migration_prob=0.05, sub_migration_prob=0.05, jacobi=0)
     r = ob.make_rng(seed=seed)
     if n_warm:
         ob.run_hier(de, phi, pops, opp, ohp, om, datas, r, n_warm)
@@ -187,7 +187,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--schedule", default="parallel", choices=["parallel", "reference"])
+    ap.add_argument("--schedule", default="parallel", choices=["parallel", "reference", "simultaneous"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -247,7 +247,7 @@ def main():
 
     model_k, S, ntr, desc = WORKLOADS[args.workload]
     s0, s1 = W.shard_bounds(S, rank, world)
-    schedule = B.SCHEDULE_PARALLEL if args.schedule == "parallel" else B.SCHEDULE_REFERENCE
+    schedule = {"parallel": B.SCHEDULE_PARALLEL, "reference": B.SCHEDULE_REFERENCE, "simultaneous": B.SCHEDULE_SIMULTANEOUS}[args.schedule]
 
     fp64_peak = E.measure_fp64_tflops(local_rank) if rank == 0 else 0.0
 

@@ -23,7 +23,7 @@ c_u32p = C.POINTER(C.c_uint32)
 c_u64p = C.POINTER(C.c_uint64)
 
 OK, ERR_ARG, ERR_CUDA, ERR_COMM, ERR_CHAINS = 0, 1, 2, 3, 4
-SCHEDULE_REFERENCE, SCHEDULE_PARALLEL = 0, 1
+SCHEDULE_REFERENCE, SCHEDULE_PARALLEL, SCHEDULE_SIMULTANEOUS = 0, 1, 2
 
 
 class GgdmcError(RuntimeError):

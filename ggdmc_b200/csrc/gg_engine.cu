@@ -405,11 +405,12 @@ struct ggdmc_engine {
         require(cfg->nchain <= 65535, "nchain too large");
         require(cfg->nmc >= 1 && cfg->thin >= 1, "nmc and thin must be >= 1");
         require(cfg->n_replicate >= 1 && cfg->seed != nullptr, "need n_replicate >= 1 seeds");
-        require(cfg->schedule == GGDMC_SCHEDULE_REFERENCE || cfg->schedule == GGDMC_SCHEDULE_PARALLEL, "bad schedule");
+        require(cfg->schedule >= GGDMC_SCHEDULE_REFERENCE && cfg->schedule <= GGDMC_SCHEDULE_SIMULTANEOUS, "bad schedule");
         require(cfg->nparameter >= 1, "de_input nparameter must be >= 1");
         device = pick_device(cfg->device);
         R = cfg->n_replicate; C = cfg->nchain; nmc = cfg->nmc; thin = cfg->thin;
-        schedule = cfg->schedule; is_hblocked = cfg->is_hblocked; is_pblocked = cfg->is_pblocked;
+        schedule = (cfg->schedule == GGDMC_SCHEDULE_PARALLEL && cfg->nchain < 4) ? GGDMC_SCHEDULE_REFERENCE : cfg->schedule;
+        is_hblocked = cfg->is_hblocked; is_pblocked = cfg->is_pblocked;
         subject_begin = cfg->subject_begin;
         CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreate(&ev0));
@@ -557,15 +558,19 @@ struct ggdmc_engine {
         const size_t prop_sm = (size_t)kProposeWarps * D * 8;
         k_sweep_begin<<<L.npop, 128, (size_t)2 * C * sizeof(int), stream>>>(L, d_iter.p, sweep, decide_once, para_idx);
         ++launches;
-        if (schedule == GGDMC_SCHEDULE_PARALLEL) {
-            k_propose<kProposeWarps><<<(L.npop * C + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1);
-            timed_like(L, sweep, -1);
+        if (schedule != GGDMC_SCHEDULE_REFERENCE) {
             const int n = L.npop * C;
-            k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, ll_part.p, trials.d.nsplit);
-            launches += 3;
+            const int nhalf = schedule == GGDMC_SCHEDULE_PARALLEL ? 2 : 1;
+            for (int h = 0; h < nhalf; ++h) {
+                const int half = nhalf == 2 ? h : -1;
+                k_propose<kProposeWarps><<<(n + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1, half);
+                timed_like(L, sweep, -1);
+                k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, ll_part.p, trials.d.nsplit);
+                launches += 3;
+            }
         } else {
             for (int step = 0; step < C; ++step) {
-                k_propose<kProposeWarps><<<(L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step);
+                k_propose<kProposeWarps><<<(L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step, -1);
                 timed_like(L, sweep, step);
                 k_accept<<<(L.npop + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, step, ll_part.p, trials.d.nsplit);
                 launches += 3;
@@ -597,15 +602,19 @@ struct ggdmc_engine {
         const int need_cur = H.need_cur;
         k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), stream>>>(P, d_iter.p, sweep, decide_once, para_idx);
         ++launches;
-        if (schedule == GGDMC_SCHEDULE_PARALLEL) {
-            k_propose<kProposeWarps><<<(R * C + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, -1);
-            hyper_eval(-1);
+        if (schedule != GGDMC_SCHEDULE_REFERENCE) {
             const int n = R * C;
-            k_phi_accept<<<(n + 127) / 128, 128, 0, stream>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur);
-            launches += 2;
+            const int nhalf = schedule == GGDMC_SCHEDULE_PARALLEL ? 2 : 1;
+            for (int h = 0; h < nhalf; ++h) {
+                const int half = nhalf == 2 ? h : -1;
+                k_propose<kProposeWarps><<<(n + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, -1, half);
+                hyper_eval(-1);
+                k_phi_accept<<<(n + 127) / 128, 128, 0, stream>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur);
+                launches += 2;
+            }
         } else {
             for (int step = 0; step < C; ++step) {
-                k_propose<kProposeWarps><<<(R + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, step);
+                k_propose<kProposeWarps><<<(R + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, step, -1);
                 hyper_eval(step);
                 k_phi_accept<<<(R + 127) / 128, 128, 0, stream>>>(P, d_iter.p, sweep, step, hsum.p, need_cur);
                 launches += 2;
@@ -852,7 +861,7 @@ int ggdmc_b200_engine_time_likelihood(ggdmc_engine_t *engine, int32_t reps, floa
     const double saved = L.mig_prob;
     L.mig_prob = 0.0;
     k_sweep_begin<<<L.npop, 128, (size_t)2 * e.C * sizeof(int), e.stream>>>(L, e.d_iter.p, 0, 1, -1);
-    k_propose<kProposeWarps><<<(L.npop * e.C + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, (size_t)kProposeWarps * e.D * 8, e.stream>>>(L, e.d_iter.p, 0, -1);
+    k_propose<kProposeWarps><<<(L.npop * e.C + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, (size_t)kProposeWarps * e.D * 8, e.stream>>>(L, e.d_iter.p, 0, -1, -1);
     L.mig_prob = saved;
     launch_like(L, e.model.d, e.trials.d, e.d_iter.p, 0, -1, e.ll_part.p, e.stream); // warm-up
     CUDA_CHECK(cudaEventRecord(e.ev0, e.stream));

@@ -198,19 +198,21 @@ __device__ __forceinline__ void warp_min_keypos(int &key, int &pos)
     }
 }
 
-// get_chains(i, 2), src/de.cpp:54-60: the two smallest shuffle keys among the other chains
-__device__ __forceinline__ void pick_partners(const DrawAddr &a, int C, int i, int lane, int &c0, int &c1)
+// get_chains(i, 2), src/de.cpp:54-60: the two smallest shuffle keys among the candidate chains.
+// half < 0: candidates = every chain but i (the reference's rule); half = 0 / 1: candidates = the
+// chains of the OTHER parity (two-half PARALLEL schedule).
+__device__ __forceinline__ void pick_partners(const DrawAddr &a, int C, int i, int half, int lane, int &c0, int &c1)
 {
-    const int nother = C - 1;
+    const int ncand = half < 0 ? C - 1 : (C + half) / 2;
     const int INTMAX = 0x7fffffff;
     int k1 = INTMAX, p1 = INTMAX, k2 = INTMAX, p2 = INTMAX; // lane-local best two
-    for (int blk = lane; blk * 4 < nother; blk += 32) {
+    for (int blk = lane; blk * 4 < ncand; blk += 32) {
         U4 w = draw_block(a, U_PARTNER, (uint32_t)blk);
         uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             int j = blk * 4 + q;
-            if (j < nother) {
+            if (j < ncand) {
                 int k = shuffle_key(word_to_uniform(ws[q]));
                 if (k < k1 || (k == k1 && j < p1)) { k2 = k1; p2 = p1; k1 = k; p1 = j; }
                 else if (k < k2 || (k == k2 && j < p2)) { k2 = k; p2 = j; }
@@ -223,8 +225,13 @@ __device__ __forceinline__ void pick_partners(const DrawAddr &a, int C, int i, i
     int sk = (k1 == bk && p1 == bp) ? k2 : k1;
     int sp = (k1 == bk && p1 == bp) ? p2 : p1;
     warp_min_keypos(sk, sp);
-    c0 = bp + (bp >= i);
-    c1 = sp + (sp >= i);
+    if (half < 0) {
+        c0 = bp + (bp >= i);
+        c1 = sp + (sp >= i);
+    } else {
+        c0 = 2 * bp + (1 - half);
+        c1 = 2 * sp + (1 - half);
+    }
 }
 
 // prior_class::sumlogprior with arma::accu's two-accumulator order (@hdr/prior.h:469-476)
@@ -260,7 +267,7 @@ __global__ void k_phi_consts(Level P, DevPrior like, int D, double *consts)
 
 // One warp per (population, sweep position).
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t *d_iter, int sweep, int step)
+__global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t *d_iter, int sweep, int step, int half)
 {
     extern __shared__ double sm_prop[]; // [WARPS][npar] prior terms scratch
     const int C = L.nchain, D = L.npar;
@@ -280,6 +287,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t 
     const int para_idx = L.para[p];
     const int nsteps = mode ? L.mig_n[p] : C;
     if (k >= nsteps) return;
+    if (half >= 0 && (mode ? half != 0 : (k & 1) != half)) return; // half-sweeps: crossover by parity, migration whole in half 0
     double *scratch = sm_prop + w * D;
     int src, tgt, c0 = 0, c1 = 0;
     if (mode) {
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t 
         tgt = k;
     }
     DrawAddr a = make_addr(L, p, iter, sweep, src);
-    if (!mode) pick_partners(a, C, src, lane, c0, c1);
+    if (!mode) pick_partners(a, C, src, half, lane, c0, c1);
     const double *th = L.theta + ((size_t)p * C + src) * D;
     const double *t0 = L.theta + ((size_t)p * C + c0) * D;
     const double *t1 = L.theta + ((size_t)p * C + c1) * D;
@@ -539,6 +547,7 @@ __global__ void k_accept(Level L, const uint32_t *d_iter, int sweep, int step, c
     const double tmp_lp = L.prop_lp[p * C + src];
     const double cur = L.lp[p * C + tgt] + L.ll[p * C + tgt];     // src/de.cpp:121 / :189-190 / :577 / :656-657
     const double mh = exp((tmp_lp + tmp_ll) - cur);               // :147
+    L.target[p * C + src] = -1;                                    // proposal consumed
     if (isnan(mh)) return;                                         // :83-87, no draw
     DrawAddr a = make_addr(L, p, *d_iter, sweep, src);
     if (draw_uniform(a, U_ACCEPT, 0) < mh) {                       // :88
@@ -673,6 +682,7 @@ __global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int ste
     }
     const double cur = L.lp[r * C + tgt] + cur_ll;
     const double mh = exp((tmp_lp + tmp_ll) - cur);
+    L.target[r * C + src] = -1; // proposal consumed
     if (isnan(mh)) return;
     DrawAddr a = make_addr(L, r, *d_iter, sweep, src);
     if (draw_uniform(a, U_ACCEPT, 0) < mh) {

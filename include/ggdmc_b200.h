@@ -43,12 +43,19 @@ enum ggdmc_dist {
     GGDMC_CAUCHY = 5, GGDMC_UNIF = 6, GGDMC_NORM = 7
 };
 
-/* How the chains of one population are swept (DESIGN.md "Schedules").
- *   REFERENCE: chains updated in place one after another, exactly like src/de.cpp:119-150 /
- *              :167-194 (later chains see earlier chains' new states); populations run in parallel.
- *   PARALLEL : all chains of a sweep are proposed from the sweep-start state and accepted
- *              together (same target distribution, different trajectory). */
-enum ggdmc_schedule { GGDMC_SCHEDULE_REFERENCE = 0, GGDMC_SCHEDULE_PARALLEL = 1 };
+/* How the chains of one population are swept (DESIGN.md "Schedules").  Populations always run in
+ * parallel.
+ *   REFERENCE   : chains updated in place one after another, exactly like src/de.cpp:119-150 /
+ *                 :167-194 (later chains see earlier chains' new states).
+ *   PARALLEL    : (default) each crossover sweep is two half-sweeps: the even chains move together
+ *                 with difference partners drawn from the odd chains, then the odd chains with
+ *                 partners from the even ones.  The partners stand still while a half moves, so every
+ *                 half-sweep is an exact Metropolis update -- same target distribution as REFERENCE,
+ *                 different trajectory.  Needs nchain >= 4 (else REFERENCE is used).
+ *   SIMULTANEOUS: every chain proposed from the sweep-start state and accepted together: one launch
+ *                 per sweep, but only approximately invariant for small nchain.
+ * Migration sweeps move all selected chains at once in PARALLEL and SIMULTANEOUS. */
+enum ggdmc_schedule { GGDMC_SCHEDULE_REFERENCE = 0, GGDMC_SCHEDULE_PARALLEL = 1, GGDMC_SCHEDULE_SIMULTANEOUS = 2 };
 
 /* dmi@model + dmi@node_1_index + dmi@is_positive_drift, flattened (SURVEY.md A.1;
  * replaces design_class, @hdr/design_light.h:77-344).  One model is shared by all subjects. */

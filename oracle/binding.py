@@ -177,7 +177,7 @@ def make_rng(seed: Optional[int] = None, stream: Optional[np.ndarray] = None, bu
 
 
 def make_de(nparameter, nchain, pop_migration_prob=0.0, sub_migration_prob=0.0, gamma_precursor=2.38, rp=0.001,
-            is_hblocked=False, is_pblocked=False, jacobi=False) -> DE:
+            is_hblocked=False, is_pblocked=False, jacobi=0) -> DE:
     return DE(pop_migration_prob, sub_migration_prob, gamma_precursor, rp, int(is_hblocked), int(is_pblocked),
               int(nparameter), int(nchain), int(jacobi))
 

@@ -484,44 +484,62 @@ static void crossover_(const orc_de *de, orc_pop *t, const ctx_t *c, orc_rng *r,
     double *tmp = (double *)malloc(sizeof(double) * (size_t)np);
     double *snap_theta = NULL, *snap_lp = NULL, *snap_ll = NULL;
     const double *src = t->theta, *slp = t->lp, *sll = t->ll;
-    if (de->jacobi) {
+    int sched = de->jacobi;
+    int nhalf = (sched == 1) ? 2 : 1; /* 1: two half-sweeps (even chains, then odd chains) */
+    unsigned *cand = (unsigned *)malloc(sizeof(unsigned) * (size_t)nc * 2), *sh = cand + nc;
+    if (sched) {
         snap_theta = (double *)malloc(sizeof(double) * (size_t)nc * np);
         snap_lp = (double *)malloc(sizeof(double) * (size_t)nc * 2);
         snap_ll = snap_lp + nc;
-        memcpy(snap_theta, t->theta, sizeof(double) * (size_t)nc * np);
-        memcpy(snap_lp, t->lp, sizeof(double) * (size_t)nc);
-        memcpy(snap_ll, t->ll, sizeof(double) * (size_t)nc);
         src = snap_theta; slp = snap_lp; sll = snap_ll;
     }
-    for (int i = 0; i < nc; ++i) {
-        orc_addr base = {pop, iter, para_idx < 0 ? 0u : (unsigned)para_idx, (unsigned)i, 0, 0};
-        double cur_ll = sll[i];
-        if (c->kind == 2) { /* :397-398 refresh the hyper-likelihood of the current phi */
-            cur_ll = like_(c, src + (size_t)i * np, i, r, &base);
-            t->ll[i] = cur_ll;
+    for (int half = 0; half < nhalf; ++half) {
+        if (sched) { /* proposals of this (half-)sweep are made from its start state */
+            memcpy(snap_theta, t->theta, sizeof(double) * (size_t)nc * np);
+            memcpy(snap_lp, t->lp, sizeof(double) * (size_t)nc);
+            memcpy(snap_ll, t->ll, sizeof(double) * (size_t)nc);
         }
-        double cur = cur_ll + slp[i];
-        memcpy(tmp, src + (size_t)i * np, sizeof(double) * (size_t)np);
-        unsigned sub[2];
-        orc_get_chains(nc, i, 2, r, &base, sub);
-        const double *th0 = src + (size_t)sub[0] * np, *th1 = src + (size_t)sub[1] * np;
-        orc_addr a = base;
-        a.purpose = ORC_U_NOISE;
-        if (para_idx >= 0) {
-            a.slot = (unsigned)para_idx;
-            tmp[para_idx] += runif_(r, &a, -de->rp, de->rp) + gamma * (th0[para_idx] - th1[para_idx]);
-        } else {
-            for (int j = 0; j < nmove; ++j) {
-                a.slot = (unsigned)j;
-                tmp[j] += runif_(r, &a, -de->rp, de->rp) + gamma * (th0[j] - th1[j]);
+        for (int i = 0; i < nc; ++i) {
+            if (sched == 1 && (i & 1) != half) continue;
+            orc_addr base = {pop, iter, para_idx < 0 ? 0u : (unsigned)para_idx, (unsigned)i, 0, 0};
+            double cur_ll = sll[i];
+            if (c->kind == 2) { /* :397-398 refresh the hyper-likelihood of the current phi */
+                cur_ll = like_(c, src + (size_t)i * np, i, r, &base);
+                t->ll[i] = cur_ll;
             }
+            double cur = cur_ll + slp[i];
+            memcpy(tmp, src + (size_t)i * np, sizeof(double) * (size_t)np);
+            unsigned sub[2];
+            if (sched == 1) { /* partners only from the other half, which stands still during this half-sweep */
+                int n = 0;
+                for (int k = 0; k < nc; ++k)
+                    if ((k & 1) != half) cand[n++] = (unsigned)k;
+                shuffle_(cand, n, r, &base, ORC_U_PARTNER, sh);
+                sub[0] = sh[0];
+                sub[1] = sh[1];
+            } else {
+                orc_get_chains(nc, i, 2, r, &base, sub);
+            }
+            const double *th0 = src + (size_t)sub[0] * np, *th1 = src + (size_t)sub[1] * np;
+            orc_addr a = base;
+            a.purpose = ORC_U_NOISE;
+            if (para_idx >= 0) {
+                a.slot = (unsigned)para_idx;
+                tmp[para_idx] += runif_(r, &a, -de->rp, de->rp) + gamma * (th0[para_idx] - th1[para_idx]);
+            } else {
+                for (int j = 0; j < nmove; ++j) {
+                    a.slot = (unsigned)j;
+                    tmp[j] += runif_(r, &a, -de->rp, de->rp) + gamma * (th0[j] - th1[j]);
+                }
+            }
+            double tmp_lp = prior_(c, tmp, i);
+            double tmp_ll = like_(c, tmp, i, r, &base);
+            double mh = exp(tmp_lp + tmp_ll - cur);
+            accept_(t, i, tmp, tmp_lp, tmp_ll, mh, r, &base);
         }
-        double tmp_lp = prior_(c, tmp, i);
-        double tmp_ll = like_(c, tmp, i, r, &base);
-        double mh = exp(tmp_lp + tmp_ll - cur);
-        accept_(t, i, tmp, tmp_lp, tmp_ll, mh, r, &base);
     }
     free(tmp);
+    free(cand);
     free(snap_theta);
     free(snap_lp);
 }

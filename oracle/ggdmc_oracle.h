@@ -71,8 +71,11 @@ typedef struct {
     int is_hblocked, is_pblocked;
     int nparameter; /* de_input@nparameter: npar (1 level) or 2*npar (hierarchical) */
     int nchain;
-    int jacobi;     /* 0: reference order (chains swept in place, one after another);
-                       1: all chains of a sweep proposed from the sweep-start snapshot */
+    int jacobi;     /* schedule.  0: reference order (chains swept in place, one after another);
+                       1: two half-sweeps -- even chains move together with partners drawn from the odd
+                          chains, then the odd chains with partners from the even ones (migration: all
+                          selected chains at once);
+                       2: all chains of a sweep proposed at once from the sweep-start state */
 } orc_de;
 
 typedef struct {

@@ -15,7 +15,7 @@ from helpers import load_fixture, sane_starts
 
 pytestmark = pytest.mark.gpu
 
-SCHEDULES = [(B.SCHEDULE_PARALLEL, True), (B.SCHEDULE_REFERENCE, False)]
+SCHEDULES = [(B.SCHEDULE_PARALLEL, 1), (B.SCHEDULE_REFERENCE, 0), (B.SCHEDULE_SIMULTANEOUS, 2)]  # (engine schedule, oracle schedule)
 
 
 def subject_start(fx, od, oprior, nchain, rng, center=None, phi=None):
