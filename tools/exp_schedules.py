@@ -7,7 +7,7 @@ from ggdmc_b200 import _lib as B, engine as E
 from oracle import binding as ob
 from helpers import load_fixture, sane_starts
 from test_gpu_sampler import hier_setup
-from test_gpu_posterior import summaries
+from test_gpu_posterior import summaries  # noqa
 
 def rhat(x):
     n = x.shape[0]; cm = x.mean(0); W = x.var(0, ddof=1).mean(0); Bn = cm.var(0, ddof=1)
