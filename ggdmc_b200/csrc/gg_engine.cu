@@ -311,40 +311,41 @@ size_t like_smem(const DevModel &M, int block)
 }
 
 template <int NACC, int BLOCK, int MINB>
-void launch_like_t(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step,
+void launch_like_t(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
                    double *ll_part, cudaStream_t st)
 {
-    dim3 grid(step < 0 ? L.npop * L.nchain : L.npop, T.nsplit);
+    const int per_pop = step >= 0 ? 1 : (half < 0 ? L.nchain : (L.nchain + 1) / 2);
+    dim3 grid(L.npop * per_pop, T.nsplit);
     const size_t sm = like_smem(M, BLOCK);
     require(sm <= 220 * 1024, "cell table does not fit in shared memory");
     allow_smem(k_like<NACC, BLOCK, MINB>, sm);
-    k_like<NACC, BLOCK, MINB><<<grid, BLOCK, sm, st>>>(L, M, T, d_iter, sweep, step, ll_part);
+    k_like<NACC, BLOCK, MINB><<<grid, BLOCK, sm, st>>>(L, M, T, d_iter, sweep, step, half, ll_part);
     CUDA_CHECK(cudaGetLastError());
 }
 
 template <int NACC>
-void launch_like_n(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step,
+void launch_like_n(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
                    double *ll_part, cudaStream_t st)
 {
     switch (like_variant()) {
-    case 0: launch_like_t<NACC, 128, 6>(L, M, T, d_iter, sweep, step, ll_part, st); break;
-    case 2: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, ll_part, st); break;
-    case 3: launch_like_t<NACC, 64, 16>(L, M, T, d_iter, sweep, step, ll_part, st); break;
-    case 1: launch_like_t<NACC, 128, 8>(L, M, T, d_iter, sweep, step, ll_part, st); break;
-    case 4: launch_like_t<NACC, 32, 24>(L, M, T, d_iter, sweep, step, ll_part, st); break;
-    case 5: launch_like_t<NACC, 32, 32>(L, M, T, d_iter, sweep, step, ll_part, st); break;
-    default: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, ll_part, st);
+    case 0: launch_like_t<NACC, 128, 6>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    case 2: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    case 3: launch_like_t<NACC, 64, 16>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    case 1: launch_like_t<NACC, 128, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    case 4: launch_like_t<NACC, 32, 24>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    case 5: launch_like_t<NACC, 32, 32>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    default: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st);
     }
 }
 
-void launch_like(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step,
+void launch_like(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
                  double *ll_part, cudaStream_t st)
 {
     switch (M.n_acc) {
-    case 2: launch_like_n<2>(L, M, T, d_iter, sweep, step, ll_part, st); break;
-    case 3: launch_like_n<3>(L, M, T, d_iter, sweep, step, ll_part, st); break;
-    case 4: launch_like_n<4>(L, M, T, d_iter, sweep, step, ll_part, st); break;
-    default: launch_like_n<0>(L, M, T, d_iter, sweep, step, ll_part, st);
+    case 2: launch_like_n<2>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    case 3: launch_like_n<3>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    case 4: launch_like_n<4>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    default: launch_like_n<0>(L, M, T, d_iter, sweep, step, half, ll_part, st);
     }
 }
 
@@ -522,10 +523,10 @@ struct ggdmc_engine {
     }
 
     // likelihood launch, optionally bracketed by CUDA events on the launching stream
-    void timed_like(const Level &L, int sweep, int step)
+    void timed_like(const Level &L, int sweep, int step, int half)
     {
         if (!profile) {
-            launch_like(L, model.d, trials.d, d_iter.p, sweep, step, ll_part.p, stream);
+            launch_like(L, model.d, trials.d, d_iter.p, sweep, step, half, ll_part.p, stream);
             return;
         }
         if (prof_used + 2 > prof_ev.size()) {
@@ -536,7 +537,7 @@ struct ggdmc_engine {
             }
         }
         CUDA_CHECK(cudaEventRecord(prof_ev[prof_used], stream));
-        launch_like(L, model.d, trials.d, d_iter.p, sweep, step, ll_part.p, stream);
+        launch_like(L, model.d, trials.d, d_iter.p, sweep, step, half, ll_part.p, stream);
         CUDA_CHECK(cudaEventRecord(prof_ev[prof_used + 1], stream));
         prof_used += 2;
     }
@@ -564,14 +565,14 @@ struct ggdmc_engine {
             for (int h = 0; h < nhalf; ++h) {
                 const int half = nhalf == 2 ? h : -1;
                 k_propose<kProposeWarps><<<(n + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1, half);
-                timed_like(L, sweep, -1);
+                timed_like(L, sweep, -1, half);
                 k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, ll_part.p, trials.d.nsplit);
                 launches += 3;
             }
         } else {
             for (int step = 0; step < C; ++step) {
                 k_propose<kProposeWarps><<<(L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step, -1);
-                timed_like(L, sweep, step);
+                timed_like(L, sweep, step, -1);
                 k_accept<<<(L.npop + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, step, ll_part.p, trials.d.nsplit);
                 launches += 3;
             }
@@ -863,9 +864,9 @@ int ggdmc_b200_engine_time_likelihood(ggdmc_engine_t *engine, int32_t reps, floa
     k_sweep_begin<<<L.npop, 128, (size_t)2 * e.C * sizeof(int), e.stream>>>(L, e.d_iter.p, 0, 1, -1);
     k_propose<kProposeWarps><<<(L.npop * e.C + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, (size_t)kProposeWarps * e.D * 8, e.stream>>>(L, e.d_iter.p, 0, -1, -1);
     L.mig_prob = saved;
-    launch_like(L, e.model.d, e.trials.d, e.d_iter.p, 0, -1, e.ll_part.p, e.stream); // warm-up
+    launch_like(L, e.model.d, e.trials.d, e.d_iter.p, 0, -1, -1, e.ll_part.p, e.stream); // warm-up
     CUDA_CHECK(cudaEventRecord(e.ev0, e.stream));
-    for (int i = 0; i < reps; ++i) launch_like(L, e.model.d, e.trials.d, e.d_iter.p, 0, -1, e.ll_part.p, e.stream);
+    for (int i = 0; i < reps; ++i) launch_like(L, e.model.d, e.trials.d, e.d_iter.p, 0, -1, -1, e.ll_part.p, e.stream);
     CUDA_CHECK(cudaEventRecord(e.ev1, e.stream));
     CUDA_CHECK(cudaStreamSynchronize(e.stream));
     e.launches += 3 + reps;
@@ -1033,7 +1034,7 @@ int ggdmc_b200_sumloglike(const ggdmc_model_t *model, const ggdmc_trials_t *tria
     Level L{};
     L.npop = S; L.nchain = n_theta; L.npar = D; L.n_rep = 1; L.prop = d_theta.p; L.target = d_target.p;
     L.mode = d_mode.p; L.seed = d_seed.p;
-    launch_like(L, M.d, T.d, d_iter.p, 0, -1, d_part.p, 0);
+    launch_like(L, M.d, T.d, d_iter.p, 0, -1, -1, d_part.p, 0);
     std::vector<double> h(n * T.d.nsplit);
     CUDA_CHECK(cudaMemcpy(h.data(), d_part.p, h.size() * 8, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; ++i) {

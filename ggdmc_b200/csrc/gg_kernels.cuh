@@ -420,27 +420,12 @@ __device__ __forceinline__ void build_cell_table(const DevModel &M, const double
     __syncthreads();
 }
 
-template <int NACC, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, TrialData T, const uint32_t *d_iter, int sweep, int step,
-                                                double *ll_part /* [npop][C][nsplit] */)
+// sum-log-likelihood of ONE proposal (population p, chain) over one trial chunk, by the whole block
+template <int NACC, int BLOCK>
+__device__ __forceinline__ void like_one(const Level &L, const DevModel &M, const TrialData &T, uint32_t iter, int sweep, int p,
+                                         int chain, int split, double *ll_part, unsigned char *sm_raw)
 {
-    extern __shared__ __align__(16) unsigned char sm_raw[];
     const int C = L.nchain, D = L.npar, na = M.n_acc;
-    int p, chain;
-    if (step < 0) {
-        p = blockIdx.x / C;
-        chain = blockIdx.x - p * C;
-    } else {
-        p = blockIdx.x;
-        const int mode = L.mode[p];
-        if (mode) {
-            if (step >= L.mig_n[p]) return;
-            chain = L.mig_list[p * C + step];
-        } else
-            chain = step;
-    }
-    if (L.target[p * C + chain] < 0) return;
-    const int split = blockIdx.y;
     const int s = p / L.n_rep;
     const int ntr = T.count[s];
     const int t_begin = split * T.chunk;
@@ -453,7 +438,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, Trial
     double *red = reinterpret_cast<double *>(ent + M.n_cell * na);
     uint8_t *bad = reinterpret_cast<uint8_t *>(red + BLOCK / 32);
     const double *th = L.prop + ((size_t)p * C + chain) * D;
-    DrawAddr addr = make_addr(L, p, *d_iter, sweep, chain);
+    DrawAddr addr = make_addr(L, p, iter, sweep, chain);
     build_cell_table<BLOCK>(M, th, ent, bad, addr);
 
     const int t_end = min(ntr, t_begin + T.chunk);
@@ -497,6 +482,47 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, Trial
     if (threadIdx.x == 0) {
         *part = v;
         if (T.counter) atomicAdd(T.counter, (unsigned long long)(t_end - t_begin));
+    }
+}
+
+// Grid.  step >= 0 (REFERENCE schedule): block x = population, its chain is sweep position `step`.
+// step < 0, half < 0: block x = (population, chain).  step < 0, half = 0 / 1 (PARALLEL schedule): block x =
+// (population, slot) with (nchain + 1) / 2 slots; a crossover population evaluates chain 2 slot + half, a
+// migrating population (whole migration in half 0) its chains slot and slot + nslots.
+template <int NACC, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, TrialData T, const uint32_t *d_iter, int sweep, int step,
+                                                       int half, double *ll_part /* [npop][C][nsplit] */)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int C = L.nchain;
+    const uint32_t iter = *d_iter;
+    int p, chain0, stride = C, nchain_blk = 1; // this block evaluates chains chain0, chain0 + stride, ... (nchain_blk of them)
+    if (step >= 0) {
+        p = blockIdx.x;
+        chain0 = step;
+        if (L.mode[p]) {
+            if (step >= L.mig_n[p]) return;
+            chain0 = L.mig_list[p * C + step];
+        }
+    } else if (half < 0) {
+        p = blockIdx.x / C;
+        chain0 = blockIdx.x - p * C;
+    } else {
+        const int nslot = (C + 1) / 2;
+        p = blockIdx.x / nslot;
+        const int slot = blockIdx.x - p * nslot;
+        if (L.mode[p] == 0) {
+            chain0 = 2 * slot + half;
+        } else {
+            if (half != 0) return;
+            chain0 = slot;
+            stride = nslot;
+            nchain_blk = 2;
+        }
+    }
+    for (int i = 0, chain = chain0; i < nchain_blk && chain < C; ++i, chain += stride) {
+        if (L.target[p * C + chain] >= 0) like_one<NACC, BLOCK>(L, M, T, iter, sweep, p, chain, blockIdx.y, ll_part, sm_raw);
+        if (nchain_blk > 1) __syncthreads(); // shared table and reduction scratch are reused by the next chain
     }
 }
 
