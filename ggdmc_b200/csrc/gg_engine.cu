@@ -98,6 +98,7 @@ struct Nccl {
     int (*GetUniqueId)(UniqueId *) = nullptr;
     int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, Comm, cudaStream_t) = nullptr;
     int (*CommDestroy)(Comm) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     Comm comm = nullptr;
@@ -115,6 +116,7 @@ struct Nccl {
         GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy)
@@ -127,6 +129,97 @@ struct Nccl {
     }
 };
 Nccl g_nccl;
+
+// Peer-memory window for the fused reduce + exchange kernel (k_hyper_reduce_exchange).  Set up once per
+// communicator: every rank cudaMallocs a window, the CUDA IPC handles travel through one ncclAllGather,
+// every rank maps its peers' windows.  GGDMC_B200_NO_P2P=1 keeps the plain NCCL all-reduce instead.
+struct P2P {
+    bool ready = false;
+    void *base = nullptr;                 // local window
+    void *peer_base[kP2PMaxRanks] = {};   // mapped peer windows (own entry = base)
+    unsigned long long *seq = nullptr;
+    int *status = nullptr;
+    P2PWindow win{};
+    static size_t slots_bytes(int n_rank) { return (size_t)2 * n_rank * kP2PMaxN * sizeof(double); }
+    static size_t window_bytes(int n_rank) { return slots_bytes(n_rank) + (size_t)2 * kP2PMaxRanks * sizeof(unsigned long long); }
+
+    void setup(Nccl &nc)
+    {
+        if (std::getenv("GGDMC_B200_NO_P2P") || nc.n_rank > kP2PMaxRanks || !nc.AllGather) return;
+        const int n = nc.n_rank;
+        const size_t bytes = window_bytes(n);
+        if (cudaMalloc(&base, bytes) != cudaSuccess) { cudaGetLastError(); base = nullptr; return; }
+        cudaMemset(base, 0, bytes);
+        cudaIpcMemHandle_t mine;
+        int ok = cudaIpcGetMemHandle(&mine, base) == cudaSuccess ? 1 : 0;
+        // gather (ok flag + handle) of every rank
+        struct Msg { int ok; cudaIpcMemHandle_t h; };
+        Msg m{ok, mine};
+        Msg *d_in = nullptr, *d_all = nullptr;
+        std::vector<Msg> all(n);
+        CUDA_CHECK(cudaMalloc(&d_in, sizeof(Msg)));
+        CUDA_CHECK(cudaMalloc(&d_all, sizeof(Msg) * n));
+        CUDA_CHECK(cudaMemcpy(d_in, &m, sizeof(Msg), cudaMemcpyHostToDevice));
+        nc.check(nc.AllGather(d_in, d_all, sizeof(Msg), /*ncclInt8*/ 0, nc.comm, 0), "ncclAllGather");
+        CUDA_CHECK(cudaStreamSynchronize(0));
+        CUDA_CHECK(cudaMemcpy(all.data(), d_all, sizeof(Msg) * n, cudaMemcpyDeviceToHost));
+        cudaFree(d_in);
+        cudaFree(d_all);
+        bool good = true;
+        for (int r = 0; r < n; ++r) good = good && all[r].ok;
+        if (good) {
+            for (int r = 0; r < n && good; ++r) {
+                if (r == nc.rank) { peer_base[r] = base; continue; }
+                if (cudaIpcOpenMemHandle(&peer_base[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    good = false;
+                }
+            }
+        }
+        // everybody must agree, otherwise some ranks would wait on flags nobody raises
+        int *d_flag = nullptr, *d_flags = nullptr;
+        int mine_ok = good ? 1 : 0;
+        std::vector<int> oks(n);
+        CUDA_CHECK(cudaMalloc(&d_flag, sizeof(int)));
+        CUDA_CHECK(cudaMalloc(&d_flags, sizeof(int) * n));
+        CUDA_CHECK(cudaMemcpy(d_flag, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
+        nc.check(nc.AllGather(d_flag, d_flags, sizeof(int), 0, nc.comm, 0), "ncclAllGather");
+        CUDA_CHECK(cudaStreamSynchronize(0));
+        CUDA_CHECK(cudaMemcpy(oks.data(), d_flags, sizeof(int) * n, cudaMemcpyDeviceToHost));
+        cudaFree(d_flag);
+        cudaFree(d_flags);
+        for (int r = 0; r < n; ++r) good = good && oks[r];
+        if (!good) { teardown(nc.rank, n); return; }
+        CUDA_CHECK(cudaMalloc(&seq, sizeof(unsigned long long)));
+        CUDA_CHECK(cudaMalloc(&status, sizeof(int)));
+        CUDA_CHECK(cudaMemset(seq, 0, sizeof(unsigned long long)));
+        CUDA_CHECK(cudaMemset(status, 0, sizeof(int)));
+        for (int r = 0; r < n; ++r) {
+            win.slots[r] = reinterpret_cast<double *>(peer_base[r]);
+            win.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(peer_base[r]) + slots_bytes(n));
+        }
+        win.seq = seq; win.status = status; win.n_rank = n; win.rank = nc.rank;
+        ready = true;
+    }
+    void teardown(int rank, int n)
+    {
+        for (int r = 0; r < n; ++r)
+            if (r != rank && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
+        for (auto &p : peer_base) p = nullptr;
+        if (base) cudaFree(base);
+        if (seq) cudaFree(seq);
+        if (status) cudaFree(status);
+        base = nullptr; seq = nullptr; status = nullptr;
+        ready = false;
+    }
+    int timed_out()
+    {
+        int v = 0;
+        if (status) cudaMemcpy(&v, status, sizeof(int), cudaMemcpyDeviceToHost);
+        return v;
+    }
+};
+P2P g_p2p;
 
 // ---------------------------------------------------------------------------------------------
 // uploads
@@ -587,12 +680,17 @@ struct ggdmc_engine {
         dim3 grid(step < 0 ? R * C : R, H.nsplit, step < 0 ? 1 : 2);
         k_hyper<kHyperBlock><<<grid, kHyperBlock, sm, stream>>>(P, H, step, hpart.p);
         const int n = R * C * 2;
-        k_hyper_reduce<<<(n + 127) / 128, 128, 0, stream>>>(hpart.p, n, H.nsplit, hsum.p);
-        launches += 2;
-        if (kind == 2 && g_nccl.comm && g_nccl.n_rank > 1) {
-            // the one exchange of the path: partial sums over the local subjects -> sums over all subjects
-            g_nccl.check(g_nccl.AllReduce(hsum.p, hsum.p, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, g_nccl.comm, stream),
-                         "ncclAllReduce");
+        const bool multi = kind == 2 && g_nccl.comm && g_nccl.n_rank > 1;
+        if (multi && g_p2p.ready && n <= kP2PMaxN) {
+            // the one exchange of the path, fused with the local reduction (peer-memory stores over NVLink)
+            k_hyper_reduce_exchange<<<1, 256, 0, stream>>>(hpart.p, n, H.nsplit, hsum.p, g_p2p.win);
+            launches += 2;
+        } else {
+            k_hyper_reduce<<<(n + 127) / 128, 128, 0, stream>>>(hpart.p, n, H.nsplit, hsum.p);
+            launches += 2;
+            if (multi) // fallback: partial sums over the local subjects -> sums over all subjects by NCCL
+                g_nccl.check(g_nccl.AllReduce(hsum.p, hsum.p, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, g_nccl.comm, stream),
+                             "ncclAllReduce");
         }
     }
 
@@ -711,6 +809,7 @@ struct ggdmc_engine {
         CUDA_CHECK(cudaGetLastError());
         if (elapsed_ms) CUDA_CHECK(cudaEventElapsedTime(elapsed_ms, ev0, ev1));
         if (profile) collect_profile();
+        if (kind == 2 && g_p2p.ready && g_p2p.timed_out()) throw Error(GGDMC_ERR_COMM, "peer exchange timed out: a rank did not arrive");
     }
 
     // Timed iterations with an L2 flush (a memset larger than L2) before each one; only the iterations
@@ -1154,11 +1253,13 @@ int ggdmc_b200_comm_init(int32_t n_rank, int32_t rank, const uint8_t id[128], in
     g_nccl.check(g_nccl.CommInitRank(&g_nccl.comm, n_rank, u, rank), "ncclCommInitRank");
     g_nccl.n_rank = n_rank;
     g_nccl.rank = rank;
+    g_p2p.setup(g_nccl);
     GG_CATCH
 }
 
 void ggdmc_b200_comm_finalize(void)
 {
+    if (g_p2p.base) g_p2p.teardown(g_nccl.rank, g_nccl.n_rank);
     if (g_nccl.comm) {
         g_nccl.CommDestroy(g_nccl.comm);
         g_nccl.comm = nullptr;

@@ -676,6 +676,71 @@ __global__ void k_hyper_reduce(const double *hpart, int n, int nsplit, double *h
     hsum[i] = v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The one exchange of the path, fused with its reduction: sum over the LOCAL subjects (the nsplit
+// partials of k_hyper) and, in the same kernel, sum over the GPUs through peer memory on NVLink.
+//
+// Every rank owns a window  slots[2][n_rank][kP2PMaxN] doubles + flags[2][n_rank] u64  in its own
+// HBM, mapped into every peer with CUDA IPC.  Exchange number `seq` (parity b = seq & 1):
+//   1. thread i reduces value i and STORES it into slot [b][my_rank][i] of every rank's window
+//      (remote stores over NVLink, posted -- nobody waits on a load round trip)
+//   2. system-scope fence, then one flag store per peer: flags[b][my_rank] = seq
+//   3. wait until the local flags[b][*] all read `seq` (every peer's data has landed)
+//   4. thread i sums slots[b][0..n_rank)[i] in rank order -> identical bits on every rank
+// Parity double-buffering is enough: a rank can only start exchange seq + 2 after every peer has
+// raised its seq + 1 flag, i.e. after every peer finished reading exchange seq.
+// A bounded spin (about 2 s) sets *status instead of hanging the GPU if a peer never arrives.
+// ------------------------------------------------------------------------------------------------
+constexpr int kP2PMaxN = 4096;   // doubles per exchange (2 * nchain * n_replicate)
+constexpr int kP2PMaxRanks = 16;
+
+struct P2PWindow {
+    double *slots[kP2PMaxRanks];               // slots base of every rank's window (index = rank; own entry = local pointer)
+    unsigned long long *flags[kP2PMaxRanks];   // flags base of every rank's window
+    unsigned long long *seq;                   // local exchange counter (device memory)
+    int *status;                               // local: set to 1 on timeout
+    int n_rank, rank;
+};
+
+__global__ void __launch_bounds__(256) k_hyper_reduce_exchange(const double *hpart, int n, int nsplit, double *hsum, P2PWindow w)
+{
+    const unsigned long long seq = *w.seq + 1;
+    const int b = (int)(seq & 1ull);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = 0.0;
+        for (int k = 0; k < nsplit; ++k) v += hpart[(size_t)i * nsplit + k];
+        for (int q = 0; q < w.n_rank; ++q) w.slots[q][((size_t)b * w.n_rank + w.rank) * kP2PMaxN + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < w.n_rank) {
+        volatile unsigned long long *f = w.flags[threadIdx.x] + (size_t)b * kP2PMaxRanks + w.rank;
+        *f = seq;
+    }
+    if (threadIdx.x < w.n_rank) {
+        volatile unsigned long long *mine = w.flags[w.rank] + (size_t)b * kP2PMaxRanks + threadIdx.x;
+        const long long t0 = clock64();
+        while (*mine < seq) {
+            if (*(volatile int *)w.status) break; // an earlier exchange already timed out: do not wait again
+            __nanosleep(64);
+            if (clock64() - t0 > 4000000000ll) { // ~2 s at 2 GHz: a peer is gone
+                *w.status = 1;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    const double *loc = w.slots[w.rank] + (size_t)b * w.n_rank * kP2PMaxN;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = 0.0;
+        for (int q = 0; q < w.n_rank; ++q) v += *(volatile const double *)(loc + (size_t)q * kP2PMaxN + i);
+        hsum[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *w.seq = seq;
+}
+
 // phi-level accept (src/de.cpp:397-400, 427-463 and :494-500, 519-549)
 __global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *hsum, int need_cur)
 {
