@@ -24,7 +24,7 @@ class Addr(C.Structure):
 
 class Rng(C.Structure):
     _fields_ = [("mode", C.c_int), ("u", c_dp), ("n", C.c_long), ("pos", C.c_long), ("seed", C.c_ulonglong),
-                ("burn_static_ctor", C.c_int), ("first_like_done", C.c_int)]
+                ("burn_static_ctor", C.c_int), ("first_like_done", C.c_int), ("rec", c_dp), ("rec_n", C.c_long), ("rec_cap", C.c_long)]
 
 
 class Model(C.Structure):
@@ -163,8 +163,13 @@ class OPop:
                      ptr(self.out_lp), ptr(self.out_ll), 0)
 
 
-def make_rng(seed: Optional[int] = None, stream: Optional[np.ndarray] = None, burn: bool = False):
+def make_rng(seed: Optional[int] = None, stream: Optional[np.ndarray] = None, burn: bool = False, record: int = 0):
+    """record > 0: keep the first `record` uniforms handed out, in order (r.recorded())."""
     r = Rng()
+    if record:
+        buf = np.zeros(record)
+        r.rec, r.rec_n, r.rec_cap = ptr(buf), 0, record
+        r._rec = buf
     if stream is not None:
         s = f64(stream)
         r.mode, r.u, r.n, r.pos = 0, ptr(s), len(s), 0
@@ -174,6 +179,10 @@ def make_rng(seed: Optional[int] = None, stream: Optional[np.ndarray] = None, bu
     r.burn_static_ctor = 1 if burn else 0
     r.first_like_done = 0
     return r
+
+
+def recorded(r: Rng) -> np.ndarray:
+    return r._rec[: r.rec_n].copy()
 
 
 def make_de(nparameter, nchain, pop_migration_prob=0.0, sub_migration_prob=0.0, gamma_precursor=2.38, rp=0.001,
@@ -234,3 +243,68 @@ def run_hier(de: DE, phi: OPop, subj: Sequence[OPop], p_prior: OPrior, h_prior: 
 def time_sumloglike(m: OModel, d: OData, thetas, reps: int) -> float:
     th = f64(thetas)
     return lib().orc_time_sumloglike(C.byref(m.c), C.byref(d.c), ptr(th), int(th.shape[0]), int(reps))
+
+
+# ---- tier-2: the reference's own sampler object code (oracle/ref_harness2.cpp) ---------------------
+def _model_args(m: OModel):
+    return [m.n_acc, m.n_cell, ptr(m.param_src, c_ip), ptr(m.const_val), ptr(m.posdrift, c_u8p)]
+
+
+def _prior_args(p: OPrior):
+    return [ptr(p.p0), ptr(p.p1), ptr(p.lower), ptr(p.upper), ptr(p.dist, c_ip), ptr(p.log_p, c_u8p)]
+
+
+def ref2_prime() -> None:
+    ref_lib().ref2_prime()
+
+
+def ref2_set_stream(u: np.ndarray) -> np.ndarray:
+    u = f64(u)
+    ref_lib().ref_set_uniform_stream(ptr(u), len(u))
+    return u
+
+
+def ref2_sweep_subject(kind: int, para_idx: int, nparameter: int, m: OModel, d: OData, prior: OPrior, theta, lp, ll, gamma_precursor=2.38,
+                       rp=0.001):
+    """de_class::crossover (kind 0) / migration (kind 1) of src/de.o on chains theta [nchain, npar]."""
+    th, a, b = f64(theta).copy(), f64(lp).copy(), f64(ll).copy()
+    nchain, npar = th.shape
+    ref_lib().ref2_sweep_subject(kind, para_idx, nchain, nparameter, C.c_double(gamma_precursor), C.c_double(rp), *_model_args(m),
+                                 ptr(d.rt), ptr(d.cell, c_u16p), len(d.rt), npar, *_prior_args(prior), ptr(th), ptr(a), ptr(b))
+    return th, a, b
+
+
+def ref2_run_chains(nparameter: int, m: OModel, d: OData, prior: OPrior, theta0, lp0, ll0, nmc: int, thin: int, sub_migration_prob=0.0,
+                    is_pblocked=False, gamma_precursor=2.38, rp=0.001):
+    """de_class::run_chains of src/de.o; returns (theta [nmc, nchain, npar], lp, ll [nmc, nchain])."""
+    th0 = f64(theta0)
+    nchain, npar = th0.shape
+    ot, olp, oll = np.zeros((nmc, nchain, npar)), np.zeros((nmc, nchain)), np.zeros((nmc, nchain))
+    ref_lib().ref2_run_chains(nchain, nparameter, C.c_double(sub_migration_prob), C.c_double(gamma_precursor), C.c_double(rp),
+                              int(is_pblocked), nmc, thin, *_model_args(m), ptr(d.rt), ptr(d.cell, c_u16p), len(d.rt), npar,
+                              *_prior_args(prior), ptr(th0), ptr(f64(lp0)), ptr(f64(ll0)), ptr(ot), ptr(olp), ptr(oll))
+    return ot, olp, oll
+
+
+def ref2_run_hchains(nparameter: int, m: OModel, datas: Sequence[OData], p_prior: OPrior, h_prior: OPrior, phi_start, subj_starts, nmc: int,
+                     thin: int, pop_migration_prob=0.0, sub_migration_prob=0.0, is_hblocked=False, is_pblocked=False,
+                     gamma_precursor=2.38, rp=0.001):
+    """de_class::run_hchains of src/de.o; returns (phi (theta, lp, ll), [subject (theta, lp, ll)])."""
+    S = len(datas)
+    off = np.zeros(S + 1, dtype=np.int64)
+    for s in range(S):
+        off[s + 1] = off[s] + len(datas[s].rt)
+    rt = f64(np.concatenate([x.rt for x in datas]))
+    cell = np.ascontiguousarray(np.concatenate([x.cell for x in datas]), dtype=np.uint16)
+    phi0, plp0, pll0 = f64(phi_start[0]), f64(phi_start[1]), f64(phi_start[2])
+    nchain, npar = phi0.shape[0], phi0.shape[1] // 2
+    st0 = f64(np.stack([s[0] for s in subj_starts]))
+    slp0, sll0 = f64(np.stack([s[1] for s in subj_starts])), f64(np.stack([s[2] for s in subj_starts]))
+    pot, polp, poll = np.zeros((nmc, nchain, 2 * npar)), np.zeros((nmc, nchain)), np.zeros((nmc, nchain))
+    sot, solp, soll = np.zeros((S, nmc, nchain, npar)), np.zeros((S, nmc, nchain)), np.zeros((S, nmc, nchain))
+    ref_lib().ref2_run_hchains(nchain, nparameter, C.c_double(pop_migration_prob), C.c_double(sub_migration_prob),
+                               C.c_double(gamma_precursor), C.c_double(rp), int(is_hblocked), int(is_pblocked), nmc, thin, S,
+                               *_model_args(m), off.ctypes.data_as(C.POINTER(C.c_longlong)), ptr(rt), ptr(cell, c_u16p), npar,
+                               *_prior_args(p_prior), *_prior_args(h_prior), ptr(phi0), ptr(plp0), ptr(pll0), ptr(st0), ptr(slp0),
+                               ptr(sll0), ptr(pot), ptr(polp), ptr(poll), ptr(sot), ptr(solp), ptr(soll))
+    return (pot, polp, poll), [(sot[s], solp[s], soll[s]) for s in range(S)]

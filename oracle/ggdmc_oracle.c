@@ -40,12 +40,13 @@ void orc_philox4x32_10(const unsigned ctr[4], const unsigned key[2], unsigned ou
 
 double orc_uniform(orc_rng *r, const orc_addr *a)
 {
+    double u;
     if (r->mode == 0) {
         if (r->pos >= r->n) {
             fprintf(stderr, "orc_uniform: stream exhausted at %ld\n", r->pos);
             abort();
         }
-        return r->u[r->pos++];
+        u = r->u[r->pos++];
     } else {
         unsigned ctr[4], key[2], w[4];
         ctr[0] = a->slot >> 2;
@@ -55,8 +56,16 @@ double orc_uniform(orc_rng *r, const orc_addr *a)
         key[0] = (unsigned)(r->seed & 0xFFFFFFFFu);
         key[1] = (unsigned)(r->seed >> 32);
         orc_philox4x32_10(ctr, key, w);
-        return ((double)w[a->slot & 3u] + 0.5) * (1.0 / 4294967296.0);
+        u = ((double)w[a->slot & 3u] + 0.5) * (1.0 / 4294967296.0);
     }
+    if (r->rec) {
+        if (r->rec_n >= r->rec_cap) {
+            fprintf(stderr, "orc_uniform: record buffer full\n");
+            abort();
+        }
+        r->rec[r->rec_n++] = u;
+    }
+    return u;
 }
 
 /* nmath runif(a, b): a == b returns a WITHOUT consuming a draw */

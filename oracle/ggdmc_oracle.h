@@ -44,6 +44,9 @@ typedef struct {
     int burn_static_ctor; /* mode 0: consume 2 extra draws before the first likelihood call
                              (one-off `static lba_class lba_obj`, @hdr/likelihood.h:77) */
     int first_like_done;
+    double *rec;          /* optional: every uniform handed out is also appended here (replay a counter-addressed run
+                             as the sequential stream the reference's Rf_runif would have consumed) */
+    long rec_n, rec_cap;
 } orc_rng;
 
 typedef struct {

@@ -129,6 +129,41 @@ def test_run_hierarchical_trajectory(schedule, jacobi, blocked):
     assert not np.array_equal(phi_out.theta[0, 0], phi_out.theta[0, -1])
 
 
+@pytest.mark.skipif(ob.ref_lib() is None, reason="oracle/_ref (reference object code) was never built")
+def test_gpu_reference_schedule_vs_reference_object_code():
+    """The GPU engine (REFERENCE schedule) against the reference's OWN machine code: the oracle replays the
+    engine's counter-addressed draws and records them in the order the reference consumes uniforms; that
+    recording is injected behind Rf_runif and de_class::run_hchains of src/de.o runs on it.  theta of every
+    stored sample must be identical; log prior / log likelihood agree to FP64 rounding."""
+    ob.ref2_prime()
+    fx = load_fixture(2)
+    rng = np.random.default_rng(77)
+    S, D = fx.n_pop, fx.ct.npar
+    nchain, nmc, thin, seed = 6 * D, 4, 2, 424242
+    phi_s, subj_s = hier_setup(fx, S, nchain, rng)
+    kw = dict(pop_migration_prob=0.3, sub_migration_prob=0.3)
+    tun = E.Tuning(nmc=nmc, nchain=nchain, thin=thin, nparameter=2 * D, schedule=B.SCHEDULE_REFERENCE, seeds=[seed], **kw)
+    phi_out, subj_out = E.run_hier(fx.ct, [fx.trials(f"pop{s}") for s in range(S)], fx.prior("p_prior"), fx.prior("h_prior"), tun,
+                                   E.PopState(*phi_s), [E.PopState(*s) for s in subj_s])
+    # the draw sequence of that run, in the reference's consumption order
+    datas = [fx.odata(f"pop{s}") for s in range(S)]
+    opp, ohp = fx.oprior("p_prior"), fx.oprior("h_prior")
+    rec = ob.make_rng(seed=seed, record=4000000)
+    ob.run_hier(ob.make_de(2 * D, nchain, **kw), ob.OPop(*phi_s, nmc, thin), [ob.OPop(*s, nmc, thin) for s in subj_s], opp, ohp, fx.om,
+                datas, rec, (nmc - 1) * thin)
+    stream = ob.recorded(rec)
+    ob.ref2_set_stream(stream)
+    (pt, plp, pll), subs = ob.ref2_run_hchains(2 * D, fx.om, datas, opp, ohp, phi_s, subj_s, nmc, thin, **kw)
+    assert ob.ref_lib().ref_uniform_stream_pos() == len(stream)
+    assert np.array_equal(phi_out.theta[0], pt)
+    assert np.allclose(phi_out.ll[0], pll, rtol=1e-9, atol=0) and np.allclose(phi_out.lp[0], plp, rtol=1e-9, atol=0)
+    for s in range(S):
+        assert np.array_equal(subj_out[s].theta[0], subs[s][0]), f"subject {s}"
+        fin = np.isfinite(subs[s][2])
+        assert np.allclose(subj_out[s].ll[0][fin], subs[s][2][fin], rtol=1e-9, atol=0)
+    assert not np.array_equal(pt[0], pt[-1])
+
+
 def test_replicates_batch_equals_separate_runs():
     fx = load_fixture(2)
     rng = np.random.default_rng(3)

@@ -136,6 +136,107 @@ def test_tnorm_bitwise_vs_reference_object_code():
         assert a == b or (np.isnan(a) and np.isnan(b))
 
 
+def _subject_state(fx, od, oprior, nchain, rng, center=None, phi=None):
+    th = sane_starts(fx, nchain, rng, center=center)
+    D = th.shape[1]
+    lp = np.array([ob.sumlogprior(oprior, th[c], None if phi is None else phi[c, :D], None if phi is None else phi[c, D:])
+                   for c in range(nchain)])
+    ll = np.array([ob.sumloglike(fx.om, od, th[c]) for c in range(nchain)])
+    return th, lp, ll
+
+
+def _hier_state(fx, S, nchain, rng):
+    D = fx.ct.npar
+    opp, ohp = fx.oprior("p_prior"), fx.oprior("h_prior")
+    center = np.concatenate([fx.g["pop_mean"], fx.g["pop_scale"]])
+    phi0 = center[None, :] * (1.0 + 0.1 * rng.standard_normal((nchain, 2 * D)))
+    subj = [_subject_state(fx, fx.odata(f"pop{s}"), opp, nchain, rng, center=fx.g["ps"][s], phi=phi0) for s in range(S)]
+    lp0 = np.array([ob.sumlogprior(ohp, phi0[c]) for c in range(nchain)])
+    ll0 = np.array([sum(ob.sumlogprior(opp, subj[s][0][c], phi0[c, :D], phi0[c, D:]) for s in range(S)) for c in range(nchain)])
+    return (phi0, lp0, ll0), subj
+
+
+@needs_ref
+def test_sampler_sweeps_bitwise_vs_reference_object_code():
+    """de_class::crossover / migration of src/de.o (src/de.cpp:111-199), driven on hand-built objects with an
+    injected uniform stream, against the restatement fed the same stream: theta, log prior and log
+    likelihood of every chain bit-identical, the same number of uniforms consumed."""
+    ob.ref2_prime()
+    R = ob.ref_lib()
+    for k, prior_name in ((2, "sub_prior"), (6, "sub_prior"), (3, "p_prior")):
+        fx = load_fixture(k)
+        rng = np.random.default_rng(30 + k)
+        od, op, D = fx.odata("sub"), fx.oprior(prior_name), fx.ct.npar
+        nchain = 3 * D
+        th, lp, ll = _subject_state(fx, od, op, nchain, rng)
+        for kind, para in ((0, -1), (1, -1), (0, 1), (1, 2), (0, -1)):
+            u = ob.ref2_set_stream(rng.uniform(size=400000))
+            a = ob.ref2_sweep_subject(kind, para, D, fx.om, od, op, th, lp, ll)
+            used = R.ref_uniform_stream_pos()
+            pop = ob.OPop(th, lp, ll, 2, 1)
+            r = ob.make_rng(stream=u)
+            f = ob.lib().orc_crossover_subject if kind == 0 else ob.lib().orc_migration_subject
+            f(C.byref(ob.make_de(D, nchain)), C.byref(pop.c), C.byref(op.c), C.byref(fx.om.c), C.byref(od.c), C.byref(r), C.c_uint(0),
+              C.c_uint(1), C.c_int(para))
+            assert r.pos == used and used > nchain
+            assert np.array_equal(a[0], pop.theta) and np.array_equal(a[1], pop.lp) and np.array_equal(a[2], pop.ll)
+            assert not np.array_equal(a[0], th)  # something was accepted
+            th, lp, ll = a
+
+
+@needs_ref
+@pytest.mark.parametrize("pblocked", [False, True])
+def test_run_chains_bitwise_vs_reference_object_code(pblocked):
+    """The reference's whole 1-level driver de_class::run_chains (src/de.cpp:201-242: migration decision,
+    blocked / unblocked crossover, theta_phi::store thinning) from src/de.o vs orc_run_subject."""
+    ob.ref2_prime()
+    fx = load_fixture(2)
+    rng = np.random.default_rng(5)
+    od, op, D = fx.odata("sub"), fx.oprior("sub_prior"), fx.ct.npar
+    nchain, nmc, thin = 3 * D, 5, 3
+    th, lp, ll = _subject_state(fx, od, op, nchain, rng)
+    u = ob.ref2_set_stream(rng.uniform(size=1500000))
+    ot, olp, oll = ob.ref2_run_chains(D, fx.om, od, op, th, lp, ll, nmc, thin, sub_migration_prob=0.3, is_pblocked=pblocked)
+    used = ob.ref_lib().ref_uniform_stream_pos()
+    pop = ob.OPop(th, lp, ll, nmc, thin)
+    r = ob.make_rng(stream=u)
+    ob.run_subject(ob.make_de(D, nchain, sub_migration_prob=0.3, is_pblocked=pblocked), pop, op, fx.om, od, r, 0, (nmc - 1) * thin)
+    assert r.pos == used
+    assert np.array_equal(ot, pop.out_theta) and np.array_equal(olp, pop.out_lp) and np.array_equal(oll, pop.out_ll)
+    assert not np.array_equal(ot[0], ot[-1])
+
+
+@needs_ref
+@pytest.mark.parametrize("blocked", [False, True])
+def test_run_hchains_bitwise_vs_reference_object_code(blocked):
+    """The reference's hierarchical driver de_class::run_hchains (src/de.cpp:272-383) from src/de.o -- phi
+    crossover / migration with refreshed hyper-likelihood, subject steps with phi-driven priors and the stale
+    log prior, per-parameter blocking, storage -- vs orc_run_hier: every stored sample bit-identical."""
+    ob.ref2_prime()
+    fx = load_fixture(2)
+    rng = np.random.default_rng(9)
+    S, D = fx.n_pop, fx.ct.npar
+    nchain = 6 * D
+    nmc, thin = (3, 1) if blocked else (4, 2)
+    phi_s, subj_s = _hier_state(fx, S, nchain, rng)
+    opp, ohp = fx.oprior("p_prior"), fx.oprior("h_prior")
+    datas = [fx.odata(f"pop{s}") for s in range(S)]
+    kw = dict(pop_migration_prob=0.3, sub_migration_prob=0.3, is_hblocked=blocked, is_pblocked=blocked)
+    u = ob.ref2_set_stream(rng.uniform(size=4000000))
+    (pt, plp, pll), subs = ob.ref2_run_hchains(2 * D, fx.om, datas, opp, ohp, phi_s, subj_s, nmc, thin, **kw)
+    used = ob.ref_lib().ref_uniform_stream_pos()
+    phi = ob.OPop(*phi_s, nmc, thin)
+    pops = [ob.OPop(*s, nmc, thin) for s in subj_s]
+    r = ob.make_rng(stream=u)
+    ob.run_hier(ob.make_de(2 * D, nchain, **kw), phi, pops, opp, ohp, fx.om, datas, r, (nmc - 1) * thin)
+    assert r.pos == used
+    assert np.array_equal(pt, phi.out_theta) and np.array_equal(plp, phi.out_lp) and np.array_equal(pll, phi.out_ll)
+    for s in range(S):
+        assert np.array_equal(subs[s][0], pops[s].out_theta) and np.array_equal(subs[s][1], pops[s].out_lp)
+        assert np.array_equal(subs[s][2], pops[s].out_ll)
+    assert not np.array_equal(pt[0], pt[-1])
+
+
 def test_philox_known_answers():
     """Random123 known-answer vectors for Philox4x32-10."""
     L = ob.lib()
