@@ -40,6 +40,7 @@ import numpy as np  # noqa: E402
 F_TRIAL = {2: 513.0, 3: 755.0, 4: 997.0}  # algorithmic flop per trial-likelihood: 242 * n_acc + 29
 METRIC = "trial-likelihoods/s, DE-MCMC iterations of a hierarchical LBA fit"
 UNIT = "trial-likelihoods/s"
+W_NPAR = {6: 13, 5: 17, 2: 8}  # free parameters of the fixture models
 
 WORKLOADS = {
     # name: (model fixture, subjects, trials per subject, description)
@@ -143,13 +144,58 @@ def oracle_hier_sample(model_k: int, n_subject: int, n_trial: int, n_iter: int, 
     return dt, n_lik
 
 
+def refobj_hier_sample(model_k: int, n_subject: int, n_trial: int, n_iter: int, seed: int):
+    """The reference's OWN machine code -- de_class::run_hchains of src/de.o (the package author's build,
+    -O0) through oracle/_ref -- on `n_subject` synthetic subjects; returns (seconds, trial-likelihoods)."""
+    from ggdmc_b200 import synth
+    from ggdmc_b200.workloads import load_model
+    from oracle import binding as ob
+
+    spec = load_model(model_k)
+    ct = spec.ct
+    D, C = ct.npar, 6 * ct.npar
+    om = ob.OModel(ct.param_src, ct.const_val, ct.posdrift, ct.npar)
+
+    def opr(p):
+        return ob.OPrior(p.p0, p.p1, p.lower, p.upper, p.dist, p.log_p)
+
+    opp, ohp = opr(spec.p_prior), opr(spec.h_prior)
+    rng = np.random.default_rng([20260101, seed])
+    center = np.concatenate([spec.pop_mean, spec.pop_scale])
+    phi0 = np.abs(center[None, :] * (1.0 + 0.05 * rng.standard_normal((C, 2 * D))))
+    datas, starts = [], []
+    for s in range(n_subject):
+        th = synth.rtnorm(spec.pop_mean, spec.pop_scale, 0.0, rng)
+        tr = synth.simulate_subject(ct, spec.node_1_index, th, n_trial, rng)
+        od = ob.OData(tr.rt, tr.cell)
+        x0 = np.abs(th[None, :] * (1.0 + 0.05 * rng.standard_normal((C, D))))
+        lp = np.array([ob.sumlogprior(opp, x0[c], phi0[c, :D], phi0[c, D:]) for c in range(C)])
+        ll = np.array([ob.sumloglike(om, od, x0[c]) for c in range(C)])
+        datas.append(od)
+        starts.append((x0, lp, ll))
+    phi_s = (phi0, np.array([ob.sumlogprior(ohp, phi0[c]) for c in range(C)]), np.zeros(C))
+    ob.ref2_prime()
+    ob.ref_lib().ref_set_uniform_stream(None, 0)  # Rf_runif falls back to the shim's own generator
+    t0 = time.perf_counter()
+    ob.ref2_run_hchains(2 * D, om, datas, opp, ohp, phi_s, starts, n_iter + 1, 1, pop_migration_prob=0.05, sub_migration_prob=0.05)
+    dt = time.perf_counter() - t0
+    n_lik = n_iter * n_subject * C * n_trial * (0.95 + 0.05 * 0.5)
+    return dt, n_lik
+
+
 def _ref_worker(args):
-    model_k, n_subject, n_trial, steps, warm, seed = args
+    model_k, n_subject, n_trial, steps, warm, seed, use_obj = args
+    if use_obj:
+        if warm:
+            refobj_hier_sample(model_k, n_subject, n_trial, warm, seed + 7)
+        return refobj_hier_sample(model_k, n_subject, n_trial, steps, seed)
     return oracle_hier_sample(model_k, n_subject, n_trial, steps, seed, n_warm=warm)
 
 
 def run_reference(args, rank, world):
-    """The reference's CPU path (oracle port), one replicate per host core, bounded sample."""
+    """The reference's CPU path on the host cores, bounded sample.  With oracle/_ref present this is the
+    reference's own object code (de_class::run_hchains of src/de.o); otherwise the oracle port.  One replicate
+    process per host core, like the reference's `ncore` forked replicates (R/sampling.R:26-55)."""
     if rank != 0:
         return
     import multiprocessing as mp
@@ -159,22 +205,26 @@ def run_reference(args, rank, world):
     n_sub = 4  # bounded sample: 4 of the subjects per replicate process
     from oracle import binding as ob
     ob.build()
+    use_obj = ob.ref_lib() is not None
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_ref_worker, [(model_k, n_sub, ntr, args.steps, args.warmup, 1000 + i) for i in range(cores)])
+        res = pool.map(_ref_worker, [(model_k, n_sub, ntr, args.steps, args.warmup, 1000 + i, use_obj) for i in range(cores)])
     wall = time.perf_counter() - t0
     tmax = max(r[0] for r in res)
     total = sum(r[1] for r in res)
     value = total / tmax
+    nchain = 6 * W_NPAR[model_k]
+    kind = "reference" if use_obj else "port"
+    what = ("the reference's own object code: de_class::run_hchains of src/de.o (package author's build, -O0) behind an R-API shim"
+            if use_obj else "oracle C port at -O2")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tmax / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "sample": f"{n_sub} subjects x {ntr} trials x {6 * 13 if model_k == 6 else 102} chains per replicate process"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": {"workload": desc, "sample": f"{n_sub} subjects x {ntr} trials x {nchain} chains per replicate process"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{cores} replicate processes (one per host core, like the reference's ncore forks), each "
-                                   f"{args.steps} DE-MCMC iterations over {n_sub} subjects of the workload; oracle C port at -O2; "
-                                   f"wall {wall:.1f} s"},
+                                   f"{args.steps} DE-MCMC iterations over {n_sub} subjects of the workload; {what}; wall {wall:.1f} s"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -328,33 +378,15 @@ def main():
         cpu = {"value": nc / dtc, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{iters} DE-MCMC iterations (run_hchains restatement, reference chain order) over 8 subjects x {ntr} trials x "
                          f"{w.nchain} chains of the same synthetic population; {dtc:.1f} s on one host core, gcc -O2"}
-        R = ob.ref_lib()
-        if R is not None:  # the reference's own object code (-O0 build) on the density alone, for context
-            g = np.load(os.path.join(ROOT, "tests", "golden", f"lba_data{model_k}.npz"))
-            tr = w.trials[0]
-            om = ob.OModel(w.spec.ct.param_src, w.spec.ct.const_val, w.spec.ct.posdrift, w.spec.ct.npar)
-            th = ob.f64(w.true_theta[0])
-            import ctypes as C
-            cells = np.unique(tr.cell)
-            Ps, rts = [], []
-            for cc in cells:
-                P = np.zeros((6, n_acc))
-                ob.lib().orc_cell_params(C.byref(om.c), ob.ptr(th), int(cc), ob.ptr(P))
-                Ps.append(P)
-                rts.append(ob.f64(tr.rt[tr.cell == cc]))
-            u = np.zeros(1 << 16)
-            t0 = time.perf_counter()
-            reps = 0
-            while time.perf_counter() - t0 < 2.0:
-                R.ref_set_uniform_stream(ob.ptr(u), len(u))
-                for P, r in zip(Ps, rts):
-                    o = np.empty_like(r)
-                    R.ref_lba_cell(ob.ptr(P), n_acc, ob.ptr(om.posdrift, ob.c_u8p), ob.ptr(r), len(r), ob.ptr(o))
-                reps += 1
-            cpu["reference_object_code_density_only"] = {
-                "value": reps * len(tr.rt) / (time.perf_counter() - t0), "unit": UNIT, "cores": 1,
-                "note": "lba_class::{set_parameters,validate_parameters,dlba} of the reference's src/de.o (author's -O0 build) "
-                        "through oracle/_ref, density only (no log/sum, no sampler)"}
+        if ob.ref_lib() is not None:  # the reference's own object code on the same kind of sample
+            dtr, nr = refobj_hier_sample(model_k, 4, ntr, 2, 9)
+            it_r = int(max(2, min(40, 10.0 / max(dtr / 2, 1e-3))))
+            dtr, nr = refobj_hier_sample(model_k, 4, ntr, it_r, 10)
+            cpu = {"value": nr / dtr, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"{it_r} DE-MCMC iterations of de_class::run_hchains from the reference's own src/de.o (package author's "
+                             f"build, -O0; R-API shim: Cody pnorm, injected runif) over 4 subjects x {ntr} trials x {w.nchain} chains; "
+                             f"{dtr:.1f} s on one host core",
+                   "port": cpu}
 
     if rank == 0:
         line = {
