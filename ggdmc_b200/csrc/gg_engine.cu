@@ -386,13 +386,13 @@ constexpr int kProposeWarps = 4;
 // The default was picked by measurement on B200 (profiles/); GGDMC_B200_LIKE_VARIANT overrides it
 // for experiments.
 struct LikeVariant { int block, minb; };
-const LikeVariant kLikeVariants[] = {{128, 6}, {128, 8}, {64, 12}, {64, 16}, {32, 24}, {32, 32}};
+const LikeVariant kLikeVariants[] = {{128, 6}, {128, 8}, {64, 12}, {64, 16}, {32, 24}, {32, 32}, {64, 10}, {64, 8}};
 int like_variant()
 {
     static int v = [] {
         const char *e = std::getenv("GGDMC_B200_LIKE_VARIANT");
         int x = e ? std::atoi(e) : 2;
-        return (x < 0 || x > 5) ? 2 : x;
+        return (x < 0 || x > 7) ? 2 : x;
     }();
     return v;
 }
@@ -427,6 +427,8 @@ void launch_like_n(const Level &L, const DevModel &M, const TrialData &T, const 
     case 1: launch_like_t<NACC, 128, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
     case 4: launch_like_t<NACC, 32, 24>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
     case 5: launch_like_t<NACC, 32, 32>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    case 6: launch_like_t<NACC, 64, 10>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
+    case 7: launch_like_t<NACC, 64, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
     default: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st);
     }
 }
