@@ -246,7 +246,6 @@ struct ModelDev {
         d.n_acc = m->n_acc; d.n_cell = m->n_cell; d.npar = m->npar; d.n_const = m->n_const;
         d.param_src = param_src.p; d.const_val = const_val.p; d.posdrift = posdrift.p;
     }
-    size_t table_bytes() const { return (size_t)d.n_cell * d.n_acc * sizeof(CellAcc); }
 };
 
 struct PriorDev {
@@ -385,8 +384,7 @@ constexpr int kProposeWarps = 4;
 // Launch shape of the likelihood kernel: (threads per block, minimum resident blocks per SM).
 // The default was picked by measurement on B200 (profiles/); GGDMC_B200_LIKE_VARIANT overrides it
 // for experiments.
-struct LikeVariant { int block, minb; };
-const LikeVariant kLikeVariants[] = {{128, 6}, {128, 8}, {64, 12}, {64, 16}, {32, 24}, {32, 32}, {64, 10}, {64, 8}};
+// variants: 0 (128, 6)  1 (128, 8)  2 (64, 12)  3 (64, 16)  4 (32, 24)  5 (32, 32)  6 (64, 10)  7 (64, 8)
 int like_variant()
 {
     static int v = [] {
@@ -480,6 +478,7 @@ struct ggdmc_engine {
     LevelDev subj, phi;
     DBuf<uint64_t> seeds;
     DBuf<uint32_t> d_iter;
+    DBuf<unsigned int> done_ctr;
     DBuf<double> ll_part, hpart, hsum, hyper_data, phi_consts;
     HyperArgs H{};
 
@@ -513,7 +512,9 @@ struct ggdmc_engine {
         CUDA_CHECK(cudaEventCreate(&ev1));
         seeds.upload(cfg->seed, R);
         uint32_t z = 0;
-        d_iter.upload(&z, 1);
+        d_iter.upload(&z, 1); // 0 while the start state is stored in slot 0, then 1 = first iteration
+        done_ctr.alloc(1);
+        done_ctr.zero();
     }
 
     void init_level_state(LevelDev &lv, const ggdmc_start_t *starts, int n_items, int D_)
@@ -575,7 +576,7 @@ struct ggdmc_engine {
             L.ovr_consts = phi_consts.p;
             setup_hyper(subj.theta.p, C * D, R * C * D, D, 1);
         }
-        CUDA_CHECK(cudaStreamSynchronize(0));
+        start_counter();
     }
 
     void create_hyper(const ggdmc_prior_t *pp, const ggdmc_prior_t *hp, const double *data_theta, int n_subject,
@@ -598,6 +599,14 @@ struct ggdmc_engine {
         P.nmove = std::min(D2, cfg->nparameter);
         init_level_state(phi, start, 1, D2);
         setup_hyper(hyper_data.p, 0, D, 0, 0);
+        start_counter();
+    }
+
+    void start_counter()
+    {
+        CUDA_CHECK(cudaStreamSynchronize(stream)); // slot-0 stores (which read iteration 0) are done
+        const uint32_t one = 1;
+        CUDA_CHECK(cudaMemcpy(d_iter.p, &one, sizeof(one), cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaStreamSynchronize(0));
     }
 
@@ -607,8 +616,8 @@ struct ggdmc_engine {
         H.x = x; H.x_rep_stride = rep_stride; H.x_subj_stride = subj_stride; H.x_chain_stride = chain_stride;
         H.S = S; H.D = D; H.need_cur = need_cur;
         // split subjects over blocks so that K4 fills the GPU (R*C blocks alone would not)
-        int want = std::max(1, (2 * 148 + R * C - 1) / (R * C));
-        int spb = std::max(16, (S + want - 1) / want);
+        int want = std::max(1, (8 * 148 + R * C - 1) / (R * C));
+        int spb = std::max(8, (S + want - 1) / want);
         H.subj_per_block = spb;
         H.nsplit = (S + spb - 1) / spb;
         hpart.alloc((size_t)R * C * 2 * H.nsplit);
@@ -659,7 +668,8 @@ struct ggdmc_engine {
             const int nhalf = schedule == GGDMC_SCHEDULE_PARALLEL ? 2 : 1;
             for (int h = 0; h < nhalf; ++h) {
                 const int half = nhalf == 2 ? h : -1;
-                k_propose<kProposeWarps><<<(n + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1, half);
+                const int nw = half < 0 ? n : L.npop * ((C + 1) / 2); // warps: one per (population, chain) or per (population, slot)
+                k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1, half);
                 timed_like(L, sweep, -1, half);
                 k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, ll_part.p, trials.d.nsplit);
                 launches += 3;
@@ -708,7 +718,8 @@ struct ggdmc_engine {
             const int nhalf = schedule == GGDMC_SCHEDULE_PARALLEL ? 2 : 1;
             for (int h = 0; h < nhalf; ++h) {
                 const int half = nhalf == 2 ? h : -1;
-                k_propose<kProposeWarps><<<(n + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, -1, half);
+                const int nw = half < 0 ? n : R * ((C + 1) / 2);
+                k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, -1, half);
                 hyper_eval(-1);
                 k_phi_accept<<<(n + 127) / 128, 128, 0, stream>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur);
                 launches += 2;
@@ -739,11 +750,20 @@ struct ggdmc_engine {
         ++launches;
     }
 
-    // one DE-MCMC iteration: run_chains body (src/de.cpp:208-240) or run_hchains body (:281-381)
+    // end of an iteration: thinned storage of every level + device-side iteration counter advance, one kernel
+    void store_and_advance(LevelDev &a, LevelDev *b)
+    {
+        size_t total = (size_t)a.L.npop * C * a.L.npar;
+        if (b) total = std::max(total, (size_t)b->L.npop * C * b->L.npar);
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+        k_store_advance<<<blocks, 256, 0, stream>>>(a.L, b ? b->L : a.L, b ? 1 : 0, d_iter.p, done_ctr.p);
+        ++launches;
+    }
+
+    // one DE-MCMC iteration: run_chains body (src/de.cpp:208-240) or run_hchains body (:281-381).
+    // The iteration number (1-based, like the reference's loop variable) lives in device memory.
     void iteration()
     {
-        k_iter_advance<<<1, 1, 0, stream>>>(d_iter.p);
-        ++launches;
         ++h_iter;
         if (kind == 2) {
             if (is_hblocked)
@@ -755,20 +775,19 @@ struct ggdmc_engine {
                 for (int p = 0; p < D; ++p) sweep_lba(p, 0, p);
             else
                 sweep_lba(0, 0, -1);
-            store(subj);
-            store(phi);
+            store_and_advance(subj, &phi);
         } else if (kind == 0) {
             if (is_pblocked)
                 for (int p = 0; p < subj.L.nmove; ++p) sweep_lba(p, 1, p);
             else
                 sweep_lba(0, 1, -1);
-            store(subj);
+            store_and_advance(subj, nullptr);
         } else {
             if (is_pblocked)
                 for (int p = 0; p < phi.L.nmove; ++p) sweep_phi(p, 1, p);
             else
                 sweep_phi(0, 1, -1);
-            store(phi);
+            store_and_advance(phi, nullptr);
         }
     }
 
@@ -1125,6 +1144,7 @@ int ggdmc_b200_sumloglike(const ggdmc_model_t *model, const ggdmc_trials_t *tria
     DBuf<int> d_target, d_mode;
     DBuf<uint64_t> d_seed;
     DBuf<uint32_t> d_iter;
+    DBuf<unsigned int> done_ctr;
     const size_t n = (size_t)S * n_theta;
     d_theta.upload(theta, n * D);
     d_part.alloc(n * T.d.nsplit);

@@ -273,21 +273,30 @@ __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t 
     const int C = L.nchain, D = L.npar;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int g = blockIdx.x * WARPS + w;
-    int p, k;
-    if (step < 0) {
-        p = g / C;
-        k = g - p * C;
-    } else {
+    int p, k, k2 = -1; // sweep positions this warp handles (k2: second one for migrating populations in half mode)
+    if (step >= 0) {
         p = g;
         k = step;
+    } else if (half < 0) {
+        p = g / C;
+        k = g - p * C;
+    } else { // half-sweep: (C + 1) / 2 slots per population; crossover -> chain 2 slot + half, migration (half 0) -> slot, slot + nslot
+        const int nslot = (C + 1) / 2;
+        p = g / nslot;
+        k = g - p * nslot;
+        if (p < L.npop) {
+            if (L.mode[p] == 0) k = 2 * k + half;
+            else if (half == 0) k2 = k + nslot;
+            else return;
+        }
     }
     if (p >= L.npop) return;
     const uint32_t iter = *d_iter;
     const int mode = L.mode[p];
     const int para_idx = L.para[p];
     const int nsteps = mode ? L.mig_n[p] : C;
-    if (k >= nsteps) return;
-    if (half >= 0 && (mode ? half != 0 : (k & 1) != half)) return; // half-sweeps: crossover by parity, migration whole in half 0
+    for (; k >= 0; k = k2, k2 = -1) {
+    if (k >= nsteps) continue;
     double *scratch = sm_prop + w * D;
     int src, tgt, c0 = 0, c1 = 0;
     if (mode) {
@@ -333,6 +342,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t 
         L.prop_lp[p * C + src] = sum_arma_order(scratch, D);
         L.target[p * C + src] = tgt;
     }
+    __syncwarp();
+    } // positions of this warp
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -788,9 +799,8 @@ __global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int ste
 // ------------------------------------------------------------------------------------------------
 // storage (theta_phi::store, @hdr/theta.h:61-74) and the iteration counter
 // ------------------------------------------------------------------------------------------------
-__global__ void k_store(Level L, const uint32_t *d_iter)
+__device__ __forceinline__ void store_level(const Level &L, uint32_t iter)
 {
-    const uint32_t iter = *d_iter;
     if (iter % (uint32_t)L.thin != 0) return;
     const uint32_t slot = iter / (uint32_t)L.thin;
     if (slot >= (uint32_t)L.nmc) return;
@@ -802,6 +812,27 @@ __global__ void k_store(Level L, const uint32_t *d_iter)
         if (r < C) {
             L.out_lp[(p * L.nmc + slot) * C + r] = L.lp[p * C + r];
             L.out_ll[(p * L.nmc + slot) * C + r] = L.ll[p * C + r];
+        }
+    }
+}
+
+__global__ void k_store(Level L, const uint32_t *d_iter) { store_level(L, *d_iter); }
+
+// End of an iteration: store both levels (has_b: second level present) and advance the device-side
+// iteration counter.  Every block reads the counter before it signals completion; the last block to
+// finish performs the increment, so no block can see the new value.
+__global__ void k_store_advance(Level A, Level Bv, int has_b, uint32_t *d_iter, unsigned int *done)
+{
+    const uint32_t iter = *d_iter;
+    store_level(A, iter);
+    if (has_b) store_level(Bv, iter);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {
+            *done = 0;
+            *d_iter = iter + 1;
         }
     }
 }
