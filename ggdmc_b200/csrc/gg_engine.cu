@@ -285,28 +285,45 @@ struct TrialsDev {
         std::vector<double> hrt;
         std::vector<uint16_t> hcl;
         if (keep_order) order.resize(S);
+        {
+            const int64_t ntot = t->subject_offset[S] - t->subject_offset[0];
+            hrt.reserve((size_t)ntot + 8 * (size_t)S);
+            hcl.reserve((size_t)ntot + 8 * (size_t)S);
+        }
         int64_t pos = 0;
         for (int s = 0; s < S; ++s) {
             const int64_t b = t->subject_offset[s], e = t->subject_offset[s + 1];
             require(e >= b && e - b < (int64_t)1 << 31, "bad subject_offset");
             const int n = (int)(e - b);
-            // stable counting sort by cell (dmi@data usually arrives grouped by cell already)
-            std::vector<int> idx(n), start((size_t)n_cell + 1, 0);
+            // group by cell: dmi@data usually arrives grouped already (then it is a straight copy), otherwise a
+            // stable counting sort
+            bool sorted = true;
             for (int i = 0; i < n; ++i) {
                 require(t->cell[b + i] < n_cell, "cell index out of range");
-                ++start[t->cell[b + i] + 1];
+                if (i > 0 && t->cell[b + i] < t->cell[b + i - 1]) sorted = false;
             }
-            for (int c = 0; c < n_cell; ++c) start[c + 1] += start[c];
-            for (int i = 0; i < n; ++i) idx[start[t->cell[b + i]]++] = i;
+            std::vector<int> idx;
+            if (!sorted || keep_order) {
+                idx.resize(n);
+                std::vector<int> start((size_t)n_cell + 1, 0);
+                for (int i = 0; i < n; ++i) ++start[t->cell[b + i] + 1];
+                for (int c = 0; c < n_cell; ++c) start[c + 1] += start[c];
+                for (int i = 0; i < n; ++i) idx[start[t->cell[b + i]]++] = i;
+            }
             off[s] = pos;
             h_count[s] = n;
             max_count = std::max(max_count, n);
             const int npad = (n + 7) & ~7;
             hrt.resize(pos + npad, 0.0);
             hcl.resize(pos + npad, 0xFFFF);
-            for (int i = 0; i < n; ++i) {
-                hrt[pos + i] = t->rt[b + idx[i]];
-                hcl[pos + i] = t->cell[b + idx[i]];
+            if (idx.empty()) {
+                std::memcpy(&hrt[pos], t->rt + b, sizeof(double) * (size_t)n);
+                std::memcpy(&hcl[pos], t->cell + b, sizeof(uint16_t) * (size_t)n);
+            } else {
+                for (int i = 0; i < n; ++i) {
+                    hrt[pos + i] = t->rt[b + idx[i]];
+                    hcl[pos + i] = t->cell[b + idx[i]];
+                }
             }
             if (keep_order) order[s] = idx;
             pos += npad;
@@ -372,6 +389,18 @@ int pick_device(int requested)
     return cur;
 }
 
+struct PhaseTimer { // GGDMC_B200_TIMING=1 prints host wall time per phase of a run* call to stderr
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    PhaseTimer() : on(std::getenv("GGDMC_B200_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *what)
+    {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[ggdmc_b200] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 template <class K>
 void allow_smem(K kernel, size_t bytes)
 {
@@ -541,16 +570,21 @@ struct ggdmc_engine {
     void create_lba(const ggdmc_model_t *m, const ggdmc_trials_t *t, const ggdmc_prior_t *pp, const ggdmc_prior_t *hp,
                     const ggdmc_config_t *cfg, const ggdmc_start_t *phi_start, const ggdmc_start_t *subj_start)
     {
+        PhaseTimer pt;
         common_init(cfg);
+        pt.lap("  init");
         kind = hp ? 2 : 0;
         model.upload(m);
         D = m->npar;
         require(pp && pp->npar == D, "p_prior length != model npar");
         p_prior.upload(pp);
+        pt.lap("  model");
         trials.upload(t, m->n_cell, false);
+        pt.lap("  trials");
         S = t->n_subject;
         trials.set_chunking((int64_t)R * S * C);
         subj.create(R * S, R, C, D, nmc, thin);
+        pt.lap("  alloc");
         Level &L = subj.L;
         L.n_rep = R; L.pop_id_base = subject_begin; L.is_phi = 0;
         L.gamma = cfg->gamma_precursor / std::sqrt(2.0 * cfg->nparameter); // src/de.cpp:12,24
@@ -558,6 +592,7 @@ struct ggdmc_engine {
         L.seed = seeds.p; L.prior = p_prior.d; L.prior_ovr = nullptr;
         L.nmove = std::min(D, kind == 2 ? cfg->nparameter / 2 : cfg->nparameter); // src/de.cpp:136 / :592
         init_level_state(subj, subj_start, S, D);
+        pt.lap("  state");
         ll_part.alloc((size_t)R * S * C * trials.d.nsplit);
         ll_part.zero();
         if (kind == 2) {
@@ -577,6 +612,7 @@ struct ggdmc_engine {
             setup_hyper(subj.theta.p, C * D, R * C * D, D, 1);
         }
         start_counter();
+        pt.lap("  phi");
     }
 
     void create_hyper(const ggdmc_prior_t *pp, const ggdmc_prior_t *hp, const double *data_theta, int n_subject,
@@ -897,18 +933,6 @@ struct ggdmc_engine {
 // C ABI
 // ---------------------------------------------------------------------------------------------
 namespace {
-struct PhaseTimer { // GGDMC_B200_TIMING=1 prints host wall time per phase of a run* call to stderr
-    bool on;
-    std::chrono::steady_clock::time_point t;
-    PhaseTimer() : on(std::getenv("GGDMC_B200_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
-    void lap(const char *what)
-    {
-        if (!on) return;
-        auto n = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "[ggdmc_b200] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
-        t = n;
-    }
-};
 int fail(char err[256], const std::exception &e, int code)
 {
     if (err) {

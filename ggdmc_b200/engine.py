@@ -31,7 +31,30 @@ def _model(ct: CellTable) -> _Keep:
     return _Keep(m, ps, cv, pd)
 
 
-def _trials(subjects: Sequence[Trials]) -> _Keep:
+class TrialsStack:
+    """All subjects' trials already concatenated (rt, cell, offsets): skips S small concatenations per call."""
+
+    def __init__(self, subjects: Sequence[Trials]):
+        self.n = len(subjects)
+        self.off = np.zeros(self.n + 1, dtype=np.int64)
+        self.off[1:] = np.cumsum([len(t.rt) for t in subjects])
+        self.rt = B.f64(np.concatenate([t.rt for t in subjects]))
+        self.cell = np.ascontiguousarray(np.concatenate([t.cell for t in subjects]), dtype=np.uint16)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return Trials(self.rt[self.off[i]:self.off[i + 1]], self.cell[self.off[i]:self.off[i + 1]])
+
+    def __iter__(self):
+        return (self[i] for i in range(self.n))
+
+
+def _trials(subjects) -> _Keep:
+    if isinstance(subjects, TrialsStack):
+        t = B.TrialsT(subjects.n, B.ptr(subjects.off, B.c_i64p), B.ptr(subjects.rt), B.ptr(subjects.cell, B.c_u16p))
+        return _Keep(t, subjects)
     off = np.zeros(len(subjects) + 1, dtype=np.int64)
     for i, t in enumerate(subjects):
         off[i + 1] = off[i] + len(t.rt)
@@ -118,6 +141,69 @@ class PopSamples:
         return B.SamplesT(D, C_, nmc, B.ptr(self.theta), B.ptr(self.lp), B.ptr(self.ll))
 
 
+def _addr(a: np.ndarray) -> int:
+    return a.__array_interface__["data"][0]
+
+
+class PopStateStack:
+    """Start states of S populations held in three stacked arrays (theta [S, R, C, D], lp / ll [S, R, C]).
+    Behaves like a list of PopState; the engine gets all S address triples without touching S objects."""
+
+    def __init__(self, theta, lp, ll):
+        self.theta, self.lp, self.ll = B.f64(theta), B.f64(lp), B.f64(ll)
+        assert self.theta.ndim == 4 and self.lp.shape == self.theta.shape[:3] == self.ll.shape
+
+    def __len__(self):
+        return self.theta.shape[0]
+
+    def __getitem__(self, i):
+        return PopState(self.theta[i], self.lp[i], self.ll[i])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class HierOutputs(list):
+    """List of per-subject PopSamples that are views of three big arrays (kept in .big)."""
+
+    big = None
+
+
+def _start_array(starts):
+    """[S] ggdmc_start_t as one numpy block of addresses (ctypes struct construction is ~10 us each)."""
+    S = len(starts)
+    tab = np.empty((S, 3), dtype=np.uint64)
+    if isinstance(starts, PopStateStack):
+        idx = np.arange(S, dtype=np.uint64)
+        for j, a in enumerate((starts.theta, starts.lp, starts.ll)):
+            tab[:, j] = np.uint64(_addr(a)) + idx * np.uint64(a.strides[0])
+    else:
+        for i, s in enumerate(starts):
+            tab[i, 0], tab[i, 1], tab[i, 2] = _addr(s.theta), _addr(s.lp), _addr(s.ll)
+    return (tab, starts), tab.ctypes.data_as(C.POINTER(B.StartT))
+
+
+_SAMPLES_DT = np.dtype([("npar", "<i4"), ("nchain", "<i4"), ("nmc", "<i4"), ("_pad", "<i4"), ("theta", "<u8"), ("lp", "<u8"), ("ll", "<u8")])
+assert _SAMPLES_DT.itemsize == C.sizeof(B.SamplesT)
+
+
+def _samples_array(outs):
+    S = len(outs)
+    tab = np.zeros(S, dtype=_SAMPLES_DT)
+    big = getattr(outs, "big", None)
+    if big is not None:
+        _, _, nmc, nchain, npar = big[0].shape
+        idx = np.arange(S, dtype=np.uint64)
+        tab["npar"], tab["nchain"], tab["nmc"] = npar, nchain, nmc
+        for name, a in zip(("theta", "lp", "ll"), big):
+            tab[name] = np.uint64(_addr(a)) + idx * np.uint64(a.strides[0])
+    else:
+        for i, o in enumerate(outs):
+            _, nmc, nchain, npar = o.theta.shape
+            tab[i] = (npar, nchain, nmc, 0, _addr(o.theta), _addr(o.lp), _addr(o.ll))
+    return (tab, outs), tab.ctypes.data_as(C.POINTER(B.SamplesT))
+
+
 def _progress(cb):
     if cb is None:
         return C.cast(None, B.PROGRESS_FN)
@@ -157,22 +243,29 @@ def alloc_hier_outputs(S: int, R: int, nmc: int, nchain: int, npar: int, touch: 
     if touch:
         for a in (big_t, big_lp, big_ll):
             a.fill(0.0)
-    return phi_out, [PopSamples(big_t[s], big_lp[s], big_ll[s]) for s in range(S)]
+    subj = HierOutputs(PopSamples(big_t[s], big_lp[s], big_ll[s]) for s in range(S))
+    subj.big = (big_t, big_lp, big_ll)
+    return phi_out, subj
 
 
 def run_hier(ct: CellTable, trials: Sequence[Trials], p_prior: PriorTable, h_prior: PriorTable, tuning: Tuning,
              phi_start: PopState, subj_start: Sequence[PopState], progress=None, out=None):
     """`run` of the reference: returns (phi PopSamples, [subject PopSamples]).  `out` may carry
     preallocated outputs from :func:`alloc_hier_outputs`."""
+    import os, time
+    t0 = time.perf_counter()
     m, t, p, h, cfg = _model(ct), _trials(trials), _prior(p_prior), _prior(h_prior), _config(tuning)
     R, S = len(tuning.seeds), len(trials)
     phi_out, subj_out = out if out is not None else alloc_hier_outputs(S, R, tuning.nmc, tuning.nchain, ct.npar)
-    starts = (B.StartT * S)(*[s.c() for s in subj_start])
-    outs = (B.SamplesT * S)(*[o.c() for o in subj_out])
+    _keep_s, starts = _start_array(subj_start)
+    _keep_o, outs = _samples_array(subj_out)
     pc, poc, err, cb = phi_start.c(), phi_out.c(), B.errbuf(), _progress(progress)
+    t1 = time.perf_counter()
     rc = B.lib().ggdmc_b200_run(C.byref(m.c), C.byref(t.c), C.byref(p.c), C.byref(h.c), C.byref(cfg.c), C.byref(pc), starts,
                                 C.byref(poc), outs, cb, None, err)
     B.check(rc, err)
+    if os.environ.get("GGDMC_B200_TIMING"):
+        print(f"[ggdmc_b200] python marshal {1e3 * (t1 - t0):.3f} ms, C call {1e3 * (time.perf_counter() - t1):.3f} ms", file=__import__("sys").stderr)
     return phi_out, subj_out
 
 
@@ -255,8 +348,8 @@ class Engine:
         S = len(trials)
         self.R, self.S, self.C, self.D = len(tuning.seeds), S, tuning.nchain, ct.npar
         self.hier = h_prior is not None
-        starts = (B.StartT * S)(*[s.c() for s in subj_start])
-        self._starts = (starts, subj_start, phi_start)
+        keep_s, starts = _start_array(subj_start)
+        self._starts = (keep_s, starts, subj_start, phi_start)
         pc = phi_start.c() if phi_start is not None else None
         self.h = C.c_void_p()
         err = B.errbuf()

@@ -58,10 +58,10 @@ class HierWorkload:
     name: str
     spec: ModelSpec
     true_theta: np.ndarray  # [S, npar]
-    trials: List[Trials]
+    trials: object  # E.TrialsStack (list-like of Trials)
     nchain: int
     phi_start: E.PopState
-    subj_start: List[E.PopState]
+    subj_start: object  # E.PopStateStack (list-like of PopState)
 
     @property
     def n_trial_total(self) -> int:
@@ -126,8 +126,8 @@ def hierarchical(name: str, model_k: int, n_subject: int, n_trial: int, n_replic
                        np.ascontiguousarray(ph[:, D:])).reshape(S, R, C)
     phi_lp = E.sumlogprior(spec.h_prior, phi0.reshape(R * C, 2 * D)).reshape(R, C)
     phi_ll = lp.sum(axis=0)  # local subjects only; refreshed (and all-reduced) by the first phi step anyway
-    return HierWorkload(name, spec, sh.true_theta, trials, C, E.PopState(phi0, phi_lp, phi_ll),
-                        [E.PopState(subj0[i], lp[i], ll[i]) for i in range(S)])
+    return HierWorkload(name, spec, sh.true_theta, E.TrialsStack(trials), C, E.PopState(phi0, phi_lp, phi_ll),
+                        E.PopStateStack(subj0, lp, ll))
 
 
 def tuning_for(w: HierWorkload, nmc: int, thin: int, seeds, schedule=None, pop_migration_prob=0.05, sub_migration_prob=0.05,
