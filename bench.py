@@ -336,8 +336,15 @@ def main():
         lik_per_launch = n_lik_prof / like_launches
         achieved = F_TRIAL[n_acc] * lik_per_launch / per_launch_s / 1e12
         bytes_per_launch = 10.0 * lik_per_launch
+        traffic = None  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_like_traffic.json")))
+            if args.workload in tj and args.schedule == "parallel" and world == 1:
+                traffic = tj[args.workload]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                    "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
                     "kernel": "gg::k_like", "peak_source": "DFMA microbenchmark on this GPU (ggdmc_b200_measure_fp64_tflops), burst",
                     "flop_per_trial_lik": F_TRIAL[n_acc], "trial_lik_per_launch": lik_per_launch,
                     "launch_ms": per_launch_s * 1e3, "kernel_share_of_step": like_ms / ms_prof,

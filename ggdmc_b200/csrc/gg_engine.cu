@@ -513,13 +513,17 @@ struct ggdmc_engine {
 
     ~ggdmc_engine()
     {
+        PhaseTimer pt;
         if (stream) cudaStreamSynchronize(stream); // buffers go back to the pool right after this
+        pt.lap("  ~sync");
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
+        pt.lap("  ~graph");
         for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
+        pt.lap("  ~stream");
     }
 
     void common_init(const ggdmc_config_t *cfg)
