@@ -1156,23 +1156,23 @@ int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *t
     GG_CATCH
 }
 
-int ggdmc_b200_sumloglike(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta, int32_t n_theta,
-                          double *out, char err[256])
+namespace {
+void sumloglike_impl(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta, int32_t n_theta, double zero_floor,
+                     double *out)
 {
-    GG_TRY
     require(model && trials && theta && out && n_theta >= 1, "bad arguments");
     pick_device(-1);
     ModelDev M;
     M.upload(model);
     TrialsDev T;
     T.upload(trials, model->n_cell, false);
+    T.d.zero_floor = zero_floor;
     const int S = T.S, D = model->npar;
     T.set_chunking((int64_t)S * n_theta);
     DBuf<double> d_theta, d_part;
     DBuf<int> d_target, d_mode;
     DBuf<uint64_t> d_seed;
     DBuf<uint32_t> d_iter;
-    DBuf<unsigned int> done_ctr;
     const size_t n = (size_t)S * n_theta;
     d_theta.upload(theta, n * D);
     d_part.alloc(n * T.d.nsplit);
@@ -1191,6 +1191,22 @@ int ggdmc_b200_sumloglike(const ggdmc_model_t *model, const ggdmc_trials_t *tria
         for (int k = 0; k < T.d.nsplit; ++k) v += h[i * T.d.nsplit + k];
         out[i] = v;
     }
+}
+} // namespace
+
+int ggdmc_b200_sumloglike(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta, int32_t n_theta,
+                          double *out, char err[256])
+{
+    GG_TRY
+    sumloglike_impl(model, trials, theta, n_theta, 0.0, out);
+    GG_CATCH
+}
+
+int ggdmc_b200_sumloglike_init(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta, int32_t n_theta,
+                               double *out, char err[256])
+{
+    GG_TRY
+    sumloglike_impl(model, trials, theta, n_theta, 2.220446049250313e-16 /* .Machine$double.eps */, out);
     GG_CATCH
 }
 

@@ -357,6 +357,7 @@ struct TrialData {
     int chunk;               // trials per block (multiple of 8)
     int nsplit;              // blocks per (population, chain)
     unsigned long long *counter; // trial-likelihoods evaluated so far (one atomicAdd per block)
+    double zero_floor;           // > 0: densities <= 0 are replaced by this value (R-side init rule, R/phi.R:3-13); 0: off
 };
 
 constexpr double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
@@ -457,6 +458,7 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
     const uint16_t *cl = T.cell + T.offset[s];
     LogProd acc;
     acc.init();
+    const double zf = T.zero_floor;
     // Hot loop.  Two trials per thread per pass: one 16-byte RT load + one 4-byte cell load (subjects are
     // padded to a multiple of 8 trials with cell = 0xFFFF); the pair is processed by a rolled loop so the
     // loop body stays small.  Only fast-path trials (regular cell, rt > t0) are evaluated here; anything
@@ -472,8 +474,12 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
             const int c = h ? c2.y : c2.x;
             const double r = h ? r2.y : r2.x;
             const CellAcc *e = ent + c * na;
-            if (bad[c] == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) acc.mul_fast(n1pdf_fast<NACC>(r, e, na));
-            else leftovers = true;
+            if (bad[c] == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) {
+                double pdf = n1pdf_fast<NACC>(r, e, na);
+                if (zf > 0.0 && pdf <= 0.0) pdf = zf;
+                acc.mul_fast(pdf);
+            } else
+                leftovers = true;
         }
     }
     if (leftovers) { // cold loop: invalid / generic cells and trials with rt <= t0
@@ -485,7 +491,9 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
                 const CellAcc *e = ent + c * na;
                 const uint8_t cls = bad[c];
                 if (cls == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) continue; // done in the hot loop
-                acc.mul(cls == kCellInvalid ? kFloor : n1pdf_generic_body<NACC>(r, e, na));
+                double pdf = cls == kCellInvalid ? kFloor : n1pdf_generic_body<NACC>(r, e, na);
+                if (zf > 0.0 && pdf <= 0.0) pdf = zf;
+                acc.mul(pdf);
             }
         }
     }

@@ -128,30 +128,6 @@ GG_HD bool n1pdf_fast_ok(double rt, const CellAcc *e, int n_acc_rt)
 template <int NACC>
 GG_HD double n1pdf_fast(double rt, const CellAcc *e, int n_acc_rt)
 {
-    if (NACC == 2) {
-        // both accumulators' four (Phi, phi) pairs in one batch of independent Horner chains
-        const double dt0 = rt - e[0].t0a;
-        const double rdt0 = fm::rcp_pos(dt0);
-        double dt1 = dt0, rdt1 = rdt0;
-        if (e[1].t0a != e[0].t0a) {
-            dt1 = rt - e[1].t0a;
-            rdt1 = fm::rcp_pos(dt1);
-        }
-        const double rts0 = e[0].inv_sdv * rdt0, tv0 = e[0].mean_v * dt0;
-        const double rts1 = e[1].inv_sdv * rdt1, tv1 = e[1].mean_v * dt1;
-        const double x1 = e[1].b - tv1, x2 = x1 - e[1].A;
-        const double z[4] = {(e[0].b - tv0) * rts0, ((e[0].b - e[0].A) - tv0) * rts0, x1 * rts1, x2 * rts1};
-        double cdf[4], pdf[4];
-        fm::norm_pairs_finite<4>(z, cdf, pdf);
-        const double t1 = e[0].mean_v * (cdf[0] - cdf[1]);
-        const double t2 = e[0].sd_v * (pdf[1] - pdf[0]);
-        const double win = fmax((t1 + t2) * (e[0].inv_A * e[0].inv_denom), kFloor);
-        const double ts = e[1].sd_v * dt1;
-        const double s = x2 * cdf[3] - x1 * cdf[2] + ts * (pdf[3] - pdf[2]);
-        double c = (1.0 + s * e[1].inv_A) * e[1].inv_denom;
-        c = c < kFloor ? kFloor : (1.0 < c ? 1.0 : c);
-        return win * (1.0 - c);
-    }
     const int n_acc = NACC > 0 ? NACC : n_acc_rt;
     double t0a = e[0].t0a;
     double dt = rt - t0a;

@@ -279,14 +279,16 @@ def trial_logdens(ct: CellTable, trials: Trials, theta: np.ndarray) -> np.ndarra
     return out
 
 
-def sumloglike(ct: CellTable, trials: Sequence[Trials], theta: np.ndarray) -> np.ndarray:
-    """theta [S, n_theta, npar] -> summed log-likelihoods [S, n_theta]."""
+def sumloglike(ct: CellTable, trials: Sequence[Trials], theta: np.ndarray, init_rule: bool = False) -> np.ndarray:
+    """theta [S, n_theta, npar] -> summed log-likelihoods [S, n_theta].  init_rule: densities <= 0 are floored at
+    .Machine$double.eps like the R-side initialisation path does (R/phi.R:3-13)."""
     m, t = _model(ct), _trials(trials)
     th = B.f64(theta)
     assert th.ndim == 3 and th.shape[0] == len(trials) and th.shape[2] == ct.npar
     out = np.empty(th.shape[:2])
     err = B.errbuf()
-    B.check(B.lib().ggdmc_b200_sumloglike(C.byref(m.c), C.byref(t.c), B.ptr(th), th.shape[1], B.ptr(out), err), err)
+    f = B.lib().ggdmc_b200_sumloglike_init if init_rule else B.lib().ggdmc_b200_sumloglike
+    B.check(f(C.byref(m.c), C.byref(t.c), B.ptr(th), th.shape[1], B.ptr(out), err), err)
     return out
 
 

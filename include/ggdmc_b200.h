@@ -165,6 +165,12 @@ int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *t
 int ggdmc_b200_sumloglike(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta,
                           int32_t n_theta, double *out, char err[256]);
 
+/* The same sum under the R-side initialisation rule (R/phi.R:3-13, `.sumlog`, used by initialise_theta
+ * R/phi.R:166-201): a density <= 0 is replaced by .Machine$double.eps before the log, so a start value
+ * whose likelihood the sampler would score -Inf still gets a finite (very low) score. */
+int ggdmc_b200_sumloglike_init(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta,
+                               int32_t n_theta, double *out, char err[256]);
+
 /* prior_class::sumlogprior (@hdr/prior.h:469-476): x [n][npar] -> out [n].  p0/p1 may be NULL
  * (use the prior's own) or [n][npar] per-vector overrides (the phi-driven case, src/de.cpp:599-600). */
 int ggdmc_b200_sumlogprior(const ggdmc_prior_t *prior, const double *x, const double *p0, const double *p1, int32_t n,

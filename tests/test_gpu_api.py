@@ -1,0 +1,122 @@
+"""GPU tests (-m gpu) of the reference-level Python mirror: ggdmc_b200.api (run_subject / run_hyper / run on
+objects with the reference's S4 slot names) and ggdmc_b200.init (initialise_theta / initialise_phi)."""
+import numpy as np
+import pytest
+
+from ggdmc_b200 import _lib as B
+from ggdmc_b200 import api, init
+from ggdmc_b200 import engine as E
+from oracle import binding as ob
+from helpers import load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def fixture_objects(k):
+    """Rebuild the reference's model / dmi / prior objects of fixture k from the committed golden file."""
+    fx = load_fixture(k)
+    g = fx.g
+    model = api.Model(parameter_x_condition_names=[str(s) for s in g["pxc_names"]], pnames=fx.ct.pnames, cell_names=fx.ct.cell_names,
+                      constants=api.NamedVector(g["const_val"], [str(s) for s in g["const_names"]]), model_boolean=g["model_boolean"],
+                      type="lba", npar=fx.ct.npar)
+
+    def dmi_of(which):
+        tr = fx.trials(which)
+        data = api.NamedList({fx.ct.cell_names[c]: tr.rt[tr.cell == c] for c in np.unique(tr.cell)})
+        return api.DMI(model=model, data=data, node_1_index=g["node_1_index"], is_positive_drift=g["is_positive_drift"])
+
+    return fx, model, dmi_of
+
+
+def test_flattening_of_reference_objects_matches_goldens():
+    for k in (2, 3, 5, 6):
+        fx, model, dmi_of = fixture_objects(k)
+        from ggdmc_b200.model import build_cell_table, flatten_data
+        ct = build_cell_table(model, fx.g["node_1_index"], fx.g["is_positive_drift"])
+        assert np.array_equal(ct.param_src, fx.ct.param_src) and np.array_equal(ct.const_val, fx.ct.const_val)
+        tr = flatten_data(dmi_of("sub").data, ct.cell_names)
+        assert np.array_equal(tr.rt, fx.trials("sub").rt) and np.array_equal(tr.cell, fx.trials("sub").cell)
+
+
+def test_run_subject_through_reference_interface():
+    """StartSampling_subject's inner call: config + dmi + fresh start samples -> posterior (R/sampling.R:446-502)."""
+    fx, model, dmi_of = fixture_objects(6)
+    dmi = dmi_of("sub")
+    D, nchain, nmc, thin = fx.ct.npar, 3 * fx.ct.npar, 6, 2
+    prior = api.Prior(nparameter=D, pnames=fx.ct.pnames, p_prior=api.prior_list(fx.prior("sub_prior")))
+    ti = api.ThetaInput(nmc=nmc, nchain=nchain, thin=thin, nparameter=D, pnames=fx.ct.pnames, report_length=2, is_print=True)
+    de = api.DEInput(sub_migration_prob=0.06, nparameter=D, nchain=nchain)
+    configs = [api.Config(prior=prior, theta_input=ti, de_input=de, seed=s) for s in (101, 202, 303)]  # ncore = 3 replicates
+    starts = [init.initialise_theta(ti, prior, dmi, seed=s) for s in (1, 2, 3)]
+    for st in starts:  # a fresh start object: slice 1 valid, the rest NaN / -Inf (R/phi.R:72-88)
+        assert np.all(np.isfinite(st.theta[:, :, 0])) and np.all(np.isnan(st.theta[:, :, 1:]))
+        assert np.all(np.isfinite(st.log_likelihoods[:, 0])) and np.all(np.isfinite(st.summed_log_prior[:, 0]))
+        # the stored scores are the oracle's R-init-path values
+        od, op = fx.odata("sub"), fx.oprior("sub_prior")
+        for c in (0, 7, nchain - 1):
+            ref = ob.sumloglike_rinit(fx.om, od, st.theta[:, c, 0])
+            assert abs(st.log_likelihoods[c, 0] - ref) <= 1e-9 * abs(ref)
+            assert abs(st.summed_log_prior[c, 0] - ob.sumlogprior(op, st.theta[:, c, 0])) <= 1e-9
+    seen = []
+    fits = api.run_subject(configs, dmi, starts, progress=seen.append)
+    assert len(fits) == 3 and seen  # progress callback fired (report_length = 2)
+    for st, fit in zip(starts, fits):
+        assert fit.theta.shape == (D, nchain, nmc) and fit.summed_log_prior.shape == (nchain, nmc) and fit.nmc == nmc
+        assert fit.pnames == fx.ct.pnames and fit.thin == thin and fit.start == 1 and fit.npar == D and fit.nchain == nchain
+        assert np.array_equal(fit.theta[:, :, 0], st.theta[:, :, 0]) and np.array_equal(fit.log_likelihoods[:, 0], st.log_likelihoods[:, 0])
+        assert np.all(np.isfinite(fit.theta)) and not np.array_equal(fit.theta[:, :, 0], fit.theta[:, :, -1])
+    # RestartSampling_subject: feed the fit back as `samples`; sampling continues from its last slice
+    again = api.run_subject(configs[0], dmi, fits[0])
+    assert np.array_equal(again.theta[:, :, 0], fits[0].theta[:, :, -1])
+    # same seed, same start -> same fit (reproducibility); other seed -> other fit
+    rep = api.run_subject(configs[0], dmi, starts[0])
+    assert np.array_equal(rep.theta, fits[0].theta) and not np.array_equal(fits[0].theta, fits[1].theta)
+
+
+def test_run_and_run_hyper_through_reference_interface():
+    """StartSampling / StartSampling_hyper inner calls (R/sampling.R:247-304, 615-677)."""
+    fx, model, dmi_of = fixture_objects(2)
+    S, D = fx.n_pop, fx.ct.npar
+    dmis = [dmi_of(f"pop{s}") for s in range(S)]
+    nchain, nmc, thin = 6 * D, 5, 2
+    pp, hp = fx.prior("p_prior"), fx.prior("h_prior")
+    prior = api.Prior(nparameter=2 * D, pnames=hp.pnames, p_prior=api.prior_list(pp), h_prior=api.prior_list(hp))
+    ti = api.ThetaInput(nmc=nmc, nchain=nchain, thin=thin, nparameter=2 * D, pnames=hp.pnames)
+    de = api.DEInput(pop_migration_prob=0.05, sub_migration_prob=0.05, nparameter=2 * D, nchain=nchain)
+    cfg = api.Config(prior=prior, theta_input=ti, de_input=de, seed=9032)
+    start = init.initialise_phi(ti, prior, dmis, seed=5)
+    assert start["phi"].theta.shape == (2 * D, nchain, nmc) and len(start["subject_theta"]) == S
+    # phi start scores = h_prior density and hyper-likelihood of the subjects' chain-k thetas (oracle)
+    opp, ohp = fx.oprior("p_prior"), fx.oprior("h_prior")
+    for c in (0, nchain - 1):
+        phi_c = start["phi"].theta[:, c, 0]
+        hl = sum(ob.sumlogprior(opp, s.theta[:, c, 0], phi_c[:D], phi_c[D:]) for s in start["subject_theta"])
+        assert abs(start["phi"].log_likelihoods[c, 0] - hl) <= 1e-9 * abs(hl)
+        assert abs(start["phi"].summed_log_prior[c, 0] - ob.sumlogprior(ohp, phi_c)) <= 1e-9
+    fit = api.run(cfg, dmis, start)
+    assert set(fit) == {"phi", "subject_theta"} and len(fit["subject_theta"]) == S
+    assert fit["phi"].theta.shape == (2 * D, nchain, nmc) and fit["subject_theta"][0].theta.shape == (D, nchain, nmc)
+    assert fit["phi"].pnames == hp.pnames and fit["subject_theta"][0].pnames == fx.ct.pnames
+    assert np.all(np.isfinite(fit["phi"].theta)) and np.array_equal(fit["phi"].theta[:, :, 0], start["phi"].theta[:, :, 0])
+    refit = api.run(cfg, dmis, fit)  # RestartSampling
+    assert np.array_equal(refit["phi"].theta[:, :, 0], fit["phi"].theta[:, :, -1])
+    # hyper-only fit on the matrix of "true" subject thetas
+    hyper_dmi = api.DMI(model=api.Model([], [], [], api.NamedVector([], []), np.zeros((0, 0, 0), bool), type="hyper"), data=fx.g["hyper_data"])
+    phi_start = start["phi"]
+    hfit = api.run_hyper(cfg, hyper_dmi, phi_start)
+    assert hfit.theta.shape == (2 * D, nchain, nmc) and np.all(np.isfinite(hfit.theta[:, :, 0]))
+
+
+def test_reference_errors_surface():
+    fx, model, dmi_of = fixture_objects(2)
+    D = fx.ct.npar
+    prior = api.Prior(nparameter=D, pnames=fx.ct.pnames, p_prior=api.prior_list(fx.prior("sub_prior")))
+    ti = api.ThetaInput(nmc=3, nchain=2, thin=1, nparameter=D, pnames=fx.ct.pnames)
+    cfg = api.Config(prior=prior, theta_input=ti, de_input=api.DEInput(nparameter=D, nchain=2), seed=1)
+    st = api.Posterior(np.ones((D, 2, 3)), np.zeros((2, 3)), np.zeros((2, 3)), 1, D, fx.ct.pnames, 3, 1, 2)
+    with pytest.raises(B.GgdmcError, match="three or more chains"):
+        api.run_subject(cfg, dmi_of("sub"), st)
+    bad = dmi_of("sub")
+    bad.model = api.Model(model.parameter_x_condition_names, model.pnames, model.cell_names, model.constants, model.model_boolean, type="fastdm")
+    with pytest.raises(B.GgdmcError, match="Undefined model type"):
+        api.run_subject(cfg, bad, st)
