@@ -488,6 +488,12 @@ struct ggdmc_engine {
     int64_t launches = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // Hierarchy: the phi sweep of an iteration does not feed the subjects' proposals or likelihoods
+    // (only their MH test, through the prior), so it runs on a high-priority side stream next to the
+    // first likelihood launch and joins before the first k_accept.  GGDMC_B200_NO_OVERLAP=1 serialises.
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap = std::getenv("GGDMC_B200_NO_OVERLAP") == nullptr;
     // optional per-launch timing of the likelihood kernel (bench.py roofline)
     // one DE-MCMC iteration captured as a CUDA graph (fixed launch sequence: every data-dependent
     // decision is taken on the device); GGDMC_B200_NO_GRAPH=1 falls back to plain stream launches
@@ -522,6 +528,9 @@ struct ggdmc_engine {
         for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side) cudaStreamDestroy(side);
         if (stream) cudaStreamDestroy(stream);
         pt.lap("  ~stream");
     }
@@ -540,7 +549,12 @@ struct ggdmc_engine {
         schedule = (cfg->schedule == GGDMC_SCHEDULE_PARALLEL && cfg->nchain < 4) ? GGDMC_SCHEDULE_REFERENCE : cfg->schedule;
         is_hblocked = cfg->is_hblocked; is_pblocked = cfg->is_pblocked;
         subject_begin = cfg->subject_begin;
-        CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_lo));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreate(&ev0));
         CUDA_CHECK(cudaEventCreate(&ev1));
         seeds.upload(cfg->seed, R);
@@ -697,7 +711,7 @@ struct ggdmc_engine {
     }
 
     // ---- one sweep at each level --------------------------------------------------------------
-    void sweep_lba(int sweep, int decide_once, int para_idx)
+    void sweep_lba(int sweep, int decide_once, int para_idx, cudaEvent_t join = nullptr)
     {
         Level &L = subj.L;
         const size_t prop_sm = (size_t)kProposeWarps * D * 8;
@@ -711,6 +725,7 @@ struct ggdmc_engine {
                 const int nw = half < 0 ? n : L.npop * ((C + 1) / 2); // warps: one per (population, chain) or per (population, slot)
                 k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1, half);
                 timed_like(L, sweep, -1, half);
+                if (join && h == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0)); // the MH test needs this iteration's phi
                 k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, ll_part.p, trials.d.nsplit);
                 launches += 3;
             }
@@ -718,6 +733,7 @@ struct ggdmc_engine {
             for (int step = 0; step < C; ++step) {
                 k_propose<kProposeWarps><<<(L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step, -1);
                 timed_like(L, sweep, step, -1);
+                if (join && step == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0));
                 k_accept<<<(L.npop + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, step, ll_part.p, trials.d.nsplit);
                 launches += 3;
             }
@@ -725,33 +741,33 @@ struct ggdmc_engine {
         CUDA_CHECK(cudaGetLastError());
     }
 
-    void hyper_eval(int step)
+    void hyper_eval(int step, cudaStream_t st)
     {
         Level &P = phi.L;
         const size_t sm = (size_t)(6 * D + 2 * (kHyperBlock / 32)) * 8;
         dim3 grid(step < 0 ? R * C : R, H.nsplit, step < 0 ? 1 : 2);
-        k_hyper<kHyperBlock><<<grid, kHyperBlock, sm, stream>>>(P, H, step, hpart.p);
+        k_hyper<kHyperBlock><<<grid, kHyperBlock, sm, st>>>(P, H, step, hpart.p);
         const int n = R * C * 2;
         const bool multi = kind == 2 && g_nccl.comm && g_nccl.n_rank > 1;
         if (multi && g_p2p.ready && n <= kP2PMaxN) {
             // the one exchange of the path, fused with the local reduction (peer-memory stores over NVLink)
-            k_hyper_reduce_exchange<<<1, 256, 0, stream>>>(hpart.p, n, H.nsplit, hsum.p, g_p2p.win);
+            k_hyper_reduce_exchange<<<1, 256, 0, st>>>(hpart.p, n, H.nsplit, hsum.p, g_p2p.win);
             launches += 2;
         } else {
-            k_hyper_reduce<<<(n + 127) / 128, 128, 0, stream>>>(hpart.p, n, H.nsplit, hsum.p);
+            k_hyper_reduce<<<(n + 127) / 128, 128, 0, st>>>(hpart.p, n, H.nsplit, hsum.p);
             launches += 2;
             if (multi) // fallback: partial sums over the local subjects -> sums over all subjects by NCCL
-                g_nccl.check(g_nccl.AllReduce(hsum.p, hsum.p, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, g_nccl.comm, stream),
+                g_nccl.check(g_nccl.AllReduce(hsum.p, hsum.p, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, g_nccl.comm, st),
                              "ncclAllReduce");
         }
     }
 
-    void sweep_phi(int sweep, int decide_once, int para_idx)
+    void sweep_phi(int sweep, int decide_once, int para_idx, cudaStream_t st)
     {
         Level &P = phi.L;
         const size_t prop_sm = (size_t)kProposeWarps * D2 * 8;
         const int need_cur = H.need_cur;
-        k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), stream>>>(P, d_iter.p, sweep, decide_once, para_idx);
+        k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), st>>>(P, d_iter.p, sweep, decide_once, para_idx);
         ++launches;
         if (schedule != GGDMC_SCHEDULE_REFERENCE) {
             const int n = R * C;
@@ -759,26 +775,26 @@ struct ggdmc_engine {
             for (int h = 0; h < nhalf; ++h) {
                 const int half = nhalf == 2 ? h : -1;
                 const int nw = half < 0 ? n : R * ((C + 1) / 2);
-                k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, -1, half);
-                hyper_eval(-1);
-                k_phi_accept<<<(n + 127) / 128, 128, 0, stream>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur);
+                k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, st>>>(P, d_iter.p, sweep, -1, half);
+                hyper_eval(-1, st);
+                k_phi_accept<<<(n + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur);
                 launches += 2;
             }
         } else {
             for (int step = 0; step < C; ++step) {
-                k_propose<kProposeWarps><<<(R + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(P, d_iter.p, sweep, step, -1);
-                hyper_eval(step);
-                k_phi_accept<<<(R + 127) / 128, 128, 0, stream>>>(P, d_iter.p, sweep, step, hsum.p, need_cur);
+                k_propose<kProposeWarps><<<(R + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, st>>>(P, d_iter.p, sweep, step, -1);
+                hyper_eval(step, st);
+                k_phi_accept<<<(R + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, step, hsum.p, need_cur);
                 launches += 2;
             }
         }
         CUDA_CHECK(cudaGetLastError());
     }
 
-    void phi_constants()
+    void phi_constants(cudaStream_t st)
     {
         const int n = R * C * D;
-        k_phi_consts<<<(n + 127) / 128, 128, 0, stream>>>(phi.L, p_prior.d, D, phi_consts.p);
+        k_phi_consts<<<(n + 127) / 128, 128, 0, st>>>(phi.L, p_prior.d, D, phi_consts.p);
         ++launches;
     }
 
@@ -806,15 +822,25 @@ struct ggdmc_engine {
     {
         ++h_iter;
         if (kind == 2) {
+            cudaStream_t ps = overlap ? side : stream;
+            if (overlap) {
+                CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+                CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork, 0));
+            }
             if (is_hblocked)
-                for (int p = 0; p < D2; ++p) sweep_phi(p, 0, p);
+                for (int p = 0; p < D2; ++p) sweep_phi(p, 0, p, ps);
             else
-                sweep_phi(0, 0, -1);
-            phi_constants();
+                sweep_phi(0, 0, -1, ps);
+            phi_constants(ps);
+            cudaEvent_t join = nullptr;
+            if (overlap) {
+                CUDA_CHECK(cudaEventRecord(ev_join, side));
+                join = ev_join;
+            }
             if (is_pblocked)
-                for (int p = 0; p < D; ++p) sweep_lba(p, 0, p);
+                for (int p = 0; p < D; ++p) sweep_lba(p, 0, p, p == 0 ? join : nullptr);
             else
-                sweep_lba(0, 0, -1);
+                sweep_lba(0, 0, -1, join);
             store_and_advance(subj, &phi);
         } else if (kind == 0) {
             if (is_pblocked)
@@ -824,9 +850,9 @@ struct ggdmc_engine {
             store_and_advance(subj, nullptr);
         } else {
             if (is_pblocked)
-                for (int p = 0; p < phi.L.nmove; ++p) sweep_phi(p, 1, p);
+                for (int p = 0; p < phi.L.nmove; ++p) sweep_phi(p, 1, p, stream);
             else
-                sweep_phi(0, 1, -1);
+                sweep_phi(0, 1, -1, stream);
             store_and_advance(phi, nullptr);
         }
     }

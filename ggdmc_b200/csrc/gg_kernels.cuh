@@ -265,6 +265,38 @@ __global__ void k_phi_consts(Level P, DevPrior like, int D, double *consts)
     consts[2 * (size_t)i + 1] = K;
 }
 
+// log prior density of one proposed parameter; ovr/oc: the phi chain that drives the prior, or null
+__device__ __forceinline__ double prior_term(const Level &L, int d, double x, const double *ovr, const double *oc)
+{
+    const int D = L.npar;
+    const double lo = L.prior.lower[d], up = L.prior.upper[d];
+    const double K = oc ? oc[2 * d + 1] : NAN;
+    if (K == K) { // phi-driven truncated normal, log scale: -(ln sqrt(2 pi) + z^2/2 + ln sd) - ln denom
+        const double z = (x - ovr[d]) * oc[2 * d];
+        return (x < lo || x > up) ? -INFINITY : -(0.5 * z * z + K);
+    }
+    const double q0 = ovr ? ovr[d] : L.prior.p0[d], q1 = ovr ? ovr[D + d] : L.prior.p1[d];
+    return dprior1(L.prior.dist[d], x, q0, q1, lo, up, L.prior.log_p[d] != 0);
+}
+
+// prior_class::sumlogprior of the proposal made from chain src under phi chain src (src/de.cpp:599-604, 646-653)
+__device__ __forceinline__ double deferred_prop_lp(const Level &L, int p, int src)
+{
+    const int C = L.nchain, D = L.npar;
+    const size_t rc = (size_t)(p % L.n_rep) * C + src;
+    const double *ovr = L.prior_ovr + rc * 2 * D;
+    const double *oc = L.ovr_consts ? L.ovr_consts + rc * 2 * D : nullptr;
+    const double *pr = L.prop + ((size_t)p * C + src) * D;
+    double a1 = 0.0, a2 = 0.0; // arma::accu order, as sum_arma_order
+    int d = 0;
+    for (; d + 1 < D; d += 2) {
+        a1 += prior_term(L, d, pr[d], ovr, oc);
+        a2 += prior_term(L, d + 1, pr[d + 1], ovr, oc);
+    }
+    if (d < D) a1 += prior_term(L, d, pr[d], ovr, oc);
+    return a1 + a2;
+}
+
 // One warp per (population, sweep position).
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t *d_iter, int sweep, int step, int half)
@@ -312,9 +344,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t 
     const double *t0 = L.theta + ((size_t)p * C + c0) * D;
     const double *t1 = L.theta + ((size_t)p * C + c1) * D;
     double *pr = L.prop + ((size_t)p * C + src) * D;
-    const size_t rc = (size_t)(p % L.n_rep) * C + src;
-    const double *ovr = L.prior_ovr ? L.prior_ovr + rc * 2 * D : nullptr;
-    const double *oc = (ovr && L.ovr_consts) ? L.ovr_consts + rc * 2 * D : nullptr;
+    // a phi-driven prior is evaluated in k_accept instead: the proposal and its likelihood do not need
+    // this iteration's phi, so they can run while the phi sweep is still in flight
+    const bool defer = L.prior_ovr != nullptr;
+    const double *ovr = nullptr, *oc = nullptr;
     for (int d = lane; d < D; d += 32) {
         double x = th[d];
         const bool moved = para_idx >= 0 ? (d == para_idx) : (d < L.nmove);
@@ -325,21 +358,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t 
             x = __dadd_rn(x, inc);
         }
         pr[d] = x;
-        const double lo = L.prior.lower[d], up = L.prior.upper[d];
-        double v;
-        const double K = oc ? oc[2 * d + 1] : NAN;
-        if (K == K) { // phi-driven truncated normal, log scale: -(ln sqrt(2 pi) + z^2/2 + ln sd) - ln denom
-            const double z = (x - ovr[d]) * oc[2 * d];
-            v = (x < lo || x > up) ? -INFINITY : -(0.5 * z * z + K);
-        } else {
-            const double q0 = ovr ? ovr[d] : L.prior.p0[d], q1 = ovr ? ovr[D + d] : L.prior.p1[d];
-            v = dprior1(L.prior.dist[d], x, q0, q1, lo, up, L.prior.log_p[d] != 0);
-        }
-        scratch[d] = v;
+        if (!defer) scratch[d] = prior_term(L, d, x, ovr, oc);
     }
     __syncwarp();
     if (lane == 0) {
-        L.prop_lp[p * C + src] = sum_arma_order(scratch, D);
+        if (!defer) L.prop_lp[p * C + src] = sum_arma_order(scratch, D);
         L.target[p * C + src] = tgt;
     }
     __syncwarp();
@@ -589,7 +612,7 @@ __global__ void k_accept(Level L, const uint32_t *d_iter, int sweep, int step, c
     double tmp_ll = 0.0;
     const double *part = ll_part + ((size_t)p * C + src) * nsplit;
     for (int k = 0; k < nsplit; ++k) tmp_ll += part[k];
-    const double tmp_lp = L.prop_lp[p * C + src];
+    const double tmp_lp = L.prior_ovr ? deferred_prop_lp(L, p, src) : L.prop_lp[p * C + src];
     const double cur = L.lp[p * C + tgt] + L.ll[p * C + tgt];     // src/de.cpp:121 / :189-190 / :577 / :656-657
     const double mh = exp((tmp_lp + tmp_ll) - cur);               // :147
     L.target[p * C + src] = -1;                                    // proposal consumed
