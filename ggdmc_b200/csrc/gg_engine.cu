@@ -339,6 +339,7 @@ struct TrialsDev {
         int want = (int)std::max<int64_t>(1, (4 * 148 + blocks_per_split_unit - 1) / blocks_per_split_unit);
         int max_split = std::max(1, (max_count + 255) / 256);
         int nsplit = std::min(want, max_split);
+        if (const char *e = std::getenv("GGDMC_B200_NSPLIT")) nsplit = std::max(1, std::min(std::atoi(e), std::max(1, max_count / 8))); // experiments
         if (max_count > 8192) nsplit = std::max(nsplit, (max_count + 4095) / 4096);
         int chunk = ((std::max(1, (max_count + nsplit - 1) / nsplit)) + 7) & ~7;
         nsplit = std::max(1, (max_count + chunk - 1) / chunk);
@@ -473,10 +474,57 @@ void launch_like(const Level &L, const DevModel &M, const TrialData &T, const ui
 
 } // namespace
 
+// GGDMC_B200_TRACE=1: every launch of an iteration is bracketed by CUDA events on its own stream and the
+// last iteration's timeline (start, duration, stream) goes to stderr -- a diagnostic, never a bench path.
+struct Tracer {
+    struct Rec { const char *name; int side; cudaEvent_t a, b; };
+    bool on = std::getenv("GGDMC_B200_TRACE") != nullptr;
+    std::vector<Rec> recs;
+    size_t used = 0;
+    void reset() { used = 0; }
+    void open(const char *name, cudaStream_t st, bool is_side)
+    {
+        if (!on) return;
+        if (used == recs.size()) {
+            Rec r{name, 0, nullptr, nullptr};
+            cudaEventCreate(&r.a);
+            cudaEventCreate(&r.b);
+            recs.push_back(r);
+        }
+        recs[used].name = name;
+        recs[used].side = is_side;
+        cudaEventRecord(recs[used].a, st);
+    }
+    void close(cudaStream_t st)
+    {
+        if (!on) return;
+        cudaEventRecord(recs[used].b, st);
+        ++used;
+    }
+    void dump(int rank)
+    {
+        if (!on || used == 0) return;
+        cudaDeviceSynchronize();
+        std::fprintf(stderr, "[ggdmc_b200 trace] rank %d, last iteration: start_us dur_us stream kernel\n", rank);
+        for (size_t i = 0; i < used; ++i) {
+            float t0 = 0.f, d = 0.f;
+            cudaEventElapsedTime(&t0, recs[0].a, recs[i].a);
+            cudaEventElapsedTime(&d, recs[i].a, recs[i].b);
+            std::fprintf(stderr, "[ggdmc_b200 trace] %9.1f %8.1f %s %s\n", t0 * 1e3, d * 1e3, recs[i].side ? "side" : "main", recs[i].name);
+        }
+    }
+    ~Tracer()
+    {
+        for (Rec &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    }
+};
+#define TR(name, st, ...) do { trace.open(name, st, (st) == side); __VA_ARGS__; trace.close(st); } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // the engine
 // ---------------------------------------------------------------------------------------------
 struct ggdmc_engine {
+    Tracer trace;
     // kind: 0 independent subjects (run_subject), 1 hyper only (run_hyper), 2 hierarchy (run)
     int kind = 0;
     int device = 0;
@@ -494,10 +542,11 @@ struct ggdmc_engine {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap = std::getenv("GGDMC_B200_NO_OVERLAP") == nullptr;
+    bool fuse_phi = std::getenv("GGDMC_B200_NO_FUSED_PHI") == nullptr;
     // optional per-launch timing of the likelihood kernel (bench.py roofline)
     // one DE-MCMC iteration captured as a CUDA graph (fixed launch sequence: every data-dependent
     // decision is taken on the device); GGDMC_B200_NO_GRAPH=1 falls back to plain stream launches
-    bool use_graph = std::getenv("GGDMC_B200_NO_GRAPH") == nullptr;
+    bool use_graph = std::getenv("GGDMC_B200_NO_GRAPH") == nullptr && std::getenv("GGDMC_B200_TRACE") == nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     int64_t launches_per_iter = 0;
@@ -513,7 +562,7 @@ struct ggdmc_engine {
     LevelDev subj, phi;
     DBuf<uint64_t> seeds;
     DBuf<uint32_t> d_iter;
-    DBuf<unsigned int> done_ctr;
+    DBuf<unsigned int> done_ctr, phi_ticket;
     DBuf<double> ll_part, hpart, hsum, hyper_data, phi_consts;
     HyperArgs H{};
 
@@ -562,6 +611,8 @@ struct ggdmc_engine {
         d_iter.upload(&z, 1); // 0 while the start state is stored in slot 0, then 1 = first iteration
         done_ctr.alloc(1);
         done_ctr.zero();
+        phi_ticket.alloc(1);
+        phi_ticket.zero();
     }
 
     void init_level_state(LevelDev &lv, const ggdmc_start_t *starts, int n_items, int D_)
@@ -671,7 +722,7 @@ struct ggdmc_engine {
         H.S = S; H.D = D; H.need_cur = need_cur;
         // split subjects over blocks so that K4 fills the GPU (R*C blocks alone would not)
         int want = std::max(1, (8 * 148 + R * C - 1) / (R * C));
-        int spb = std::max(8, (S + want - 1) / want);
+        int spb = std::max(64, (S + want - 1) / want); // >= 3 terms per thread: the per-block setup (proposal, 4 Phi + 2 log per parameter) is not free
         H.subj_per_block = spb;
         H.nsplit = (S + spb - 1) / spb;
         hpart.alloc((size_t)R * C * 2 * H.nsplit);
@@ -684,7 +735,7 @@ struct ggdmc_engine {
     void timed_like(const Level &L, int sweep, int step, int half)
     {
         if (!profile) {
-            launch_like(L, model.d, trials.d, d_iter.p, sweep, step, half, ll_part.p, stream);
+            TR("k_like", stream, launch_like(L, model.d, trials.d, d_iter.p, sweep, step, half, ll_part.p, stream));
             return;
         }
         if (prof_used + 2 > prof_ev.size()) {
@@ -715,7 +766,7 @@ struct ggdmc_engine {
     {
         Level &L = subj.L;
         const size_t prop_sm = (size_t)kProposeWarps * D * 8;
-        k_sweep_begin<<<L.npop, 128, (size_t)2 * C * sizeof(int), stream>>>(L, d_iter.p, sweep, decide_once, para_idx);
+        TR("k_sweep_begin", stream, k_sweep_begin<<<L.npop, 128, (size_t)2 * C * sizeof(int), stream>>>(L, d_iter.p, sweep, decide_once, para_idx));
         ++launches;
         if (schedule != GGDMC_SCHEDULE_REFERENCE) {
             const int n = L.npop * C;
@@ -723,18 +774,18 @@ struct ggdmc_engine {
             for (int h = 0; h < nhalf; ++h) {
                 const int half = nhalf == 2 ? h : -1;
                 const int nw = half < 0 ? n : L.npop * ((C + 1) / 2); // warps: one per (population, chain) or per (population, slot)
-                k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1, half);
+                TR("k_propose", stream, k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1, half));
                 timed_like(L, sweep, -1, half);
                 if (join && h == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0)); // the MH test needs this iteration's phi
-                k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, ll_part.p, trials.d.nsplit);
+                TR("k_accept", stream, k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, ll_part.p, trials.d.nsplit));
                 launches += 3;
             }
         } else {
             for (int step = 0; step < C; ++step) {
-                k_propose<kProposeWarps><<<(L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step, -1);
+                TR("k_propose", stream, k_propose<kProposeWarps><<<(L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step, -1));
                 timed_like(L, sweep, step, -1);
                 if (join && step == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0));
-                k_accept<<<(L.npop + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, step, ll_part.p, trials.d.nsplit);
+                TR("k_accept", stream, k_accept<<<(L.npop + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, step, ll_part.p, trials.d.nsplit));
                 launches += 3;
             }
         }
@@ -746,15 +797,15 @@ struct ggdmc_engine {
         Level &P = phi.L;
         const size_t sm = (size_t)(6 * D + 2 * (kHyperBlock / 32)) * 8;
         dim3 grid(step < 0 ? R * C : R, H.nsplit, step < 0 ? 1 : 2);
-        k_hyper<kHyperBlock><<<grid, kHyperBlock, sm, st>>>(P, H, step, hpart.p);
+        TR("k_hyper", st, k_hyper<kHyperBlock><<<grid, kHyperBlock, sm, st>>>(P, H, step, hpart.p));
         const int n = R * C * 2;
         const bool multi = kind == 2 && g_nccl.comm && g_nccl.n_rank > 1;
         if (multi && g_p2p.ready && n <= kP2PMaxN) {
             // the one exchange of the path, fused with the local reduction (peer-memory stores over NVLink)
-            k_hyper_reduce_exchange<<<1, 256, 0, st>>>(hpart.p, n, H.nsplit, hsum.p, g_p2p.win);
+            TR("k_hyper_reduce_exchange", st, k_hyper_reduce_exchange<<<1, 256, 0, st>>>(hpart.p, n, H.nsplit, hsum.p, g_p2p.win));
             launches += 2;
         } else {
-            k_hyper_reduce<<<(n + 127) / 128, 128, 0, st>>>(hpart.p, n, H.nsplit, hsum.p);
+            TR("k_hyper_reduce", st, k_hyper_reduce<<<(n + 127) / 128, 128, 0, st>>>(hpart.p, n, H.nsplit, hsum.p));
             launches += 2;
             if (multi) // fallback: partial sums over the local subjects -> sums over all subjects by NCCL
                 g_nccl.check(g_nccl.AllReduce(hsum.p, hsum.p, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, g_nccl.comm, st),
@@ -767,24 +818,36 @@ struct ggdmc_engine {
         Level &P = phi.L;
         const size_t prop_sm = (size_t)kProposeWarps * D2 * 8;
         const int need_cur = H.need_cur;
-        k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), st>>>(P, d_iter.p, sweep, decide_once, para_idx);
+        TR("k_sweep_begin", st, k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), st>>>(P, d_iter.p, sweep, decide_once, para_idx));
         ++launches;
-        if (schedule != GGDMC_SCHEDULE_REFERENCE) {
+        const bool multi = kind == 2 && g_nccl.comm && g_nccl.n_rank > 1;
+        const bool p2p = multi && g_p2p.ready && R * C * 2 <= kP2PMaxN;
+        if (schedule != GGDMC_SCHEDULE_REFERENCE && fuse_phi && (!multi || p2p)) {
+            // one launch per half-sweep: proposal + hyper-likelihood + reduction (+ peer exchange) + MH test
+            const int nhalf = schedule == GGDMC_SCHEDULE_PARALLEL ? 2 : 1;
+            const size_t sm = (size_t)(6 * D + 2 * (kHyperBlock / 32) + 2 * D2) * 8;
+            for (int h = 0; h < nhalf; ++h) {
+                dim3 grid(R * C, H.nsplit);
+                TR("k_phi_half", st, k_phi_half<kHyperBlock><<<grid, kHyperBlock, sm, st>>>(P, H, d_iter.p, sweep, nhalf == 2 ? h : -1, hpart.p,
+                                                                                           hsum.p, phi_ticket.p, g_p2p.win, p2p ? 1 : 0));
+                ++launches;
+            }
+        } else if (schedule != GGDMC_SCHEDULE_REFERENCE) {
             const int n = R * C;
             const int nhalf = schedule == GGDMC_SCHEDULE_PARALLEL ? 2 : 1;
             for (int h = 0; h < nhalf; ++h) {
                 const int half = nhalf == 2 ? h : -1;
                 const int nw = half < 0 ? n : R * ((C + 1) / 2);
-                k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, st>>>(P, d_iter.p, sweep, -1, half);
+                TR("k_propose", st, k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, st>>>(P, d_iter.p, sweep, -1, half));
                 hyper_eval(-1, st);
-                k_phi_accept<<<(n + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur);
+                TR("k_phi_accept", st, k_phi_accept<<<(n + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur));
                 launches += 2;
             }
         } else {
             for (int step = 0; step < C; ++step) {
-                k_propose<kProposeWarps><<<(R + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, st>>>(P, d_iter.p, sweep, step, -1);
+                TR("k_propose", st, k_propose<kProposeWarps><<<(R + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, st>>>(P, d_iter.p, sweep, step, -1));
                 hyper_eval(step, st);
-                k_phi_accept<<<(R + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, step, hsum.p, need_cur);
+                TR("k_phi_accept", st, k_phi_accept<<<(R + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, step, hsum.p, need_cur));
                 launches += 2;
             }
         }
@@ -794,7 +857,7 @@ struct ggdmc_engine {
     void phi_constants(cudaStream_t st)
     {
         const int n = R * C * D;
-        k_phi_consts<<<(n + 127) / 128, 128, 0, st>>>(phi.L, p_prior.d, D, phi_consts.p);
+        TR("k_phi_consts", st, k_phi_consts<<<(n + 127) / 128, 128, 0, st>>>(phi.L, p_prior.d, D, phi_consts.p));
         ++launches;
     }
 
@@ -802,7 +865,7 @@ struct ggdmc_engine {
     {
         const size_t total = (size_t)lv.L.npop * C * lv.L.npar;
         int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
-        k_store<<<blocks, 256, 0, stream>>>(lv.L, d_iter.p);
+        TR("k_store", stream, k_store<<<blocks, 256, 0, stream>>>(lv.L, d_iter.p));
         ++launches;
     }
 
@@ -812,7 +875,7 @@ struct ggdmc_engine {
         size_t total = (size_t)a.L.npop * C * a.L.npar;
         if (b) total = std::max(total, (size_t)b->L.npop * C * b->L.npar);
         const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
-        k_store_advance<<<blocks, 256, 0, stream>>>(a.L, b ? b->L : a.L, b ? 1 : 0, d_iter.p, done_ctr.p);
+        TR("k_store_advance", stream, k_store_advance<<<blocks, 256, 0, stream>>>(a.L, b ? b->L : a.L, b ? 1 : 0, d_iter.p, done_ctr.p));
         ++launches;
     }
 
@@ -821,6 +884,7 @@ struct ggdmc_engine {
     void iteration()
     {
         ++h_iter;
+        trace.reset();
         if (kind == 2) {
             cudaStream_t ps = overlap ? side : stream;
             if (overlap) {
@@ -896,6 +960,7 @@ struct ggdmc_engine {
         CUDA_CHECK(cudaGetLastError());
         if (elapsed_ms) CUDA_CHECK(cudaEventElapsedTime(elapsed_ms, ev0, ev1));
         if (profile) collect_profile();
+        trace.dump(g_nccl.comm ? g_nccl.rank : 0);
         if (kind == 2 && g_p2p.ready && g_p2p.timed_out()) throw Error(GGDMC_ERR_COMM, "peer exchange timed out: a rank did not arrive");
     }
 

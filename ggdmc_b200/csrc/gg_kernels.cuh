@@ -297,6 +297,50 @@ __device__ __forceinline__ double deferred_prop_lp(const Level &L, int p, int sr
     return a1 + a2;
 }
 
+// The proposal at sweep position k of population p, made by one warp (src/de.cpp:111-141 crossover,
+// :157-185 migration, and their phi / hierarchy twins).  `out` = where the proposed vector goes (null: its row
+// of L.prop).  src / tgt: the chain proposed from and the chain it is compared with; lp (lane 0): log prior of
+// the proposal unless the prior is phi-driven (then k_accept evaluates it).
+__device__ __forceinline__ void propose_position(const Level &L, int p, int k, int mode, int nsteps, int para_idx, uint32_t iter,
+                                                 int sweep, int half, int lane, double *scratch, double *out, int &src, int &tgt,
+                                                 double &lp)
+{
+    const int C = L.nchain, D = L.npar;
+    int c0 = 0, c1 = 0;
+    if (mode) {
+        src = L.mig_list[p * C + k];
+        tgt = L.mig_list[p * C + ((k + 1 == nsteps) ? 0 : k + 1)];
+    } else {
+        src = k;
+        tgt = k;
+    }
+    DrawAddr a = make_addr(L, p, iter, sweep, src);
+    if (!mode) pick_partners(a, C, src, half, lane, c0, c1);
+    const double *th = L.theta + ((size_t)p * C + src) * D;
+    const double *t0 = L.theta + ((size_t)p * C + c0) * D;
+    const double *t1 = L.theta + ((size_t)p * C + c1) * D;
+    double *pr = out ? out : L.prop + ((size_t)p * C + src) * D;
+    // a phi-driven prior is evaluated in k_accept instead: the proposal and its likelihood do not need
+    // this iteration's phi, so they can run while the phi sweep is still in flight
+    const bool defer = L.prior_ovr != nullptr;
+    for (int d = lane; d < D; d += 32) {
+        double x = th[d];
+        const bool moved = para_idx >= 0 ? (d == para_idx) : (d < L.nmove);
+        if (moved) {
+            double u = draw_uniform(a, U_NOISE, (uint32_t)d);
+            double noise = runif_from(-L.rp, L.rp, u);
+            double inc = mode ? noise : __dadd_rn(noise, __dmul_rn(L.gamma, __dsub_rn(t0[d], t1[d])));
+            x = __dadd_rn(x, inc);
+        }
+        pr[d] = x;
+        if (!defer) scratch[d] = prior_term(L, d, x, nullptr, nullptr);
+    }
+    __syncwarp();
+    lp = 0.0;
+    if (lane == 0 && !defer) lp = sum_arma_order(scratch, D);
+    __syncwarp();
+}
+
 // One warp per (population, sweep position).
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t *d_iter, int sweep, int step, int half)
@@ -328,45 +372,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t 
     const int para_idx = L.para[p];
     const int nsteps = mode ? L.mig_n[p] : C;
     for (; k >= 0; k = k2, k2 = -1) {
-    if (k >= nsteps) continue;
-    double *scratch = sm_prop + w * D;
-    int src, tgt, c0 = 0, c1 = 0;
-    if (mode) {
-        src = L.mig_list[p * C + k];
-        tgt = L.mig_list[p * C + ((k + 1 == nsteps) ? 0 : k + 1)];
-    } else {
-        src = k;
-        tgt = k;
-    }
-    DrawAddr a = make_addr(L, p, iter, sweep, src);
-    if (!mode) pick_partners(a, C, src, half, lane, c0, c1);
-    const double *th = L.theta + ((size_t)p * C + src) * D;
-    const double *t0 = L.theta + ((size_t)p * C + c0) * D;
-    const double *t1 = L.theta + ((size_t)p * C + c1) * D;
-    double *pr = L.prop + ((size_t)p * C + src) * D;
-    // a phi-driven prior is evaluated in k_accept instead: the proposal and its likelihood do not need
-    // this iteration's phi, so they can run while the phi sweep is still in flight
-    const bool defer = L.prior_ovr != nullptr;
-    const double *ovr = nullptr, *oc = nullptr;
-    for (int d = lane; d < D; d += 32) {
-        double x = th[d];
-        const bool moved = para_idx >= 0 ? (d == para_idx) : (d < L.nmove);
-        if (moved) {
-            double u = draw_uniform(a, U_NOISE, (uint32_t)d);
-            double noise = runif_from(-L.rp, L.rp, u);
-            double inc = mode ? noise : __dadd_rn(noise, __dmul_rn(L.gamma, __dsub_rn(t0[d], t1[d])));
-            x = __dadd_rn(x, inc);
+        if (k >= nsteps) continue;
+        int src, tgt;
+        double lp;
+        propose_position(L, p, k, mode, nsteps, para_idx, iter, sweep, half, lane, sm_prop + w * D, nullptr, src, tgt, lp);
+        if (lane == 0) {
+            if (!L.prior_ovr) L.prop_lp[p * C + src] = lp;
+            L.target[p * C + src] = tgt;
         }
-        pr[d] = x;
-        if (!defer) scratch[d] = prior_term(L, d, x, ovr, oc);
+        __syncwarp();
     }
-    __syncwarp();
-    if (lane == 0) {
-        if (!defer) L.prop_lp[p * C + src] = sum_arma_order(scratch, D);
-        L.target[p * C + src] = tgt;
-    }
-    __syncwarp();
-    } // positions of this warp
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -644,32 +659,14 @@ struct HyperArgs {
     int need_cur;             // refresh current hyper-likelihood (hierarchy) or not (run_hyper)
 };
 
+// hyper-likelihood terms of one block: the subjects [s_begin, s_end) of (replicate r, chain c) under the
+// current phi (cm, cs, cl) and the proposed phi (pm, ps, pl); sm_h layout as in k_hyper
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_hyper(Level L, HyperArgs H, int step, double *hpart /* [npop][C][2][nsplit] */)
+__device__ __forceinline__ void hyper_block(const HyperArgs &H, int r, int c, int split, const double *phi_c, const double *phi_p,
+                                            bool has_prop, double *sm_h, double &vc, double &vp)
 {
-    extern __shared__ double sm_h[]; // cur: mean[D] sd[D] logden[D]; prop: same; then reduction scratch
-    const int C = L.nchain, D = H.D;
-    int r, c;
-    if (step < 0) {
-        r = blockIdx.x / C;
-        c = blockIdx.x - r * C;
-    } else {
-        r = blockIdx.x;
-        const int mode = L.mode[r];
-        if (mode) { // in-place migration step: both the source chain (z = 0) and the chain it is compared with (z = 1)
-            const int n = L.mig_n[r];
-            if (step >= n) return;
-            c = blockIdx.z == 0 ? L.mig_list[r * C + step] : L.mig_list[r * C + ((step + 1 == n) ? 0 : step + 1)];
-        } else {
-            if (blockIdx.z != 0) return;
-            c = step;
-        }
-    }
-    const int split = blockIdx.y;
-    const bool has_prop = L.target[r * C + c] >= 0;
+    const int D = H.D;
     double *cm = sm_h, *cs = cm + D, *cl = cs + D, *pm = cl + D, *ps = pm + D, *pl = ps + D, *red = pl + D;
-    const double *phi_c = L.theta + ((size_t)r * C + c) * 2 * D;
-    const double *phi_p = L.prop + ((size_t)r * C + c) * 2 * D;
     for (int d = threadIdx.x; d < D; d += BLOCK) {
         const double lo = H.like.lower[d], up = H.like.upper[d];
         double m = phi_c[d], s = phi_c[D + d];
@@ -699,8 +696,35 @@ __global__ void __launch_bounds__(BLOCK) k_hyper(Level L, HyperArgs H, int step,
             if (has_prop) sum_p += dprior1(dist, x, pm[d], ps[d], lo, up, lg);
         }
     }
-    double vc = block_sum<BLOCK>(sum_c, red);
-    double vp = block_sum<BLOCK>(sum_p, red + BLOCK / 32);
+    vc = block_sum<BLOCK>(sum_c, red);
+    vp = block_sum<BLOCK>(sum_p, red + BLOCK / 32);
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_hyper(Level L, HyperArgs H, int step, double *hpart /* [npop][C][2][nsplit] */)
+{
+    extern __shared__ double sm_h[]; // cur: mean[D] sd[D] logden[D]; prop: same; then reduction scratch
+    const int C = L.nchain, D = H.D;
+    int r, c;
+    if (step < 0) {
+        r = blockIdx.x / C;
+        c = blockIdx.x - r * C;
+    } else {
+        r = blockIdx.x;
+        const int mode = L.mode[r];
+        if (mode) { // in-place migration step: both the source chain (z = 0) and the chain it is compared with (z = 1)
+            const int n = L.mig_n[r];
+            if (step >= n) return;
+            c = blockIdx.z == 0 ? L.mig_list[r * C + step] : L.mig_list[r * C + ((step + 1 == n) ? 0 : step + 1)];
+        } else {
+            if (blockIdx.z != 0) return;
+            c = step;
+        }
+    }
+    const int split = blockIdx.y;
+    double vc, vp;
+    hyper_block<BLOCK>(H, r, c, split, L.theta + ((size_t)r * C + c) * 2 * D, L.prop + ((size_t)r * C + c) * 2 * D,
+                       L.target[r * C + c] >= 0, sm_h, vc, vp);
     if (threadIdx.x == 0) {
         double *o = hpart + (((size_t)r * C + c) * 2) * H.nsplit + split;
         o[0] = vc;
@@ -744,13 +768,14 @@ struct P2PWindow {
     int n_rank, rank;
 };
 
-__global__ void __launch_bounds__(256) k_hyper_reduce_exchange(const double *hpart, int n, int nsplit, double *hsum, P2PWindow w)
+// block-wide: reduce the nsplit partials of every value, exchange with the peers, leave the all-rank sums in hsum
+__device__ __forceinline__ void reduce_exchange_block(const double *hpart, int n, int nsplit, double *hsum, const P2PWindow &w)
 {
     const unsigned long long seq = *w.seq + 1;
     const int b = (int)(seq & 1ull);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double v = 0.0;
-        for (int k = 0; k < nsplit; ++k) v += hpart[(size_t)i * nsplit + k];
+        for (int k = 0; k < nsplit; ++k) v += *(volatile const double *)(hpart + (size_t)i * nsplit + k);
         for (int q = 0; q < w.n_rank; ++q) w.slots[q][((size_t)b * w.n_rank + w.rank) * kP2PMaxN + i] = v;
     }
     __threadfence_system();
@@ -783,10 +808,43 @@ __global__ void __launch_bounds__(256) k_hyper_reduce_exchange(const double *hpa
     if (threadIdx.x == 0) *w.seq = seq;
 }
 
-// phi-level accept (src/de.cpp:397-400, 427-463 and :494-500, 519-549)
-__global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *hsum, int need_cur)
+__global__ void __launch_bounds__(256) k_hyper_reduce_exchange(const double *hpart, int n, int nsplit, double *hsum, P2PWindow w)
+{
+    reduce_exchange_block(hpart, n, nsplit, hsum, w);
+}
+
+// phi-level accept of the proposal made from chain src (src/de.cpp:397-400, 427-463 and :494-500, 519-549)
+__device__ __forceinline__ void phi_accept_one(const Level &L, int r, int src, uint32_t iter, int sweep, bool in_place_migration,
+                                               const double *hsum, int need_cur)
 {
     const int C = L.nchain, D = L.npar;
+    const int tgt = L.target[r * C + src];
+    if (tgt < 0) return;
+    const double tmp_ll = hsum[((size_t)r * C + src) * 2 + 1];
+    const double tmp_lp = L.prop_lp[r * C + src];
+    double cur_ll = L.ll[r * C + tgt];
+    if (need_cur) {
+        cur_ll = hsum[((size_t)r * C + tgt) * 2 + 0];
+        if (in_place_migration) L.ll[r * C + src] = hsum[((size_t)r * C + src) * 2 + 0]; // :494-496 (in place order only)
+        L.ll[r * C + tgt] = cur_ll; // :397-398 / :498-500
+    }
+    const double cur = L.lp[r * C + tgt] + cur_ll;
+    const double mh = exp((tmp_lp + tmp_ll) - cur);
+    L.target[r * C + src] = -1; // proposal consumed
+    if (isnan(mh)) return;
+    DrawAddr a = make_addr(L, r, iter, sweep, src);
+    if (draw_uniform(a, U_ACCEPT, 0) < mh) {
+        const double *pr = L.prop + ((size_t)r * C + src) * D;
+        double *th = L.theta + ((size_t)r * C + tgt) * D;
+        for (int d = 0; d < D; ++d) th[d] = pr[d];
+        L.lp[r * C + tgt] = tmp_lp;
+        L.ll[r * C + tgt] = tmp_ll;
+    }
+}
+
+__global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *hsum, int need_cur)
+{
+    const int C = L.nchain;
     int r, src;
     if (step < 0) {
         int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -803,28 +861,81 @@ __global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int ste
         } else
             src = step;
     }
-    const int tgt = L.target[r * C + src];
-    if (tgt < 0) return;
-    const double tmp_ll = hsum[((size_t)r * C + src) * 2 + 1];
-    const double tmp_lp = L.prop_lp[r * C + src];
-    double cur_ll = L.ll[r * C + tgt];
-    if (need_cur) {
-        cur_ll = hsum[((size_t)r * C + tgt) * 2 + 0];
-        if (step >= 0 && L.mode[r]) L.ll[r * C + src] = hsum[((size_t)r * C + src) * 2 + 0]; // :494-496 (in place order only)
-        L.ll[r * C + tgt] = cur_ll; // :397-398 / :498-500
+    phi_accept_one(L, r, src, *d_iter, sweep, step >= 0 && L.mode[r] != 0, hsum, need_cur);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One half-sweep (or one whole snapshot sweep, half < 0) of the phi level in ONE launch:
+//   every block (replicate r, chain c, subject split): the proposal made from chain c (recomputed by each
+//   split -- it is a pure function of the counter-addressed draws), then its share of the two hyper-likelihood
+//   sums; the block that finishes last (ticket): sum over the splits, exchange with the peer GPUs through the
+//   peer-memory window (multi-GPU), MH test of every proposal.
+// Replaces k_propose + k_hyper + k_hyper_reduce(_exchange) + k_phi_accept on the phi critical path.
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_phi_half(Level L, HyperArgs H, const uint32_t *d_iter, int sweep, int half, double *hpart,
+                                                    double *hsum, unsigned int *ticket, P2PWindow w, int use_p2p)
+{
+    extern __shared__ double sm_h[]; // hyper_block's 6 D + 2 BLOCK/32, then proposal [2 D], prior scratch [2 D]
+    __shared__ int s_k, s_last;
+    const int C = L.nchain, D = H.D, D2 = 2 * D;
+    const int r = blockIdx.x / C, c = blockIdx.x - r * C, split = blockIdx.y;
+    const uint32_t iter = *d_iter;
+    const int mode = L.mode[r], para_idx = L.para[r];
+    const int nsteps = mode ? L.mig_n[r] : C;
+    double *sprop = sm_h + 6 * D + 2 * (BLOCK / 32), *scratch = sprop + D2;
+    if (threadIdx.x == 0) { // sweep position at which chain c proposes in this launch, -1: it does not
+        int k = -1;
+        if (mode == 0) {
+            if (half < 0 || (c & 1) == half) k = c;
+        } else if (mode == 1 && half <= 0) {
+            for (int j = 0; j < nsteps; ++j)
+                if (L.mig_list[r * C + j] == c) { k = j; break; }
+        }
+        s_k = k;
     }
-    const double cur = L.lp[r * C + tgt] + cur_ll;
-    const double mh = exp((tmp_lp + tmp_ll) - cur);
-    L.target[r * C + src] = -1; // proposal consumed
-    if (isnan(mh)) return;
-    DrawAddr a = make_addr(L, r, *d_iter, sweep, src);
-    if (draw_uniform(a, U_ACCEPT, 0) < mh) {
-        const double *pr = L.prop + ((size_t)r * C + src) * D;
-        double *th = L.theta + ((size_t)r * C + tgt) * D;
-        for (int d = 0; d < D; ++d) th[d] = pr[d];
-        L.lp[r * C + tgt] = tmp_lp;
-        L.ll[r * C + tgt] = tmp_ll;
+    __syncthreads();
+    const int k = s_k;
+    if (k >= 0 && threadIdx.x < 32) {
+        int src, tgt;
+        double lp;
+        propose_position(L, r, k, mode, nsteps, para_idx, iter, sweep, half, (int)threadIdx.x, scratch, sprop, src, tgt, lp);
+        if (split == 0) {
+            double *pr = L.prop + ((size_t)r * C + c) * D2;
+            for (int d = threadIdx.x; d < D2; d += 32) pr[d] = sprop[d];
+            if (threadIdx.x == 0) {
+                L.prop_lp[r * C + c] = lp;
+                L.target[r * C + c] = tgt;
+            }
+        }
     }
+    __syncthreads();
+    double vc, vp;
+    hyper_block<BLOCK>(H, r, c, split, L.theta + ((size_t)r * C + c) * D2, k >= 0 ? sprop : L.theta + ((size_t)r * C + c) * D2, k >= 0,
+                       sm_h, vc, vp);
+    if (threadIdx.x == 0) {
+        double *o = hpart + (((size_t)r * C + c) * 2) * H.nsplit + split;
+        o[0] = vc;
+        o[H.nsplit] = vp;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int n = L.npop * C * 2;
+    if (use_p2p) {
+        reduce_exchange_block(hpart, n, H.nsplit, hsum, w);
+    } else {
+        for (int i = threadIdx.x; i < n; i += BLOCK) {
+            double v = 0.0;
+            for (int q = 0; q < H.nsplit; ++q) v += *(volatile const double *)(hpart + (size_t)i * H.nsplit + q);
+            hsum[i] = v;
+        }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < L.npop * C; g += BLOCK) phi_accept_one(L, g / C, g - (g / C) * C, iter, sweep, false, hsum, H.need_cur);
+    if (threadIdx.x == 0) *ticket = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
