@@ -482,7 +482,7 @@ struct Tracer {
     std::vector<Rec> recs;
     size_t used = 0;
     void reset() { used = 0; }
-    void open(const char *name, cudaStream_t st, bool is_side)
+    void open(const char *name, cudaStream_t st, int is_side)
     {
         if (!on) return;
         if (used == recs.size()) {
@@ -510,7 +510,7 @@ struct Tracer {
             float t0 = 0.f, d = 0.f;
             cudaEventElapsedTime(&t0, recs[0].a, recs[i].a);
             cudaEventElapsedTime(&d, recs[i].a, recs[i].b);
-            std::fprintf(stderr, "[ggdmc_b200 trace] %9.1f %8.1f %s %s\n", t0 * 1e3, d * 1e3, recs[i].side ? "side" : "main", recs[i].name);
+            std::fprintf(stderr, "[ggdmc_b200 trace] %9.1f %8.1f %s %s\n", t0 * 1e3, d * 1e3, recs[i].side == 1 ? "side" : recs[i].side == 0 ? "main" : "grp ", recs[i].name);
         }
     }
     ~Tracer()
@@ -518,7 +518,7 @@ struct Tracer {
         for (Rec &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     }
 };
-#define TR(name, st, ...) do { trace.open(name, st, (st) == side); __VA_ARGS__; trace.close(st); } while (0)
+#define TR(name, st, ...) do { trace.open(name, st, stream_tag(st)); __VA_ARGS__; trace.close(st); } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // the engine
@@ -543,6 +543,14 @@ struct ggdmc_engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool overlap = std::getenv("GGDMC_B200_NO_OVERLAP") == nullptr;
     bool fuse_phi = std::getenv("GGDMC_B200_NO_FUSED_PHI") == nullptr;
+    // The subjects are independent given phi, so they run as groups on their own streams: one group's
+    // proposal / MH kernels and the drain of its likelihood launch overlap another group's likelihood.
+    // GGDMC_B200_GROUPS=n overrides the group count (1 = one launch over all subjects).
+    static constexpr int kMaxGroups = 8;
+    struct SubjGroup { Level L; TrialData T; double *ll_part; };
+    std::vector<SubjGroup> groups;
+    cudaStream_t gstream[kMaxGroups] = {};
+    cudaEvent_t ev_gdone[kMaxGroups] = {};
     // optional per-launch timing of the likelihood kernel (bench.py roofline)
     // one DE-MCMC iteration captured as a CUDA graph (fixed launch sequence: every data-dependent
     // decision is taken on the device); GGDMC_B200_NO_GRAPH=1 falls back to plain stream launches
@@ -579,6 +587,10 @@ struct ggdmc_engine {
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        for (int g = 1; g < kMaxGroups; ++g) {
+            if (ev_gdone[g]) cudaEventDestroy(ev_gdone[g]);
+            if (gstream[g]) cudaStreamDestroy(gstream[g]);
+        }
         if (side) cudaStreamDestroy(side);
         if (stream) cudaStreamDestroy(stream);
         pt.lap("  ~stream");
@@ -680,6 +692,7 @@ struct ggdmc_engine {
             L.ovr_consts = phi_consts.p;
             setup_hyper(subj.theta.p, C * D, R * C * D, D, 1);
         }
+        make_groups();
         start_counter();
         pt.lap("  phi");
     }
@@ -707,6 +720,35 @@ struct ggdmc_engine {
         start_counter();
     }
 
+    // group g = local subjects [S g / G, S (g + 1) / G): views of the subject level, its trials and its partial sums
+    void make_groups()
+    {
+        int G = S >= 2 ? 2 : 1;
+        if (const char *e = std::getenv("GGDMC_B200_GROUPS")) G = std::atoi(e);
+        G = std::max(1, std::min(std::min(G, S), kMaxGroups));
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        gstream[0] = nullptr; // group 0 runs on `stream`
+        groups.clear();
+        for (int g = 0; g < G; ++g) {
+            const int i0 = (int)((int64_t)S * g / G), i1 = (int)((int64_t)S * (g + 1) / G);
+            const size_t p0 = (size_t)i0 * R;
+            SubjGroup sg{subj.L, trials.d, ll_part.p + p0 * C * trials.d.nsplit};
+            Level &L = sg.L;
+            L.npop = (i1 - i0) * R;
+            L.pop_id_base += i0;
+            L.theta += p0 * C * D; L.prop += p0 * C * D;
+            L.lp += p0 * C; L.ll += p0 * C; L.prop_lp += p0 * C; L.target += p0 * C; L.mig_list += p0 * C;
+            L.mode += p0; L.mig_n += p0; L.para += p0; L.mode0 += p0;
+            sg.T.offset += i0; sg.T.count += i0;
+            groups.push_back(sg);
+            if (g > 0) {
+                CUDA_CHECK(cudaStreamCreateWithPriority(&gstream[g], cudaStreamNonBlocking, prio_lo));
+                CUDA_CHECK(cudaEventCreateWithFlags(&ev_gdone[g], cudaEventDisableTiming));
+            }
+        }
+    }
+
     void start_counter()
     {
         CUDA_CHECK(cudaStreamSynchronize(stream)); // slot-0 stores (which read iteration 0) are done
@@ -732,10 +774,13 @@ struct ggdmc_engine {
     }
 
     // likelihood launch, optionally bracketed by CUDA events on the launching stream
-    void timed_like(const Level &L, int sweep, int step, int half)
+    int stream_tag(cudaStream_t st) const { return st == side ? 1 : st == this->stream ? 0 : 2; }
+
+    void timed_like(const SubjGroup &G, cudaStream_t stream, int sweep, int step, int half)
     {
+        const Level &L = G.L;
         if (!profile) {
-            TR("k_like", stream, launch_like(L, model.d, trials.d, d_iter.p, sweep, step, half, ll_part.p, stream));
+            TR("k_like", stream, launch_like(L, model.d, G.T, d_iter.p, sweep, step, half, G.ll_part, stream));
             return;
         }
         if (prof_used + 2 > prof_ev.size()) {
@@ -746,7 +791,7 @@ struct ggdmc_engine {
             }
         }
         CUDA_CHECK(cudaEventRecord(prof_ev[prof_used], stream));
-        launch_like(L, model.d, trials.d, d_iter.p, sweep, step, half, ll_part.p, stream);
+        launch_like(L, model.d, G.T, d_iter.p, sweep, step, half, G.ll_part, stream);
         CUDA_CHECK(cudaEventRecord(prof_ev[prof_used + 1], stream));
         prof_used += 2;
     }
@@ -762,9 +807,9 @@ struct ggdmc_engine {
     }
 
     // ---- one sweep at each level --------------------------------------------------------------
-    void sweep_lba(int sweep, int decide_once, int para_idx, cudaEvent_t join = nullptr)
+    void sweep_lba(const SubjGroup &G, cudaStream_t stream, int sweep, int decide_once, int para_idx, cudaEvent_t join = nullptr)
     {
-        Level &L = subj.L;
+        const Level &L = G.L;
         const size_t prop_sm = (size_t)kProposeWarps * D * 8;
         TR("k_sweep_begin", stream, k_sweep_begin<<<L.npop, 128, (size_t)2 * C * sizeof(int), stream>>>(L, d_iter.p, sweep, decide_once, para_idx));
         ++launches;
@@ -775,21 +820,37 @@ struct ggdmc_engine {
                 const int half = nhalf == 2 ? h : -1;
                 const int nw = half < 0 ? n : L.npop * ((C + 1) / 2); // warps: one per (population, chain) or per (population, slot)
                 TR("k_propose", stream, k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1, half));
-                timed_like(L, sweep, -1, half);
+                timed_like(G, stream, sweep, -1, half);
                 if (join && h == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0)); // the MH test needs this iteration's phi
-                TR("k_accept", stream, k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, ll_part.p, trials.d.nsplit));
+                TR("k_accept", stream, k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, G.ll_part, G.T.nsplit));
                 launches += 3;
             }
         } else {
             for (int step = 0; step < C; ++step) {
                 TR("k_propose", stream, k_propose<kProposeWarps><<<(L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step, -1));
-                timed_like(L, sweep, step, -1);
+                timed_like(G, stream, sweep, step, -1);
                 if (join && step == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0));
-                TR("k_accept", stream, k_accept<<<(L.npop + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, step, ll_part.p, trials.d.nsplit));
+                TR("k_accept", stream, k_accept<<<(L.npop + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, step, G.ll_part, G.T.nsplit));
                 launches += 3;
             }
         }
         CUDA_CHECK(cudaGetLastError());
+    }
+
+    // the subject-level sweep(s) of one iteration, group by group (ev_fork has been recorded on `stream`)
+    void sweep_groups(int decide_once, cudaEvent_t join, bool conc)
+    {
+        const int nsweep = is_pblocked ? (kind == 2 ? D : subj.L.nmove) : 1;
+        for (size_t g = 0; g < groups.size(); ++g) {
+            cudaStream_t st = (conc && g > 0) ? gstream[g] : stream;
+            if (st != stream) CUDA_CHECK(cudaStreamWaitEvent(st, ev_fork, 0));
+            for (int p = 0; p < nsweep; ++p)
+                sweep_lba(groups[g], st, p, decide_once, is_pblocked ? p : -1, p == 0 ? join : nullptr);
+            if (st != stream) {
+                CUDA_CHECK(cudaEventRecord(ev_gdone[g], st));
+                CUDA_CHECK(cudaStreamWaitEvent(stream, ev_gdone[g], 0));
+            }
+        }
     }
 
     void hyper_eval(int step, cudaStream_t st)
@@ -885,9 +946,10 @@ struct ggdmc_engine {
     {
         ++h_iter;
         trace.reset();
+        const bool conc = overlap && !profile; // per-launch timing (bench.py roofline pass) wants one launch at a time
         if (kind == 2) {
-            cudaStream_t ps = overlap ? side : stream;
-            if (overlap) {
+            cudaStream_t ps = conc ? side : stream;
+            if (conc) {
                 CUDA_CHECK(cudaEventRecord(ev_fork, stream));
                 CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork, 0));
             }
@@ -897,20 +959,15 @@ struct ggdmc_engine {
                 sweep_phi(0, 0, -1, ps);
             phi_constants(ps);
             cudaEvent_t join = nullptr;
-            if (overlap) {
+            if (conc) {
                 CUDA_CHECK(cudaEventRecord(ev_join, side));
                 join = ev_join;
             }
-            if (is_pblocked)
-                for (int p = 0; p < D; ++p) sweep_lba(p, 0, p, p == 0 ? join : nullptr);
-            else
-                sweep_lba(0, 0, -1, join);
+            sweep_groups(0, join, conc);
             store_and_advance(subj, &phi);
         } else if (kind == 0) {
-            if (is_pblocked)
-                for (int p = 0; p < subj.L.nmove; ++p) sweep_lba(p, 1, p);
-            else
-                sweep_lba(0, 1, -1);
+            if (conc && groups.size() > 1) CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+            sweep_groups(1, nullptr, conc);
             store_and_advance(subj, nullptr);
         } else {
             if (is_pblocked)
