@@ -239,6 +239,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--schedule", default="parallel", choices=["parallel", "reference", "simultaneous"])
     ap.add_argument("--subjects", type=int, default=0, help="experiments only: override the workload's subject count")
+    ap.add_argument("--migration", type=float, default=0.05, help="experiments only: pop and sub migration probability")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -308,7 +309,7 @@ def main():
     n_acc = w.spec.ct.n_acc
     seeds = [9032]
     K, Wm = args.steps, args.warmup
-    tun = W.tuning_for(w, nmc=2, thin=1 << 30, seeds=seeds, schedule=schedule, subject_begin=s0, n_subject_total=S, device=local_rank)
+    tun = W.tuning_for(w, nmc=2, thin=1 << 30, seeds=seeds, schedule=schedule, pop_migration_prob=args.migration, sub_migration_prob=args.migration, subject_begin=s0, n_subject_total=S, device=local_rank)
     eng = E.Engine(w.spec.ct, w.trials, w.spec.p_prior, w.spec.h_prior, tun, w.phi_start, w.subj_start)
 
     eng.iterate(Wm)

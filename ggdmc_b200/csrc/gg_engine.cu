@@ -420,7 +420,7 @@ int like_variant()
     static int v = [] {
         const char *e = std::getenv("GGDMC_B200_LIKE_VARIANT");
         int x = e ? std::atoi(e) : 2;
-        return (x < 0 || x > 7) ? 2 : x;
+        return (x < 0 || x > 8) ? 2 : x;
     }();
     return v;
 }
@@ -433,42 +433,49 @@ size_t like_smem(const DevModel &M, int block)
 
 template <int NACC, int BLOCK, int MINB>
 void launch_like_t(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
-                   double *ll_part, cudaStream_t st)
+                   double *ll_part, cudaStream_t st, const int *prio)
 {
     const int per_pop = step >= 0 ? 1 : (half < 0 ? L.nchain : (L.nchain + 1) / 2);
     dim3 grid(L.npop * per_pop, T.nsplit);
     const size_t sm = like_smem(M, BLOCK);
     require(sm <= 220 * 1024, "cell table does not fit in shared memory");
     allow_smem(k_like<NACC, BLOCK, MINB>, sm);
-    k_like<NACC, BLOCK, MINB><<<grid, BLOCK, sm, st>>>(L, M, T, d_iter, sweep, step, half, ll_part);
-    CUDA_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority; // dispatch order among the likelihood launches of concurrent subject groups
+    at[0].val.priority = prio ? *prio : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = prio ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_like<NACC, BLOCK, MINB>, L, M, T, d_iter, sweep, step, half, ll_part));
 }
 
 template <int NACC>
 void launch_like_n(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
-                   double *ll_part, cudaStream_t st)
+                   double *ll_part, cudaStream_t st, const int *prio)
 {
     switch (like_variant()) {
-    case 0: launch_like_t<NACC, 128, 6>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    case 2: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    case 3: launch_like_t<NACC, 64, 16>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    case 1: launch_like_t<NACC, 128, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    case 4: launch_like_t<NACC, 32, 24>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    case 5: launch_like_t<NACC, 32, 32>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    case 6: launch_like_t<NACC, 64, 10>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    case 7: launch_like_t<NACC, 64, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    default: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st);
+    case 0: launch_like_t<NACC, 128, 6>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 2: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 3: launch_like_t<NACC, 64, 16>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 1: launch_like_t<NACC, 128, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 4: launch_like_t<NACC, 32, 24>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 5: launch_like_t<NACC, 32, 32>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 6: launch_like_t<NACC, 64, 10>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 7: launch_like_t<NACC, 64, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 8: launch_like_t<NACC, 256, 3>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    default: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio);
     }
 }
 
 void launch_like(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
-                 double *ll_part, cudaStream_t st)
+                 double *ll_part, cudaStream_t st, const int *prio = nullptr)
 {
     switch (M.n_acc) {
-    case 2: launch_like_n<2>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    case 3: launch_like_n<3>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    case 4: launch_like_n<4>(L, M, T, d_iter, sweep, step, half, ll_part, st); break;
-    default: launch_like_n<0>(L, M, T, d_iter, sweep, step, half, ll_part, st);
+    case 2: launch_like_n<2>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 3: launch_like_n<3>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 4: launch_like_n<4>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    default: launch_like_n<0>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio);
     }
 }
 
@@ -547,7 +554,7 @@ struct ggdmc_engine {
     // proposal / MH kernels and the drain of its likelihood launch overlap another group's likelihood.
     // GGDMC_B200_GROUPS=n overrides the group count (1 = one launch over all subjects).
     static constexpr int kMaxGroups = 8;
-    struct SubjGroup { Level L; TrialData T; double *ll_part; };
+    struct SubjGroup { Level L; TrialData T; double *ll_part; int index; };
     std::vector<SubjGroup> groups;
     cudaStream_t gstream[kMaxGroups] = {};
     cudaEvent_t ev_gdone[kMaxGroups] = {};
@@ -610,7 +617,6 @@ struct ggdmc_engine {
         schedule = (cfg->schedule == GGDMC_SCHEDULE_PARALLEL && cfg->nchain < 4) ? GGDMC_SCHEDULE_REFERENCE : cfg->schedule;
         is_hblocked = cfg->is_hblocked; is_pblocked = cfg->is_pblocked;
         subject_begin = cfg->subject_begin;
-        int prio_lo = 0, prio_hi = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_lo));
         CUDA_CHECK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
@@ -726,14 +732,12 @@ struct ggdmc_engine {
         int G = S >= 2 ? 2 : 1;
         if (const char *e = std::getenv("GGDMC_B200_GROUPS")) G = std::atoi(e);
         G = std::max(1, std::min(std::min(G, S), kMaxGroups));
-        int prio_lo = 0, prio_hi = 0;
-        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         gstream[0] = nullptr; // group 0 runs on `stream`
         groups.clear();
         for (int g = 0; g < G; ++g) {
             const int i0 = (int)((int64_t)S * g / G), i1 = (int)((int64_t)S * (g + 1) / G);
             const size_t p0 = (size_t)i0 * R;
-            SubjGroup sg{subj.L, trials.d, ll_part.p + p0 * C * trials.d.nsplit};
+            SubjGroup sg{subj.L, trials.d, ll_part.p + p0 * C * trials.d.nsplit, g};
             Level &L = sg.L;
             L.npop = (i1 - i0) * R;
             L.pop_id_base += i0;
@@ -774,13 +778,35 @@ struct ggdmc_engine {
     }
 
     // likelihood launch, optionally bracketed by CUDA events on the launching stream
+    // Launch with the highest dispatch priority whatever the stream's own: the short proposal / MH kernels of a
+    // subject group must not queue behind the not-yet-dispatched blocks of another group's likelihood launch.
+    int prio_hi = 0, prio_lo = 0;
+    template <typename... KArgs, typename... Args>
+    void launch_hi(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributePriority;
+        at[0].val.priority = prio_hi;
+        cfg.attrs = at;
+        cfg.numAttrs = hi_small ? 1 : 0;
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+    }
+    bool hi_small = std::getenv("GGDMC_B200_NO_HI_SMALL") == nullptr;
+
     int stream_tag(cudaStream_t st) const { return st == side ? 1 : st == this->stream ? 0 : 2; }
 
     void timed_like(const SubjGroup &G, cudaStream_t stream, int sweep, int step, int half)
     {
         const Level &L = G.L;
         if (!profile) {
-            TR("k_like", stream, launch_like(L, model.d, G.T, d_iter.p, sweep, step, half, G.ll_part, stream));
+            // concurrent groups: likelihood launches are dispatched in pipeline order (group 0 half 0, group 1 half 0,
+            // group 0 half 1, ...) instead of sharing the SMs in lock-step, so one group's short kernels and launch
+            // ramp / drain fall under another group's likelihood
+            int prio = std::min(prio_lo, prio_hi + 1 + std::max(half, 0) * (int)groups.size() + G.index);
+            const bool staged = hi_small && groups.size() > 1 && stream_tag(stream) != 1;
+            TR("k_like", stream, launch_like(L, model.d, G.T, d_iter.p, sweep, step, half, G.ll_part, stream, staged ? &prio : nullptr));
             return;
         }
         if (prof_used + 2 > prof_ev.size()) {
@@ -811,7 +837,7 @@ struct ggdmc_engine {
     {
         const Level &L = G.L;
         const size_t prop_sm = (size_t)kProposeWarps * D * 8;
-        TR("k_sweep_begin", stream, k_sweep_begin<<<L.npop, 128, (size_t)2 * C * sizeof(int), stream>>>(L, d_iter.p, sweep, decide_once, para_idx));
+        TR("k_sweep_begin", stream, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), stream, L, d_iter.p, sweep, decide_once, para_idx));
         ++launches;
         if (schedule != GGDMC_SCHEDULE_REFERENCE) {
             const int n = L.npop * C;
@@ -819,18 +845,18 @@ struct ggdmc_engine {
             for (int h = 0; h < nhalf; ++h) {
                 const int half = nhalf == 2 ? h : -1;
                 const int nw = half < 0 ? n : L.npop * ((C + 1) / 2); // warps: one per (population, chain) or per (population, slot)
-                TR("k_propose", stream, k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, -1, half));
+                TR("k_propose", stream, launch_hi(k_propose<kProposeWarps>, (nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream, L, d_iter.p, sweep, -1, half));
                 timed_like(G, stream, sweep, -1, half);
                 if (join && h == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0)); // the MH test needs this iteration's phi
-                TR("k_accept", stream, k_accept<<<(n + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, -1, G.ll_part, G.T.nsplit));
+                TR("k_accept", stream, launch_hi(k_accept, (n + 127) / 128, 128, 0, stream, L, d_iter.p, sweep, -1, (const double *)G.ll_part, G.T.nsplit));
                 launches += 3;
             }
         } else {
             for (int step = 0; step < C; ++step) {
-                TR("k_propose", stream, k_propose<kProposeWarps><<<(L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream>>>(L, d_iter.p, sweep, step, -1));
+                TR("k_propose", stream, launch_hi(k_propose<kProposeWarps>, (L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream, L, d_iter.p, sweep, step, -1));
                 timed_like(G, stream, sweep, step, -1);
                 if (join && step == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0));
-                TR("k_accept", stream, k_accept<<<(L.npop + 127) / 128, 128, 0, stream>>>(L, d_iter.p, sweep, step, G.ll_part, G.T.nsplit));
+                TR("k_accept", stream, launch_hi(k_accept, (L.npop + 127) / 128, 128, 0, stream, L, d_iter.p, sweep, step, (const double *)G.ll_part, G.T.nsplit));
                 launches += 3;
             }
         }
@@ -1033,6 +1059,9 @@ struct ggdmc_engine {
         for (auto &e : ev) CUDA_CHECK(cudaEventCreate(&e));
         for (int i = 0; i < n_iter; ++i) {
             CUDA_CHECK(cudaMemsetAsync(flush.p, i & 0xff, flush_bytes, stream));
+            // the flush de-synchronises the ranks (a fit keeps them in lock-step through its exchanges): line them
+            // up again before the bracket opens, so that the skew of the memsets is not booked as exchange wait
+            if (kind == 2 && g_nccl.comm && g_nccl.n_rank > 1 && g_p2p.ready) k_peer_barrier<<<1, 32, 0, stream>>>(g_p2p.win);
             CUDA_CHECK(cudaEventRecord(ev[2 * i], stream));
             step_once();
             CUDA_CHECK(cudaEventRecord(ev[2 * i + 1], stream));
@@ -1168,6 +1197,25 @@ int ggdmc_b200_engine_time_likelihood(ggdmc_engine_t *engine, int32_t reps, floa
     e.launches += 3 + reps;
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, e.ev0, e.ev1));
+    if (const char *path = std::getenv("GGDMC_B200_BLOCKTRACE")) { // diagnostics: one more launch with per-block time stamps
+        const size_t nblk = (size_t)L.npop * e.C * e.trials.d.nsplit;
+        DBuf<unsigned long long> bt;
+        bt.alloc(3 * nblk + 2);
+        bt.zero();
+        CUDA_CHECK(cudaStreamSynchronize(0));
+        TrialData T = e.trials.d;
+        T.btrace = bt.p + 2;
+        k_stamp<<<1, 1, 0, e.stream>>>(bt.p);
+        launch_like(L, e.model.d, T, e.d_iter.p, 0, -1, -1, e.ll_part.p, e.stream);
+        k_stamp<<<1, 1, 0, e.stream>>>(bt.p + 1);
+        CUDA_CHECK(cudaStreamSynchronize(e.stream));
+        std::vector<unsigned long long> h(3 * nblk + 2);
+        CUDA_CHECK(cudaMemcpy(h.data(), bt.p, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE *f = std::fopen(path, "wb")) {
+            std::fwrite(h.data(), 8, h.size(), f);
+            std::fclose(f);
+        }
+    }
     if (elapsed_ms) *elapsed_ms = ms / reps;
     if (n_trial_lik) *n_trial_lik = (int64_t)e.R * e.C * e.trials.total;
     GG_CATCH

@@ -396,6 +396,7 @@ struct TrialData {
     int nsplit;              // blocks per (population, chain)
     unsigned long long *counter; // trial-likelihoods evaluated so far (one atomicAdd per block)
     double zero_floor;           // > 0: densities <= 0 are replaced by this value (R-side init rule, R/phi.R:3-13); 0: off
+    unsigned long long *btrace;  // diagnostics (GGDMC_B200_BLOCKTRACE): per block {start ns, end ns, SM id}, normally null
 };
 
 constexpr double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
@@ -503,35 +504,76 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
     // else is left to the cold loop below, which keeps every rare branch -- and its registers -- out of
     // the code the FP64 pipe spends its time in.
     bool leftovers = false;
-    for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
-        const double2 r2 = __ldg(reinterpret_cast<const double2 *>(rt + t));
-        const ushort2 c2 = __ldg(reinterpret_cast<const ushort2 *>(cl + t));
-        const int nh = (t + 1 < t_end) ? 2 : 1;
-#pragma unroll 1
-        for (int h = 0; h < nh; ++h) {
-            const int c = h ? c2.y : c2.x;
-            const double r = h ? r2.y : r2.x;
-            const CellAcc *e = ent + c * na;
-            if (bad[c] == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) {
-                double pdf = n1pdf_fast<NACC>(r, e, na);
-                if (zf > 0.0 && pdf <= 0.0) pdf = zf;
-                acc.mul_fast(pdf);
+    if constexpr (NACC == 2) {
+        // two trials of a thread advance together (n1pdf_fast2); with more accumulators the second trial's
+        // state no longer fits the register budget of 12 blocks per SM and the one-trial loop below is faster
+        for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
+            const double2 r2 = __ldg(reinterpret_cast<const double2 *>(rt + t));
+            const ushort2 c2 = __ldg(reinterpret_cast<const ushort2 *>(cl + t));
+            const int c0 = c2.x, c1 = (t + 1 < t_end) ? c2.y : c2.x; // the partner of a last odd trial is padding
+            const CellAcc *e0 = ent + c0 * na, *e1 = ent + c1 * na;
+            const bool pair_ok = (t + 1 < t_end) && bad[c0] == kCellRegular && bad[c1] == kCellRegular && n1pdf_fast_ok<NACC>(r2.x, e0, na) &&
+                                 n1pdf_fast_ok<NACC>(r2.y, e1, na);
+            if (pair_ok) {
+                double p0, p1;
+                n1pdf_fast2<NACC>(r2.x, e0, r2.y, e1, na, p0, p1);
+                if (zf > 0.0) {
+                    if (p0 <= 0.0) p0 = zf;
+                    if (p1 <= 0.0) p1 = zf;
+                }
+                acc.mul_fast(p0);
+                acc.mul_fast(p1);
             } else
                 leftovers = true;
         }
-    }
-    if (leftovers) { // cold loop: invalid / generic cells and trials with rt <= t0
+        if (leftovers) { // cold loop: pairs with an invalid / generic cell or rt <= t0 in them, and a last odd trial
+            for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
+                const int nh = (t + 1 < t_end) ? 2 : 1;
+                if (nh == 2) {
+                    const int c0 = cl[t], c1 = cl[t + 1];
+                    if (bad[c0] == kCellRegular && bad[c1] == kCellRegular && n1pdf_fast_ok<NACC>(rt[t], ent + c0 * na, na) &&
+                        n1pdf_fast_ok<NACC>(rt[t + 1], ent + c1 * na, na))
+                        continue; // done in the hot loop
+                }
+                for (int h = 0; h < nh; ++h) {
+                    const int c = cl[t + h];
+                    double pdf = n1pdf_any<NACC>(bad[c], rt[t + h], ent + c * na, na);
+                    if (zf > 0.0 && pdf <= 0.0) pdf = zf;
+                    acc.mul(pdf);
+                }
+            }
+        }
+    } else {
         for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
+            const double2 r2 = __ldg(reinterpret_cast<const double2 *>(rt + t));
+            const ushort2 c2 = __ldg(reinterpret_cast<const ushort2 *>(cl + t));
             const int nh = (t + 1 < t_end) ? 2 : 1;
+#pragma unroll 1
             for (int h = 0; h < nh; ++h) {
-                const int c = cl[t + h];
-                const double r = rt[t + h];
+                const int c = h ? c2.y : c2.x;
+                const double r = h ? r2.y : r2.x;
                 const CellAcc *e = ent + c * na;
-                const uint8_t cls = bad[c];
-                if (cls == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) continue; // done in the hot loop
-                double pdf = cls == kCellInvalid ? kFloor : n1pdf_generic_body<NACC>(r, e, na);
-                if (zf > 0.0 && pdf <= 0.0) pdf = zf;
-                acc.mul(pdf);
+                if (bad[c] == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) {
+                    double pdf = n1pdf_fast<NACC>(r, e, na);
+                    if (zf > 0.0 && pdf <= 0.0) pdf = zf;
+                    acc.mul_fast(pdf);
+                } else
+                    leftovers = true;
+            }
+        }
+        if (leftovers) { // cold loop: invalid / generic cells and trials with rt <= t0
+            for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
+                const int nh = (t + 1 < t_end) ? 2 : 1;
+                for (int h = 0; h < nh; ++h) {
+                    const int c = cl[t + h];
+                    const double r = rt[t + h];
+                    const CellAcc *e = ent + c * na;
+                    const uint8_t cls = bad[c];
+                    if (cls == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) continue; // done in the hot loop
+                    double pdf = cls == kCellInvalid ? kFloor : n1pdf_generic_body<NACC>(r, e, na);
+                    if (zf > 0.0 && pdf <= 0.0) pdf = zf;
+                    acc.mul(pdf);
+                }
             }
         }
     }
@@ -543,6 +585,30 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
 }
 
 // Grid.  step >= 0 (REFERENCE schedule): block x = population, its chain is sweep position `step`.
+struct BlockTrace { // thread 0 of a block stamps its start / end time and SM into btrace[3 * block]
+    unsigned long long *slot;
+    __device__ __forceinline__ static unsigned long long now()
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        return t;
+    }
+    __device__ __forceinline__ explicit BlockTrace(unsigned long long *base) : slot(nullptr)
+    {
+        if (base && threadIdx.x == 0) {
+            slot = base + 3 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+            unsigned int sm;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+            slot[0] = now();
+            slot[2] = sm;
+        }
+    }
+    __device__ __forceinline__ ~BlockTrace()
+    {
+        if (slot) slot[1] = now();
+    }
+};
+
 // step < 0, half < 0: block x = (population, chain).  step < 0, half = 0 / 1 (PARALLEL schedule): block x =
 // (population, slot) with (nchain + 1) / 2 slots; a crossover population evaluates chain 2 slot + half, a
 // migrating population (whole migration in half 0) its chains slot and slot + nslots.
@@ -553,6 +619,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, Trial
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int C = L.nchain;
     const uint32_t iter = *d_iter;
+    BlockTrace bt(T.btrace);
     int p, chain0, stride = C, nchain_blk = 1; // this block evaluates chains chain0, chain0 + stride, ... (nchain_blk of them)
     if (step >= 0) {
         p = blockIdx.x;
@@ -813,6 +880,9 @@ __global__ void __launch_bounds__(256) k_hyper_reduce_exchange(const double *hpa
     reduce_exchange_block(hpart, n, nsplit, hsum, w);
 }
 
+// all ranks arrive (an exchange of zero values): used to line the ranks up outside timed regions
+__global__ void k_peer_barrier(P2PWindow w) { reduce_exchange_block(nullptr, 0, 0, nullptr, w); }
+
 // phi-level accept of the proposal made from chain src (src/de.cpp:397-400, 427-463 and :494-500, 519-549)
 __device__ __forceinline__ void phi_accept_one(const Level &L, int r, int src, uint32_t iter, int sweep, bool in_place_migration,
                                                const double *hsum, int need_cur)
@@ -980,6 +1050,7 @@ __global__ void k_store_advance(Level A, Level Bv, int has_b, uint32_t *d_iter, 
 }
 
 __global__ void k_iter_advance(uint32_t *d_iter) { *d_iter += 1; }
+__global__ void k_stamp(unsigned long long *t) { *t = BlockTrace::now(); }
 
 // ------------------------------------------------------------------------------------------------
 // test / utility kernels

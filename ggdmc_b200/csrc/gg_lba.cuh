@@ -164,6 +164,63 @@ GG_HD double n1pdf_fast(double rt, const CellAcc *e, int n_acc_rt)
     return pdf;
 }
 
+// Two fast-path trials of one thread advanced together: per accumulator the four (Phi, phi) pairs of the two
+// trials form one lock-step batch, and everything around them comes in two independent copies.  A warp whose
+// consecutive FP64 instructions depend on each other cannot fill the FP64 pipe even with every scheduler slot
+// taken (measured on B200, tools/cuda_probe/dfma_lat.cu: 3.0 / 2.5 / 2.2 cycles per DFMA per scheduler with
+// 1 / 2 / 4 independent chains per warp at 6 warps per scheduler).  Per trial the arithmetic is n1pdf_fast's.
+template <int NACC>
+GG_HD void n1pdf_fast2(double rtA, const CellAcc *eA, double rtB, const CellAcc *eB, int n_acc_rt, double &outA, double &outB)
+{
+    const int n_acc = NACC > 0 ? NACC : n_acc_rt;
+    double t0A = eA[0].t0a, t0B = eB[0].t0a;
+    double dtA = rtA - t0A, dtB = rtB - t0B;
+    double rdtA = fm::rcp_pos(dtA), rdtB = fm::rcp_pos(dtB);
+    double pdfA, pdfB;
+    {
+        const double rtsA = eA[0].inv_sdv * rdtA, tvA = eA[0].mean_v * dtA;
+        const double rtsB = eB[0].inv_sdv * rdtB, tvB = eB[0].mean_v * dtB;
+        const double z[4] = {(eA[0].b - tvA) * rtsA, ((eA[0].b - eA[0].A) - tvA) * rtsA, (eB[0].b - tvB) * rtsB,
+                             ((eB[0].b - eB[0].A) - tvB) * rtsB};
+        double cdf[4], phi[4];
+        fm::norm_pairs_stepmajor<4>(z, cdf, phi);
+        const double a1 = eA[0].mean_v * (cdf[0] - cdf[1]), a2 = eA[0].sd_v * (phi[1] - phi[0]);
+        const double b1 = eB[0].mean_v * (cdf[2] - cdf[3]), b2 = eB[0].sd_v * (phi[3] - phi[2]);
+        pdfA = fmax((a1 + a2) * (eA[0].inv_A * eA[0].inv_denom), kFloor);
+        pdfB = fmax((b1 + b2) * (eB[0].inv_A * eB[0].inv_denom), kFloor);
+    }
+#pragma unroll
+    for (int j = 1; j < n_acc; ++j) {
+        if (eA[j].t0a != t0A) {
+            t0A = eA[j].t0a;
+            dtA = rtA - t0A;
+            rdtA = fm::rcp_pos(dtA);
+        }
+        if (eB[j].t0a != t0B) {
+            t0B = eB[j].t0a;
+            dtB = rtB - t0B;
+            rdtB = fm::rcp_pos(dtB);
+        }
+        const double tsA = eA[j].sd_v * dtA, rtsA = eA[j].inv_sdv * rdtA, tvA = eA[j].mean_v * dtA;
+        const double tsB = eB[j].sd_v * dtB, rtsB = eB[j].inv_sdv * rdtB, tvB = eB[j].mean_v * dtB;
+        const double x1A = eA[j].b - tvA, x2A = x1A - eA[j].A;
+        const double x1B = eB[j].b - tvB, x2B = x1B - eB[j].A;
+        const double z[4] = {x1A * rtsA, x2A * rtsA, x1B * rtsB, x2B * rtsB};
+        double c[4], phi[4];
+        fm::norm_pairs_stepmajor<4>(z, c, phi);
+        const double sA = x2A * c[1] - x1A * c[0] + tsA * (phi[1] - phi[0]);
+        const double sB = x2B * c[3] - x1B * c[2] + tsB * (phi[3] - phi[2]);
+        double cdfA = (1.0 + sA * eA[j].inv_A) * eA[j].inv_denom;
+        double cdfB = (1.0 + sB * eB[j].inv_A) * eB[j].inv_denom;
+        cdfA = cdfA < kFloor ? kFloor : (1.0 < cdfA ? 1.0 : cdfA);
+        cdfB = cdfB < kFloor ? kFloor : (1.0 < cdfB ? 1.0 : cdfB);
+        pdfA = pdfA * (1.0 - cdfA);
+        pdfB = pdfB * (1.0 - cdfB);
+    }
+    outA = pdfA;
+    outB = pdfB;
+}
+
 // density of any trial of any cell class (used outside the hot loop)
 template <int NACC>
 GG_HD double n1pdf_any(uint8_t cls, double rt, const CellAcc *e, int n_acc)
