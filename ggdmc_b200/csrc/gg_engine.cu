@@ -276,12 +276,44 @@ struct TrialsDev {
     int S = 0, max_count = 0;
     int64_t total = 0;
     TrialData d{};
+    // Already grouped by cell, every subject a multiple of 8 trials: the caller's arrays ARE the device layout
+    // (one validation pass, then two copies straight from the caller's memory, no staging).
+    bool upload_direct(const ggdmc_trials_t *t, int n_cell, std::vector<int64_t> &off)
+    {
+        const int64_t base = t->subject_offset[0];
+        int mx = 0;
+        for (int s = 0; s < S; ++s) {
+            const int64_t b = t->subject_offset[s], e = t->subject_offset[s + 1];
+            if (e < b || e - b >= ((int64_t)1 << 31) || ((e - b) & 7) != 0) return false;
+            const uint16_t *c = t->cell + b;
+            const int n = (int)(e - b);
+            unsigned prev = 0, bad = 0;
+            for (int i = 0; i < n; ++i) {
+                bad |= (unsigned)(c[i] >= n_cell) | (unsigned)(c[i] < prev);
+                prev = c[i];
+            }
+            if (bad) return false; // out of range (reported by the general path) or not grouped
+            off[s] = b - base;
+            h_count[s] = n;
+            mx = std::max(mx, n);
+        }
+        max_count = mx;
+        total = t->subject_offset[S] - base;
+        rt.upload(t->rt + base, (size_t)total);
+        cell.upload(t->cell + base, (size_t)total);
+        offset.upload(off); count.upload(h_count);
+        counter.alloc(1); counter.zero();
+        d.rt = rt.p; d.cell = cell.p; d.offset = offset.p; d.count = count.p; d.counter = counter.p;
+        return true;
+    }
+
     void upload(const ggdmc_trials_t *t, int n_cell, bool keep_order)
     {
         require(t && t->n_subject >= 1, "no subjects");
         S = t->n_subject;
         std::vector<int64_t> off(S);
         h_count.resize(S);
+        if (!keep_order && upload_direct(t, n_cell, off)) return;
         std::vector<double> hrt;
         std::vector<uint16_t> hcl;
         if (keep_order) order.resize(S);
@@ -592,6 +624,8 @@ struct ggdmc_engine {
         for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (cudaEvent_t e : slot_ev) if (e) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         for (int g = 1; g < kMaxGroups; ++g) {
@@ -639,9 +673,22 @@ struct ggdmc_engine {
         // so item i's block is one contiguous copy
         const size_t CD = (size_t)C * D_, blk = (size_t)R * CD, blk1 = (size_t)R * C;
         CUDA_CHECK(cudaStreamSynchronize(0)); // pool allocations (ordered on the default stream) are now usable on `stream`
-        std::vector<double> th((size_t)n_items * blk), lp((size_t)n_items * blk1), ll(lp.size());
+        bool adjacent = true;
         for (int i = 0; i < n_items; ++i) {
             require(starts[i].theta && starts[i].lp && starts[i].ll, "null start state");
+            if (i > 0 && (starts[i].theta != starts[i - 1].theta + blk || starts[i].lp != starts[i - 1].lp + blk1 ||
+                          starts[i].ll != starts[i - 1].ll + blk1))
+                adjacent = false;
+        }
+        if (adjacent) { // the caller's arrays are the device layout (the Python binding and the R glue allocate them that way)
+            CUDA_CHECK(cudaMemcpyAsync(lv.theta.p, starts[0].theta, (size_t)n_items * blk * 8, cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaMemcpyAsync(lv.lp.p, starts[0].lp, (size_t)n_items * blk1 * 8, cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaMemcpyAsync(lv.ll.p, starts[0].ll, (size_t)n_items * blk1 * 8, cudaMemcpyHostToDevice, stream));
+            store(lv);
+            return;
+        }
+        std::vector<double> th((size_t)n_items * blk), lp((size_t)n_items * blk1), ll(lp.size());
+        for (int i = 0; i < n_items; ++i) {
             std::memcpy(&th[i * blk], starts[i].theta, blk * 8);
             std::memcpy(&lp[i * blk1], starts[i].lp, blk1 * 8);
             std::memcpy(&ll[i * blk1], starts[i].ll, blk1 * 8);
@@ -1027,18 +1074,79 @@ struct ggdmc_engine {
         ++h_iter;
     }
 
+    // ---- streamed results: stored slot k goes to the caller's arrays while later iterations run -------
+    struct OutSink { LevelDev *lv; int n_items; ggdmc_samples_t *outs; };
+    std::vector<OutSink> sinks;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> slot_ev;
+    int slots_sent = 0;
+
+    void stream_results_to(LevelDev &lv, int n_items, ggdmc_samples_t *outs)
+    {
+        for (int i = 0; i < n_items; ++i) {
+            require(outs[i].theta && outs[i].lp && outs[i].ll, "null output arrays");
+            outs[i].npar = lv.L.npar; outs[i].nchain = C; outs[i].nmc = nmc;
+        }
+        sinks.push_back(OutSink{&lv, n_items, outs});
+        if (!copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    }
+    // copy slots [slots_sent, upto): one strided copy per array when the per-item arrays are adjacent
+    void send_slots(int upto)
+    {
+        for (; slots_sent < upto; ++slots_sent) {
+            const int k = slots_sent;
+            if (k > 0) CUDA_CHECK(cudaStreamWaitEvent(copy_stream, slot_ev[k], 0));
+            for (OutSink &o : sinks) {
+                const int D_ = o.lv->L.npar;
+                const size_t row = (size_t)C * D_ * 8, row1 = (size_t)C * 8;
+                const size_t blk = (size_t)R * nmc * C * D_, blk1 = (size_t)R * nmc * C;
+                bool adjacent = true;
+                for (int i = 1; i < o.n_items; ++i)
+                    if (o.outs[i].theta != o.outs[i - 1].theta + blk || o.outs[i].lp != o.outs[i - 1].lp + blk1 ||
+                        o.outs[i].ll != o.outs[i - 1].ll + blk1)
+                        adjacent = false;
+                const int n_copy = adjacent ? 1 : o.n_items, rows = adjacent ? o.n_items * R : R;
+                for (int i = 0; i < n_copy; ++i) {
+                    CUDA_CHECK(cudaMemcpy2DAsync(o.outs[i].theta + (size_t)k * C * D_, row * nmc, o.lv->out_theta.p + i * blk + (size_t)k * C * D_,
+                                                 row * nmc, row, rows, cudaMemcpyDeviceToHost, copy_stream));
+                    CUDA_CHECK(cudaMemcpy2DAsync(o.outs[i].lp + (size_t)k * C, row1 * nmc, o.lv->out_lp.p + i * blk1 + (size_t)k * C, row1 * nmc,
+                                                 row1, rows, cudaMemcpyDeviceToHost, copy_stream));
+                    CUDA_CHECK(cudaMemcpy2DAsync(o.outs[i].ll + (size_t)k * C, row1 * nmc, o.lv->out_ll.p + i * blk1 + (size_t)k * C, row1 * nmc,
+                                                 row1, rows, cudaMemcpyDeviceToHost, copy_stream));
+                }
+            }
+        }
+    }
+
     void iterate(int n_iter, float *elapsed_ms, ggdmc_progress_fn progress, void *user, int report_length)
     {
         CUDA_CHECK(cudaSetDevice(device));
         CUDA_CHECK(cudaEventRecord(ev0, stream));
+        const bool streaming = !sinks.empty();
+        if (streaming) {
+            CUDA_CHECK(cudaStreamSynchronize(stream)); // slot 0 (the start state) is stored
+            slot_ev.resize((size_t)nmc, nullptr);
+        }
         for (int i = 0; i < n_iter; ++i) {
             step_once();
+            if (streaming && h_iter % (uint32_t)thin == 0 && h_iter / (uint32_t)thin < (uint32_t)nmc) {
+                // slot k is complete once this iteration is; it is sent one slot late, so that the (host-blocking, for
+                // pageable arrays) copy runs while the device already works on the iterations of the next slot
+                const int k = (int)(h_iter / (uint32_t)thin);
+                if (!slot_ev[k]) CUDA_CHECK(cudaEventCreateWithFlags(&slot_ev[k], cudaEventDisableTiming));
+                CUDA_CHECK(cudaEventRecord(slot_ev[k], stream));
+                send_slots(k);
+            }
             if (progress && report_length > 0 && h_iter % (uint32_t)thin == 0) {
                 uint32_t stored = h_iter / (uint32_t)thin; // theta_phi::print_progress, @hdr/theta.h:76-85
                 if ((stored + 1) % (uint32_t)report_length == 0) progress((int32_t)(stored + 1), user);
             }
         }
         CUDA_CHECK(cudaEventRecord(ev1, stream));
+        if (streaming) {
+            send_slots((int)std::min<uint32_t>((uint32_t)nmc, h_iter / (uint32_t)thin + 1));
+            CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+        }
         CUDA_CHECK(cudaStreamSynchronize(stream));
         CUDA_CHECK(cudaGetLastError());
         if (elapsed_ms) CUDA_CHECK(cudaEventElapsedTime(elapsed_ms, ev0, ev1));
@@ -1079,35 +1187,6 @@ struct ggdmc_engine {
         if (profile) collect_profile();
     }
 
-    // device storage -> the caller's posterior arrays.  Device order is item-major
-    // ([item][R][nmc][C][D]), i.e. exactly the concatenation of the per-item host arrays; when the
-    // caller's arrays are adjacent in memory (the Python binding and the R glue allocate them that
-    // way) the whole level comes back in three large copies.
-    void download_level(LevelDev &lv, int n_items, ggdmc_samples_t *outs)
-    {
-        const int D_ = lv.L.npar;
-        const size_t blk = (size_t)R * nmc * C * D_, blk1 = (size_t)R * nmc * C;
-        bool contiguous = true;
-        for (int i = 0; i < n_items; ++i) {
-            require(outs[i].theta && outs[i].lp && outs[i].ll, "null output arrays");
-            if (i > 0 && (outs[i].theta != outs[i - 1].theta + blk || outs[i].lp != outs[i - 1].lp + blk1 ||
-                          outs[i].ll != outs[i - 1].ll + blk1))
-                contiguous = false;
-            outs[i].npar = D_; outs[i].nchain = C; outs[i].nmc = nmc;
-        }
-        if (contiguous) {
-            CUDA_CHECK(cudaMemcpyAsync(outs[0].theta, lv.out_theta.p, (size_t)n_items * blk * 8, cudaMemcpyDeviceToHost, stream));
-            CUDA_CHECK(cudaMemcpyAsync(outs[0].lp, lv.out_lp.p, (size_t)n_items * blk1 * 8, cudaMemcpyDeviceToHost, stream));
-            CUDA_CHECK(cudaMemcpyAsync(outs[0].ll, lv.out_ll.p, (size_t)n_items * blk1 * 8, cudaMemcpyDeviceToHost, stream));
-        } else {
-            for (int i = 0; i < n_items; ++i) {
-                CUDA_CHECK(cudaMemcpyAsync(outs[i].theta, lv.out_theta.p + i * blk, blk * 8, cudaMemcpyDeviceToHost, stream));
-                CUDA_CHECK(cudaMemcpyAsync(outs[i].lp, lv.out_lp.p + i * blk1, blk1 * 8, cudaMemcpyDeviceToHost, stream));
-                CUDA_CHECK(cudaMemcpyAsync(outs[i].ll, lv.out_ll.p + i * blk1, blk1 * 8, cudaMemcpyDeviceToHost, stream));
-            }
-        }
-        CUDA_CHECK(cudaStreamSynchronize(stream));
-    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1283,8 +1362,8 @@ int ggdmc_b200_run_subject(const ggdmc_model_t *model, const ggdmc_trials_t *tri
     require(trials->n_subject == 1, "run_subject takes exactly one subject");
     ggdmc_engine e;
     e.create_lba(model, trials, p_prior, nullptr, cfg, nullptr, start);
+    e.stream_results_to(e.subj, 1, out);
     e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length); // m_nsample - 1 iterations
-    e.download_level(e.subj, 1, out);
     GG_CATCH
 }
 
@@ -1296,8 +1375,8 @@ int ggdmc_b200_run_hyper(const ggdmc_prior_t *p_prior, const ggdmc_prior_t *h_pr
     require(cfg && start && out, "null argument");
     ggdmc_engine e;
     e.create_hyper(p_prior, h_prior, data_theta, n_subject, cfg, start);
+    e.stream_results_to(e.phi, 1, out);
     e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length);
-    e.download_level(e.phi, 1, out);
     GG_CATCH
 }
 
@@ -1313,11 +1392,10 @@ int ggdmc_b200_run(const ggdmc_model_t *model, const ggdmc_trials_t *trials, con
         ggdmc_engine e;
         e.create_lba(model, trials, p_prior, h_prior, cfg, phi_start, subj_start);
         pt.lap("create");
+        e.stream_results_to(e.subj, e.S, subj_out);
+        e.stream_results_to(e.phi, 1, phi_out);
         e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length);
-        pt.lap("iterate");
-        e.download_level(e.subj, e.S, subj_out);
-        e.download_level(e.phi, 1, phi_out);
-        pt.lap("download");
+        pt.lap("iterate+download");
     }
     pt.lap("destroy");
     GG_CATCH
