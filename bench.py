@@ -348,7 +348,8 @@ def main():
         traffic = None  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_like_traffic.json")))
-            if args.workload in tj and args.schedule == "parallel" and world == 1:
+            if args.workload in tj and args.schedule == "parallel" and world == 1 and args.subjects == 0 \
+                    and abs(tj[args.workload]["trial_lik_per_launch"] - lik_per_launch) < 0.02 * lik_per_launch:
                 traffic = tj[args.workload]["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -378,7 +379,7 @@ def main():
         e2e = {"value": n_lik / dt_max, "unit": UNIT, "h2d_bytes_per_step": allsum(h2d) / K, "d2h_bytes_per_step": allsum(d2h) / K,
                "ms_per_step": 1e3 * dt_max / K, "thin": thin, "nmc": nmc,
                "call": "ggdmc_b200_run (C-ABI twin of .Call('_ggdmc_run')) with pageable host buffers: upload of trials + start "
-                       f"state, {K} iterations storing every {thin}th (nmc = {nmc}), download of all stored samples; host wall "
+                       f"state, {K} iterations storing every {thin}th (nmc = {nmc}), every stored sample copied to the host arrays (streamed one slot behind the sampler); host wall "
                        "clock around the call, max over ranks; trial-likelihoods per iteration from the resident phase's device counter"}
         assert np.all(np.isfinite(phi_out.theta))
     eng.close()
@@ -409,8 +410,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "schedule": args.schedule, "subjects_per_gpu": s1 - s0, "nchain": w.nchain,
-                       "trials_per_subject": ntr, "l2": "flushed: 256 MiB memset before every timed iteration, outside the event brackets",
-                       "timing": "CUDA events on the engine stream around each iteration (one CUDA-graph launch), summed; max over ranks",
+                       "trials_per_subject": ntr, "l2": "flushed: 256 MiB memset before every timed iteration, outside the event brackets (at N > 1 followed by a peer-memory barrier, also outside, so the memsets' skew is not booked as exchange wait)",
+                       "timing": "CUDA events on the engine stream around each iteration (one CUDA-graph launch: phi sweep on a side stream, two subject groups on their own streams, all joined before the closing event), summed; max over ranks. roofline pass: same iterations as plain launches on ONE stream so that every k_like launch is timed alone",
                        "seeds": seeds},
             "iters_per_s": K / (ms_max * 1e-3),
             "iters_per_s_unflushed": K / (ms_warm * 1e-3),

@@ -813,8 +813,12 @@ struct ggdmc_engine {
         H.like = p_prior.d;
         H.x = x; H.x_rep_stride = rep_stride; H.x_subj_stride = subj_stride; H.x_chain_stride = chain_stride;
         H.S = S; H.D = D; H.need_cur = need_cur;
-        // split subjects over blocks so that K4 fills the GPU (R*C blocks alone would not)
-        int want = std::max(1, (8 * 148 + R * C - 1) / (R * C));
+        // split subjects over blocks so that the phi kernels fill the GPU (R*C blocks alone would not) in ONE wave
+        int per_sm = 4, n_sm = 148;
+        const size_t sm_bytes = (size_t)(6 * D + 2 * (kHyperBlock / 32) + 4 * D) * 8;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_phi_half<kHyperBlock>, kHyperBlock, sm_bytes);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        int want = std::max(1, (std::max(per_sm, 1) * n_sm) / (R * C));
         int spb = std::max(64, (S + want - 1) / want); // >= 3 terms per thread: the per-block setup (proposal, 4 Phi + 2 log per parameter) is not free
         H.subj_per_block = spb;
         H.nsplit = (S + spb - 1) / spb;
