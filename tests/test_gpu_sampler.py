@@ -220,3 +220,43 @@ def test_error_behaviour():
     with pytest.raises(B.GgdmcError) as ei:
         E.run_subject(fx.ct, bad, prior, E.Tuning(nmc=3, nchain=3, nparameter=D), st)
     assert ei.value.code == B.ERR_ARG
+
+
+def test_results_do_not_depend_on_host_layout():
+    """The engine has a no-staging path for inputs that already have the device layout (trials grouped by cell with
+    every subject a multiple of 8 trials; start and output arrays of the subjects adjacent in memory) and a general
+    path (counting sort + padding, per-subject copies).  Both must give the same bits."""
+    from ggdmc_b200 import workloads as W
+    w = W.hierarchical("layout", 6, 5, 64, n_replicate=2)
+    D, C_ = w.spec.ct.npar, w.nchain
+    tun = W.tuning_for(w, nmc=4, thin=3, seeds=[11, 12], pop_migration_prob=0.3, sub_migration_prob=0.3)
+    stacked_trials = w.trials
+    assert all(len(t.rt) % 8 == 0 and np.all(np.diff(t.cell.astype(int)) >= 0) for t in stacked_trials)  # direct path applies
+    phi_a, subj_a = E.run_hier(w.spec.ct, stacked_trials, w.spec.p_prior, w.spec.h_prior, tun, w.phi_start, w.subj_start)
+
+    # general path: every subject's trials interleaved round-robin over its cells (a stable grouping by cell restores
+    # exactly the original order), separately allocated start states and separately allocated output arrays
+    rng = np.random.default_rng(3)
+    mixed = []
+    for t in stacked_trials:
+        cells = [np.nonzero(t.cell == c)[0] for c in np.unique(t.cell)]
+        order = [idx[i] for i in range(max(len(c) for c in cells)) for idx in cells if i < len(idx)]
+        assert sorted(order) == list(range(len(t.rt))) and not np.all(np.diff(t.cell[order].astype(int)) >= 0)
+        mixed.append(Trials(t.rt[order].copy(), t.cell[order].copy()))
+    pad = [np.empty(rng.integers(1, 50)) for _ in range(3 * len(mixed))]  # keeps the allocations apart
+    starts = [E.PopState(s.theta.copy(), s.lp.copy(), s.ll.copy()) for s in w.subj_start]
+    R, nmc = 2, 4
+    outs = [E.PopSamples.empty(R, nmc, C_, D) for _ in mixed]
+    phi_out = E.PopSamples.empty(R, nmc, C_, 2 * D)
+    phi_b, subj_b = E.run_hier(w.spec.ct, mixed, w.spec.p_prior, w.spec.h_prior, tun, w.phi_start, starts, out=(phi_out, outs))
+    del pad
+    assert np.array_equal(phi_a.theta, phi_b.theta) and np.array_equal(phi_a.ll, phi_b.ll) and np.array_equal(phi_a.lp, phi_b.lp)
+    for a, b in zip(subj_a, subj_b):
+        assert np.array_equal(a.theta, b.theta) and np.array_equal(a.lp, b.lp) and np.array_equal(a.ll, b.ll)
+    assert np.all(np.isfinite(phi_a.theta)) and not np.array_equal(phi_a.theta[:, 0], phi_a.theta[:, -1])
+
+    # a ragged subject (61 trials: padding, odd tail) changes only that subject's likelihoods, not the machinery
+    ragged = [Trials(t.rt[:61].copy(), t.cell[:61].copy()) if i == 2 else t for i, t in enumerate(stacked_trials)]
+    ll2 = E.sumloglike(w.spec.ct, ragged, np.stack([s.theta[0] for s in w.subj_start]))
+    ll1 = E.sumloglike(w.spec.ct, stacked_trials, np.stack([s.theta[0] for s in w.subj_start]))
+    assert np.array_equal(np.delete(ll1, 2, axis=0), np.delete(ll2, 2, axis=0)) and not np.array_equal(ll1[2], ll2[2])
