@@ -53,6 +53,30 @@ def load_model(k: int) -> ModelSpec:
                      _prior(g, "h_prior"), _prior(g, "sub_prior"))
 
 
+def sweep_model():
+    """BASELINE config 3's model: the 5-parameter, 2-accumulator LBA of the reference's first test model
+    (tests/testthat/Group1/data/0_lba_model0.r:22-30: A, B, mean_v.false, mean_v.true, t0 free; sd_v = 1, st0 = 0),
+    2 stimuli x 2 responses = 4 cells.  Returns (cell table, node_1_index, p_vector, uniform prior)."""
+    pnames = ["A", "B", "mean_v.false", "mean_v.true", "t0"]
+    const_val = np.array([1.0, 0.0])  # sd_v, st0
+    n_cell, n_acc = 4, 2
+    param_src = np.zeros((n_cell, 6, n_acc), dtype=np.int32)
+    node_1 = np.zeros((n_cell, n_acc), dtype=np.int64)
+    names = []
+    for s_ in range(2):
+        for r in range(2):
+            c = 2 * s_ + r
+            names.append(f"s{s_ + 1}.r{r + 1}")
+            node_1[c] = (r, 1 - r)  # responder first
+            for j, acc in enumerate((r, 1 - r)):
+                param_src[c, :, j] = (0, 1, 3 if acc == s_ else 2, -1, -2, 4)  # rows A, B, mean_v, sd_v, st0, t0
+    ct = CellTable(n_acc, n_cell, 5, param_src, const_val, np.array([1, 1], dtype=np.uint8), pnames, names)
+    p_vector = np.array([0.75, 1.25, 1.5, 2.5, 0.15])
+    prior = PriorTable(5, np.zeros(5), np.full(5, 10.0), np.zeros(5), np.full(5, 10.0), np.full(5, 6, dtype=np.int32),
+                       np.ones(5, dtype=np.uint8), pnames)
+    return ct, node_1, p_vector, prior
+
+
 @dataclass
 class HierWorkload:
     name: str

@@ -189,3 +189,37 @@ def test_chain_selection_bit_exact():
                 s2 = (C.c_uint * nchain)()
                 n2 = R.ref_get_subchains(nchain, s2)
                 assert n2 == on[i] and list(s2[:n2]) == list(om[i][:n2])
+
+
+def test_likelihood_sweep_config3_shapes():
+    """BASELINE config 3 (likelihood-only sweep: 5-parameter 2-accumulator model, 15 chains, 1e3 .. 1e7 trials of ONE
+    subject): the trial-chunked grid (a subject with > 8192 trials is split over blocks) against the oracle at the
+    sizes the oracle finishes in seconds, and at 1e7 trials through additivity / tiling."""
+    from ggdmc_b200 import synth
+    from ggdmc_b200 import workloads as W
+    ct, node_1, p_vector, _ = W.sweep_model()
+    om = ob.OModel(ct.param_src, ct.const_val, ct.posdrift, ct.npar)
+    rng = np.random.default_rng(20260103)
+    theta = p_vector * (1.0 + 0.05 * rng.uniform(-1, 1, size=(15, 5)))  # p_vector +- 5 % per chain (SURVEY 8d)
+    base = synth.simulate_subject(ct, node_1, p_vector, 100_000, rng)
+    for n in (1_000, 10_000, 100_000):
+        sub = Trials(base.rt[:: 100_000 // n][:n].copy(), base.cell[:: 100_000 // n][:n].copy())
+        got = E.sumloglike(ct, [sub], theta[None])[0]
+        od = ob.OData(sub.rt, sub.cell)
+        ref = np.array([ob.sumloglike(om, od, th) for th in theta])
+        assert np.all(np.isfinite(ref)) and np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-12, (n, got, ref)
+        # per-trial log densities of the first chain at this size
+        ld = E.trial_logdens(ct, sub, theta[:1])[0]
+        assert abs(ld.sum() - ref[0]) <= 1e-10 * abs(ref[0])
+    ll_1e5 = E.sumloglike(ct, [base], theta[None])[0]
+    # 1e6 and 1e7 trials = the 1e5 block tiled: the sum must scale (each block keeps its own fixed-order partial sums)
+    for reps in (10, 100):
+        big = Trials(np.tile(base.rt, reps), np.tile(base.cell, reps))
+        got = E.sumloglike(ct, [big], theta[None])[0]
+        assert np.max(np.abs(got - reps * ll_1e5) / np.abs(reps * ll_1e5)) <= 1e-11, reps
+    # ragged split of 1e6 trials into 7 subjects: additivity across subjects and chunk boundaries
+    big = Trials(np.tile(base.rt, 10), np.tile(base.cell, 10))
+    cuts = np.sort(rng.choice(np.arange(1, 1_000_000), size=6, replace=False))
+    parts = [Trials(r.copy(), c.copy()) for r, c in zip(np.split(big.rt, cuts), np.split(big.cell, cuts))]
+    per = E.sumloglike(ct, parts, np.broadcast_to(theta, (7, 15, 5)).copy())
+    assert np.max(np.abs(per.sum(axis=0) - 10 * ll_1e5) / np.abs(10 * ll_1e5)) <= 1e-11
