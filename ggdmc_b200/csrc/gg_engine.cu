@@ -459,7 +459,7 @@ int like_variant()
 
 size_t like_smem(const DevModel &M, int block)
 {
-    size_t b = (size_t)M.n_cell * M.n_acc * sizeof(CellAcc) + (size_t)(block / 32) * 8 + (size_t)M.n_cell;
+    size_t b = (size_t)M.n_cell * M.n_acc * sizeof(CellAcc) + (size_t)(block / 32) * 8 + (size_t)M.n_cell * (1 + M.n_acc);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -1283,7 +1283,7 @@ int ggdmc_b200_engine_time_likelihood(ggdmc_engine_t *engine, int32_t reps, floa
     if (const char *path = std::getenv("GGDMC_B200_BLOCKTRACE")) { // diagnostics: one more launch with per-block time stamps
         const size_t nblk = (size_t)L.npop * e.C * e.trials.d.nsplit;
         DBuf<unsigned long long> bt;
-        bt.alloc(3 * nblk + 2);
+        bt.alloc(5 * nblk + 2);
         bt.zero();
         CUDA_CHECK(cudaStreamSynchronize(0));
         TrialData T = e.trials.d;
@@ -1292,7 +1292,7 @@ int ggdmc_b200_engine_time_likelihood(ggdmc_engine_t *engine, int32_t reps, floa
         launch_like(L, e.model.d, T, e.d_iter.p, 0, -1, -1, e.ll_part.p, e.stream);
         k_stamp<<<1, 1, 0, e.stream>>>(bt.p + 1);
         CUDA_CHECK(cudaStreamSynchronize(e.stream));
-        std::vector<unsigned long long> h(3 * nblk + 2);
+        std::vector<unsigned long long> h(5 * nblk + 2);
         CUDA_CHECK(cudaMemcpy(h.data(), bt.p, h.size() * 8, cudaMemcpyDeviceToHost));
         if (FILE *f = std::fopen(path, "wb")) {
             std::fwrite(h.data(), 8, h.size(), f);
@@ -1420,7 +1420,7 @@ int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *t
     DBuf<double> d_theta, d_out;
     d_theta.upload(theta, (size_t)n_theta * model->npar);
     d_out.alloc((size_t)n_theta * std::max(ntr, 1));
-    const size_t sm = ((size_t)M.d.n_cell * M.d.n_acc * sizeof(CellAcc) + (size_t)M.d.n_cell + 15) & ~(size_t)15;
+    const size_t sm = ((size_t)M.d.n_cell * M.d.n_acc * sizeof(CellAcc) + (size_t)M.d.n_cell * (1 + M.d.n_acc) + 15) & ~(size_t)15;
     allow_smem(k_trial_logdens<128>, sm);
     if (ntr > 0) {
         dim3 grid(n_theta, std::min(64, (ntr + 127) / 128));

@@ -399,6 +399,34 @@ struct TrialData {
     unsigned long long *btrace;  // diagnostics (GGDMC_B200_BLOCKTRACE): per block {start ns, end ns, SM id}, normally null
 };
 
+struct BlockTrace { // thread 0 of a block stamps start, end, SM id, end of table build, end of trial loop into btrace[5 * block]
+    unsigned long long *slot;
+    __device__ __forceinline__ static unsigned long long now()
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        return t;
+    }
+    __device__ __forceinline__ explicit BlockTrace(unsigned long long *base) : slot(nullptr)
+    {
+        if (base && threadIdx.x == 0) {
+            slot = base + 5 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+            unsigned int sm;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+            slot[0] = now();
+            slot[2] = sm;
+        }
+    }
+    __device__ __forceinline__ ~BlockTrace()
+    {
+        if (slot) slot[1] = now();
+    }
+    __device__ __forceinline__ void mark(int i) const
+    {
+        if (slot) slot[i] = now();
+    }
+};
+
 constexpr double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
 
 // running product of densities as (mantissa in [1,2), exponent) -- replaces one log() per trial
@@ -442,6 +470,7 @@ __device__ __forceinline__ void build_cell_table(const DevModel &M, const double
                                                  uint8_t *cell_bad, const DrawAddr &addr)
 {
     const int n = M.n_cell * M.n_acc, na = M.n_acc;
+    uint8_t *row_cls = cell_bad + M.n_cell; // [n_cell * n_acc] class of every row on its own
     for (int k = threadIdx.x; k < n; k += BLOCK) {
         const int c = k / na, j = k - c * na;
         const int *src = M.param_src + (size_t)c * 6 * na;
@@ -454,19 +483,16 @@ __device__ __forceinline__ void build_cell_table(const DevModel &M, const double
         double u = 0.0;
         if (v[4] != 0.0) u = draw_uniform(addr, U_ST0, (uint32_t)k);
         cellacc_build(ent[k], v[0], v[1], v[2], v[3], v[4], v[5], M.posdrift[j] != 0, u);
-        if (j == 0) { // this thread also classifies the cell from ALL of its accumulators
-            uint8_t cls = cell_class_update(kCellRegular, v[0], v[1], v[2], v[3], v[4], v[5]);
-            for (int jj = 1; jj < na; ++jj) {
-                double w[6];
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    const int s = src[r * na + jj];
-                    w[r] = s >= 0 ? theta[s] : M.const_val[-1 - s];
-                }
-                cls = cell_class_update(cls, w[0], w[1], w[2], w[3], w[4], w[5]);
-            }
-            cell_bad[c] = cls;
+        row_cls[k] = cell_class_update(kCellRegular, v[0], v[1], v[2], v[3], v[4], v[5]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < M.n_cell; c += BLOCK) { // a cell is invalid if any row is, else generic if any row is
+        uint8_t cls = kCellRegular;
+        for (int j = 0; j < na; ++j) {
+            const uint8_t r = row_cls[c * na + j];
+            cls = (r == kCellInvalid || cls == kCellInvalid) ? (uint8_t)kCellInvalid : (r != kCellRegular ? r : cls);
         }
+        cell_bad[c] = cls;
     }
     __syncthreads();
 }
@@ -478,23 +504,26 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
 {
     const int C = L.nchain, D = L.npar, na = M.n_acc;
     const int s = p / L.n_rep;
-    const int ntr = T.count[s];
+    const int ntr = T.count[s]; // these two loads are only needed after the table is built: they travel meanwhile
+    const int64_t t_off = T.offset[s];
     const int t_begin = split * T.chunk;
     double *part = ll_part + ((size_t)p * C + chain) * T.nsplit + split;
-    if (t_begin >= ntr) {
-        if (threadIdx.x == 0) *part = 0.0;
-        return;
-    }
     CellAcc *ent = reinterpret_cast<CellAcc *>(sm_raw);
     double *red = reinterpret_cast<double *>(ent + M.n_cell * na);
     uint8_t *bad = reinterpret_cast<uint8_t *>(red + BLOCK / 32);
     const double *th = L.prop + ((size_t)p * C + chain) * D;
     DrawAddr addr = make_addr(L, p, iter, sweep, chain);
     build_cell_table<BLOCK>(M, th, ent, bad, addr);
+    unsigned long long *bslot = (T.btrace && threadIdx.x == 0) ? T.btrace + 5 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+    if (bslot) bslot[3] = BlockTrace::now();
+    if (t_begin >= ntr) { // empty chunk (a subject with fewer trials than the longest one)
+        if (threadIdx.x == 0) *part = 0.0;
+        return;
+    }
 
     const int t_end = min(ntr, t_begin + T.chunk);
-    const double *rt = T.rt + T.offset[s];
-    const uint16_t *cl = T.cell + T.offset[s];
+    const double *rt = T.rt + t_off;
+    const uint16_t *cl = T.cell + t_off;
     LogProd acc;
     acc.init();
     const double zf = T.zero_floor;
@@ -577,6 +606,7 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
             }
         }
     }
+    if (bslot) bslot[4] = BlockTrace::now();
     double v = block_sum<BLOCK>(acc.value(), red);
     if (threadIdx.x == 0) {
         *part = v;
@@ -585,30 +615,6 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
 }
 
 // Grid.  step >= 0 (REFERENCE schedule): block x = population, its chain is sweep position `step`.
-struct BlockTrace { // thread 0 of a block stamps its start / end time and SM into btrace[3 * block]
-    unsigned long long *slot;
-    __device__ __forceinline__ static unsigned long long now()
-    {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        return t;
-    }
-    __device__ __forceinline__ explicit BlockTrace(unsigned long long *base) : slot(nullptr)
-    {
-        if (base && threadIdx.x == 0) {
-            slot = base + 3 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
-            unsigned int sm;
-            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
-            slot[0] = now();
-            slot[2] = sm;
-        }
-    }
-    __device__ __forceinline__ ~BlockTrace()
-    {
-        if (slot) slot[1] = now();
-    }
-};
-
 // step < 0, half < 0: block x = (population, chain).  step < 0, half = 0 / 1 (PARALLEL schedule): block x =
 // (population, slot) with (nchain + 1) / 2 slots; a crossover population evaluates chain 2 slot + half, a
 // migrating population (whole migration in half 0) its chains slot and slot + nslots.

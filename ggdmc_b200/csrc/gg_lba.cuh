@@ -22,19 +22,27 @@ struct CellAcc {
 // Entry (cell, column j) of the table.  P* are the raw core parameters of that column
 // (A, B, mean_v, sd_v, st0, t0); u_st0 is the uniform of `t0 + st0 * U` (@hdr/lba.h:117).
 // Returns true when this accumulator makes the cell INVALID (@hdr/lba.h:121-146).
+// 1 / x for the cell table: hardware seed + two Newton steps (<= 1 ulp) when x is a comfortable positive normal
+// number -- true of A, sd_v and the drift denominator of every regular cell --, IEEE division otherwise, so the
+// generic path keeps the reference's behaviour for zeros, negatives, infinities and NaN
+GG_HD bool rcp_safe(double x) { return x > 1e-290 && x < 1e290; }
+GG_HD double rcp_table(double x) { return rcp_safe(x) ? fm::rcp_pos(x) : 1.0 / x; }
+
 GG_HD void cellacc_build(CellAcc &e, double A, double B, double mean_v, double sd_v, double st0, double t0,
                          bool posdrift, double u_st0)
 {
     double b = A + B; // design_light.h:336-340: row B += row A
-    double denom = posdrift ? fmax(fm::norm_pair(mean_v / sd_v).cdf, kFloor) : 1.0; // lba.h:112-115
+    const double inv_sdv = rcp_table(sd_v);
+    const double zv = rcp_safe(sd_v) ? mean_v * inv_sdv : mean_v / sd_v;
+    double denom = posdrift ? fmax(fm::norm_cdf_lowlatency(zv), kFloor) : 1.0; // lba.h:112-115
     e.b = b;
     e.A = A;
     e.mean_v = mean_v;
     e.sd_v = sd_v;
     e.t0a = (st0 != 0.0) ? t0 + st0 * u_st0 : t0 + st0 * 0.0; // lba.h:117 (t0 + 0*U == t0 + 0)
-    e.inv_sdv = 1.0 / sd_v;
-    e.inv_A = 1.0 / A;
-    e.inv_denom = 1.0 / denom;
+    e.inv_sdv = inv_sdv;
+    e.inv_A = rcp_table(A);
+    e.inv_denom = posdrift ? rcp_table(denom) : 1.0;
 }
 
 typedef fm::Pair PhiPair;

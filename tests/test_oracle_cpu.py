@@ -317,6 +317,16 @@ def test_fast_norm_pair_accuracy(hostmath):
     H.hm_norm_pair(zs.ctypes.data_as(dp), len(zs), cdf.ctypes.data_as(dp), pdf.ctypes.data_as(dp))
     assert list(cdf[:6]) == [0.5, 1.0, 0.0, 1.0, 0.0, 1.0] and np.isnan(cdf[6]) and np.isnan(pdf[6])
     assert pdf[0] == 0.3989422804014327 and list(pdf[1:6]) == [0.0] * 5
+    # the Estrin-scheme twin used by the cell-table build: same accuracy class, same special values
+    z = np.concatenate([rng.uniform(-37.5, 9, 2000), rng.uniform(-6, 6, 2000)])
+    low = np.zeros_like(z)
+    H.hm_norm_cdf_lowlatency(z.ctypes.data_as(dp), len(z), low.ctypes.data_as(dp))
+    for zi, c in zip(z, low):
+        rc = mp.ncdf(mp.mpf(float(zi)))
+        assert abs((mp.mpf(float(c)) - rc) / rc) < 1e-15, (zi, c)
+    low = np.zeros_like(zs)
+    H.hm_norm_cdf_lowlatency(zs.ctypes.data_as(dp), len(zs), low.ctypes.data_as(dp))
+    assert list(low[:6]) == [0.5, 1.0, 0.0, 1.0, 0.0, 1.0] and np.isnan(low[6])
 
 
 def test_device_prior_math_on_host_matches_oracle(hostmath):

@@ -13,10 +13,12 @@ ms, n = eng.time_likelihood(10)
 print(f"S={S}: {ms*1e3:.1f} us per launch (events, 10 launches back to back), {n} trial-likelihoods")
 h = np.fromfile(path, dtype=np.uint64)
 t0, t1 = int(h[0]), int(h[1])
-b = h[2:].reshape(-1, 3).astype(np.int64)
+b = h[2:].reshape(-1, 5).astype(np.int64)
 st, en, sm = b[:, 0] - t0, b[:, 1] - t0, b[:, 2]
 print(f"blocks {len(b)}; kernel bracket (stamp kernels) {1e-3*(t1-t0):.1f} us; first block start {st.min()*1e-3:.1f} us, last block end {en.max()*1e-3:.1f} us")
 dur = (en - st) * 1e-3
+pro, loop, epi = (b[:, 3] - b[:, 0]) * 1e-3, (b[:, 4] - b[:, 3]) * 1e-3, (b[:, 1] - b[:, 4]) * 1e-3
+print(f"  per block (thread 0's view): table build {pro.mean():.2f} us, trial loop {loop.mean():.2f} us, reduction + exit {epi.mean():.2f} us")
 order = np.argsort(st)
 nb = len(b)
 for lo, hi in [(0, 0.1), (0.1, 0.35), (0.35, 0.7), (0.7, 0.9), (0.9, 1.0)]:
