@@ -19,15 +19,14 @@ struct CellAcc {
     double b, A, mean_v, sd_v, t0a, inv_sdv, inv_A, inv_denom;
 };
 
-// Entry (cell, column j) of the table.  P* are the raw core parameters of that column
-// (A, B, mean_v, sd_v, st0, t0); u_st0 is the uniform of `t0 + st0 * U` (@hdr/lba.h:117).
-// Returns true when this accumulator makes the cell INVALID (@hdr/lba.h:121-146).
 // 1 / x for the cell table: hardware seed + two Newton steps (<= 1 ulp) when x is a comfortable positive normal
 // number -- true of A, sd_v and the drift denominator of every regular cell --, IEEE division otherwise, so the
 // generic path keeps the reference's behaviour for zeros, negatives, infinities and NaN
 GG_HD bool rcp_safe(double x) { return x > 1e-290 && x < 1e290; }
 GG_HD double rcp_table(double x) { return rcp_safe(x) ? fm::rcp_pos(x) : 1.0 / x; }
 
+// Entry (cell, column j) of the table from the raw core parameters of that column (A, B, mean_v, sd_v, st0, t0);
+// u_st0 is the uniform of `t0 + st0 * U` (@hdr/lba.h:117).
 GG_HD void cellacc_build(CellAcc &e, double A, double B, double mean_v, double sd_v, double st0, double t0,
                          bool posdrift, double u_st0)
 {
