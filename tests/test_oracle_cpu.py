@@ -380,3 +380,34 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(_lib.GgdmcError) as ei:
         engine.trial_logdens(fx.ct, fx.trials("sub"), fx.g["sub_theta"][:2])
     assert ei.value.code == _lib.ERR_CUDA
+
+
+def test_rprior_draws_follow_every_prior_family():
+    """ggdmc_b200.init.rprior (host side of initialise_theta / initialise_phi): support and moments of all seven
+    families, checked against the oracle's density through a histogram."""
+    from ggdmc_b200.init import rprior, _first_valid
+    from ggdmc_b200.model import PriorTable
+    #        tnorm        beta_lu     gamma_l     lnorm_l     cauchy      unif        norm
+    p0 = np.array([1.0, 2.0, 3.0, 0.2, 0.5, -1.0, 2.0])
+    p1 = np.array([0.8, 3.0, 0.5, 0.4, 1.5, 4.0, 0.7])
+    lo = np.array([0.2, -1.0, 0.5, 1.0, -3.0, -np.inf, -np.inf])
+    up = np.array([2.5, 4.0, np.inf, np.inf, 6.0, np.inf, np.inf])
+    dist = np.array([1, 2, 3, 4, 5, 6, 7], dtype=np.int32)
+    tab = PriorTable(7, p0, p1, lo, up, dist, np.zeros(7, dtype=np.uint8), [f"p{i}" for i in range(7)])
+    x = rprior(tab, 200_000, np.random.default_rng(5))
+    assert x.shape == (200_000, 7) and np.all(np.isfinite(x))
+    for i in range(7):
+        op = ob.OPrior(p0[i:i + 1], p1[i:i + 1], lo[i:i + 1], up[i:i + 1], dist[i:i + 1], np.zeros(1, dtype=np.uint8))  # log_p = 0: the density
+        xi = x[:, i]
+        a, b = (p0[i], p1[i]) if dist[i] == 6 else (lo[i], up[i])
+        assert np.all(xi >= a) and np.all(xi <= b), i
+        # histogram on the central 90 % against the oracle's density (dprior of one parameter at a time)
+        q = np.quantile(xi, [0.05, 0.95])
+        edges = np.linspace(q[0], q[1], 21)
+        h, _ = np.histogram(xi, bins=edges)
+        mid = 0.5 * (edges[1:] + edges[:-1])
+        dens = np.array([ob.sumlogprior(op, [m]) for m in mid])
+        expect = dens * (edges[1] - edges[0]) * len(xi)
+        assert np.all(np.abs(h - expect) <= 6 * np.sqrt(expect) + 0.01 * expect), (i, h, expect)
+    v = np.array([[False, True, True], [False, False, False], [True, False, True]])
+    assert list(_first_valid(v)) == [1, -1, 0]
