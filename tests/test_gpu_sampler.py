@@ -260,3 +260,22 @@ def test_results_do_not_depend_on_host_layout():
     ll2 = E.sumloglike(w.spec.ct, ragged, np.stack([s.theta[0] for s in w.subj_start]))
     ll1 = E.sumloglike(w.spec.ct, stacked_trials, np.stack([s.theta[0] for s in w.subj_start]))
     assert np.array_equal(np.delete(ll1, 2, axis=0), np.delete(ll2, 2, axis=0)) and not np.array_equal(ll1[2], ll2[2])
+
+
+def test_hierarchical_replicates_batch_equals_separate_runs():
+    """The ncore replicates of StartSampling are a batch dimension of one call (R/sampling.R:30-55 forks instead):
+    replicate r of a batched hierarchical run must be the run with seed r alone, bit for bit."""
+    from ggdmc_b200 import workloads as W
+    w = W.hierarchical("reps", 6, 5, 64, n_replicate=2)
+    seeds = [21, 22]
+    kw = dict(nmc=4, thin=2, pop_migration_prob=0.3, sub_migration_prob=0.3)
+    phi_b, subj_b = E.run_hier(w.spec.ct, w.trials, w.spec.p_prior, w.spec.h_prior, W.tuning_for(w, seeds=seeds, **kw), w.phi_start,
+                               w.subj_start)
+    for r, seed in enumerate(seeds):
+        phi0 = E.PopState(w.phi_start.theta[r:r + 1].copy(), w.phi_start.lp[r:r + 1].copy(), w.phi_start.ll[r:r + 1].copy())
+        subj0 = [E.PopState(s.theta[r:r + 1].copy(), s.lp[r:r + 1].copy(), s.ll[r:r + 1].copy()) for s in w.subj_start]
+        phi_1, subj_1 = E.run_hier(w.spec.ct, w.trials, w.spec.p_prior, w.spec.h_prior, W.tuning_for(w, seeds=[seed], **kw), phi0, subj0)
+        assert np.array_equal(phi_1.theta[0], phi_b.theta[r]) and np.array_equal(phi_1.ll[0], phi_b.ll[r])
+        for a, b in zip(subj_1, subj_b):
+            assert np.array_equal(a.theta[0], b.theta[r]) and np.array_equal(a.ll[0], b.ll[r]) and np.array_equal(a.lp[0], b.lp[r])
+    assert not np.array_equal(phi_b.theta[0], phi_b.theta[1])
