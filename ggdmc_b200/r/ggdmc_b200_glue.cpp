@@ -6,9 +6,11 @@
 //     run_subject(config_r, dmi, samples), run_hyper(config_r, dmi, samples), run(config_r, dmis, samples)
 // (src/de2R.cpp:8-171), so R/RcppExports.R, R/sampling.R and every user script stay unchanged.
 //
-// This file cannot be compiled in the build image (no R, Rcpp or Armadillo there); the same
-// flattening rules are implemented and tested in Python (ggdmc_b200/model.py, api.py), which is the
-// executable specification of what this file does.
+// The build image has no R, Rcpp or Armadillo, so this file is compiled there against a small stand-in for the Rcpp
+// calls it makes (tests/host/mock_rcpp/Rcpp.h) and driven with R-like objects by tests/glue_mock.py: its flattening
+// rules are checked against the reference's fixtures (tests/test_glue_cpu.py) and its three entry points return the
+// same posterior objects, bit for bit, as the Python mirror of the interface (tests/test_gpu_api.py).  Against real
+// Rcpp it needs nothing else: every call used here has Rcpp's spelling and semantics.
 //
 // [[Rcpp::depends(Rcpp)]]
 #include <Rcpp.h>

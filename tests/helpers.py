@@ -5,6 +5,8 @@ from typing import List
 
 import numpy as np
 
+from ggdmc_b200 import api
+
 from ggdmc_b200.model import CellTable, PriorTable, Trials
 from oracle import binding as ob
 
@@ -70,3 +72,19 @@ def cond_mask_tolerance(logd_ref: np.ndarray, rel=1e-10):
     d = np.exp(logd_ref)
     tol = rel * np.maximum(np.abs(logd_ref), 1.0) + 4e-15 / np.maximum(d, 1e-300)
     return tol
+
+
+def fixture_objects(k):
+    """Rebuild the reference's model / dmi / prior objects of fixture k from the committed golden file."""
+    fx = load_fixture(k)
+    g = fx.g
+    model = api.Model(parameter_x_condition_names=[str(s) for s in g["pxc_names"]], pnames=fx.ct.pnames, cell_names=fx.ct.cell_names,
+                      constants=api.NamedVector(g["const_val"], [str(s) for s in g["const_names"]]), model_boolean=g["model_boolean"],
+                      type="lba", npar=fx.ct.npar)
+
+    def dmi_of(which):
+        tr = fx.trials(which)
+        data = api.NamedList({fx.ct.cell_names[c]: tr.rt[tr.cell == c] for c in np.unique(tr.cell)})
+        return api.DMI(model=model, data=data, node_1_index=g["node_1_index"], is_positive_drift=g["is_positive_drift"])
+
+    return fx, model, dmi_of

@@ -7,25 +7,9 @@ from ggdmc_b200 import _lib as B
 from ggdmc_b200 import api, init
 from ggdmc_b200 import engine as E
 from oracle import binding as ob
-from helpers import load_fixture
+from helpers import fixture_objects, load_fixture
 
 pytestmark = pytest.mark.gpu
-
-
-def fixture_objects(k):
-    """Rebuild the reference's model / dmi / prior objects of fixture k from the committed golden file."""
-    fx = load_fixture(k)
-    g = fx.g
-    model = api.Model(parameter_x_condition_names=[str(s) for s in g["pxc_names"]], pnames=fx.ct.pnames, cell_names=fx.ct.cell_names,
-                      constants=api.NamedVector(g["const_val"], [str(s) for s in g["const_names"]]), model_boolean=g["model_boolean"],
-                      type="lba", npar=fx.ct.npar)
-
-    def dmi_of(which):
-        tr = fx.trials(which)
-        data = api.NamedList({fx.ct.cell_names[c]: tr.rt[tr.cell == c] for c in np.unique(tr.cell)})
-        return api.DMI(model=model, data=data, node_1_index=g["node_1_index"], is_positive_drift=g["is_positive_drift"])
-
-    return fx, model, dmi_of
 
 
 def test_flattening_of_reference_objects_matches_goldens():
@@ -120,3 +104,42 @@ def test_reference_errors_surface():
     bad.model = api.Model(model.parameter_x_condition_names, model.pnames, model.cell_names, model.constants, model.model_boolean, type="fastdm")
     with pytest.raises(B.GgdmcError, match="Undefined model type"):
         api.run_subject(cfg, bad, st)
+
+
+def test_rcpp_glue_entry_points_equal_the_python_mirror():
+    """ggdmc_b200/r/ggdmc_b200_glue.cpp -- the file a ggdmc maintainer drops into src/ -- compiled against the Rcpp
+    stand-in (tests/host/mock_rcpp) and driven with R-like objects: run_subject, run_hyper and run return posterior
+    objects with the same slots and the same numbers as the Python mirror of the interface (same seed = same Philox key)."""
+    import glue_mock as G
+    fx, model, dmi_of = fixture_objects(2)
+    S, D = 4, fx.ct.npar
+    nchain, nmc, thin = 6 * D, 4, 2
+    pp, hp = fx.prior("p_prior"), fx.prior("h_prior")
+    prior = api.Prior(nparameter=2 * D, pnames=hp.pnames, p_prior=api.prior_list(pp), h_prior=api.prior_list(hp))
+    ti = api.ThetaInput(nmc=nmc, nchain=nchain, thin=thin, nparameter=2 * D, pnames=hp.pnames, report_length=2, is_print=True)
+    de = api.DEInput(pop_migration_prob=0.2, sub_migration_prob=0.2, nparameter=2 * D, nchain=nchain)
+    cfg = api.Config(prior=prior, theta_input=ti, de_input=de, seed=4242)
+    dmis = [dmi_of(f"pop{s}") for s in range(S)]
+    start = init.initialise_phi(ti, prior, dmis, seed=3)
+
+    def same(a: api.Posterior, b: api.Posterior):
+        assert np.array_equal(a.theta, b.theta) and np.array_equal(a.summed_log_prior, b.summed_log_prior)
+        assert np.array_equal(a.log_likelihoods, b.log_likelihoods)
+        assert (a.start, a.npar, a.pnames, a.nmc, a.thin, a.nchain) == (b.start, b.npar, b.pnames, b.nmc, b.thin, b.nchain)
+
+    # run (hierarchical)
+    ref = api.run(cfg, dmis, start)
+    got = G.run(cfg, dmis, start)
+    same(got["phi"], ref["phi"])
+    assert len(got["subject_theta"]) == S
+    for a, b in zip(got["subject_theta"], ref["subject_theta"]):
+        same(a, b)
+    # run_subject (first subject, its own prior), continuing from the hierarchical fit like RestartSampling does
+    sub_prior = api.Prior(nparameter=D, pnames=fx.ct.pnames, p_prior=api.prior_list(fx.prior("sub_prior")))
+    cfg1 = api.Config(prior=sub_prior, theta_input=api.ThetaInput(nmc=nmc, nchain=nchain, thin=thin, nparameter=D, pnames=fx.ct.pnames),
+                      de_input=api.DEInput(sub_migration_prob=0.1, nparameter=D, nchain=nchain), seed=7)
+    st1 = ref["subject_theta"][0]
+    same(G.run_subject(cfg1, dmis[0], st1), api.run_subject(cfg1, dmis[0], st1))
+    # run_hyper on a matrix of subject-level estimates
+    hyper_dmi = api.DMI(model=api.Model([], [], [], api.NamedVector([], []), np.zeros((0, 0, 0), bool), type="hyper"), data=fx.g["hyper_data"])
+    same(G.run_hyper(cfg, hyper_dmi, start["phi"]), api.run_hyper(cfg, hyper_dmi, start["phi"]))
