@@ -117,8 +117,19 @@ struct FlatPrior {
 };
 
 struct FlatConfig {
-    uint64_t seed;
+    std::vector<uint64_t> seeds; // one Philox key per replicate
     ggdmc_config_t c{};
+    // the replicates of one StartSampling call share everything but the seed (R/sampling.R:13-29 builds them that way)
+    explicit FlatConfig(const Rcpp::List &configs) : FlatConfig(Rcpp::as<Rcpp::S4>(configs[0]))
+    {
+        seeds.clear();
+        for (R_xlen_t r = 0; r < configs.size(); ++r) {
+            Rcpp::S4 cr = Rcpp::as<Rcpp::S4>(configs[r]);
+            seeds.push_back((uint64_t)Rcpp::as<double>(cr.slot("seed")));
+        }
+        c.n_replicate = (int32_t)seeds.size();
+        c.seed = seeds.data();
+    }
     explicit FlatConfig(const Rcpp::S4 &config_r)
     {
         Rcpp::S4 ti = config_r.slot("theta_input"), de = config_r.slot("de_input");
@@ -130,8 +141,8 @@ struct FlatConfig {
         c.nparameter = de.slot("nparameter");
         c.schedule = GGDMC_SCHEDULE_PARALLEL; // options(ggdmc.schedule = "reference") could select the other
         c.n_replicate = 1; c.device = -1;
-        seed = (uint64_t)Rcpp::as<double>(config_r.slot("seed")); // config@seed -> Philox key (R/model-class.R:1514-1515)
-        c.seed = &seed;
+        seeds.push_back((uint64_t)Rcpp::as<double>(config_r.slot("seed"))); // config@seed -> Philox key (R/model-class.R:1514-1515)
+        c.seed = seeds.data();
     }
 };
 
@@ -139,7 +150,10 @@ struct FlatConfig {
 struct StartState {
     std::vector<double> theta, lp, ll;
     ggdmc_start_t c{};
-    StartState(const Rcpp::S4 &samples)
+    StartState() = default;
+    StartState(const Rcpp::S4 &samples) { append(samples); }
+    // one more replicate: the ABI takes [n_replicate][nchain][npar] per population
+    void append(const Rcpp::S4 &samples)
     {
         Rcpp::NumericVector th = samples.slot("theta");
         Rcpp::IntegerVector d = th.attr("dim");
@@ -151,7 +165,7 @@ struct StartState {
             if (ok) break;
         }
         Rcpp::NumericMatrix lpm = samples.slot("summed_log_prior"), llm = samples.slot("log_likelihoods");
-        theta.assign(th.begin() + s * blk, th.begin() + (s + 1) * blk); // npar x nchain col-major == [nchain][npar]
+        theta.insert(theta.end(), th.begin() + s * blk, th.begin() + (s + 1) * blk); // npar x nchain col-major == [nchain][npar]
         for (size_t k = 0; k < nchain; ++k) { lp.push_back(lpm(k, s)); ll.push_back(llm(k, s)); }
         c.theta = theta.data(); c.lp = lp.data(); c.ll = ll.data();
     }
@@ -159,12 +173,14 @@ struct StartState {
 
 void progress_cb(int32_t i, void *) { Rcpp::Rcout << i << " "; } // theta_phi::print_progress, @hdr/theta.h:76-85
 
-Rcpp::S4 make_posterior(const ggdmc_samples_t &s, const std::vector<std::string> &pnames, int thin)
+// replicate r of the sample arrays of one population -> one `posterior`
+Rcpp::S4 make_posterior(const ggdmc_samples_t &s, const std::vector<std::string> &pnames, int thin, int r = 0)
 {
     Rcpp::S4 out("posterior"); // src/type_casting.h:10-26
-    Rcpp::NumericVector th(s.theta, s.theta + (size_t)s.npar * s.nchain * s.nmc);
+    const size_t blk = (size_t)s.npar * s.nchain * s.nmc, blk1 = (size_t)s.nchain * s.nmc;
+    Rcpp::NumericVector th(s.theta + r * blk, s.theta + (r + 1) * blk);
     th.attr("dim") = Rcpp::IntegerVector::create(s.npar, s.nchain, s.nmc);
-    Rcpp::NumericMatrix lp(s.nchain, s.nmc, s.lp), ll(s.nchain, s.nmc, s.ll);
+    Rcpp::NumericMatrix lp(s.nchain, s.nmc, s.lp + r * blk1), ll(s.nchain, s.nmc, s.ll + r * blk1);
     out.slot("theta") = th; out.slot("summed_log_prior") = lp; out.slot("log_likelihoods") = ll;
     out.slot("start") = 1; out.slot("npar") = s.npar; out.slot("pnames") = pnames;
     out.slot("nmc") = s.nmc; out.slot("thin") = thin; out.slot("nchain") = s.nchain;
@@ -174,7 +190,8 @@ Rcpp::S4 make_posterior(const ggdmc_samples_t &s, const std::vector<std::string>
 struct OutBuf {
     std::vector<double> theta, lp, ll;
     ggdmc_samples_t c{};
-    OutBuf(int npar, int nchain, int nmc) : theta((size_t)npar * nchain * nmc), lp((size_t)nchain * nmc), ll((size_t)nchain * nmc)
+    OutBuf(int npar, int nchain, int nmc, int n_rep = 1)
+        : theta((size_t)n_rep * npar * nchain * nmc), lp((size_t)n_rep * nchain * nmc), ll((size_t)n_rep * nchain * nmc)
     {
         c.npar = npar; c.nchain = nchain; c.nmc = nmc; c.theta = theta.data(); c.lp = lp.data(); c.ll = ll.data();
     }
@@ -252,4 +269,78 @@ Rcpp::List run(const Rcpp::S4 &config_r, const Rcpp::List &dmis, const Rcpp::Lis
     Rcpp::S4 ti = config_r.slot("theta_input");
     return Rcpp::List::create(Rcpp::Named("phi") = make_posterior(phi_out.c, Rcpp::as<std::vector<std::string>>(ti.slot("pnames")), cfg.c.thin),
                               Rcpp::Named("subject_theta") = theta_out);
+}
+
+// ---- the ncore replicates of a StartSampling call as ONE call ---------------------------------------------------
+// The reference forks ncore R processes (parallel_lapply, R/sampling.R:13-121), one replicate each.  Forking after
+// CUDA is initialised is not supported and ncore processes would time-share one GPU anyway, so the replicates become
+// a batch dimension of the engine: parallel_lapply calls these once with the list of configs.
+
+// [[Rcpp::export]]
+Rcpp::List run_subject_batch(const Rcpp::List &configs, const Rcpp::S4 &dmi, const Rcpp::List &samples)
+{
+    const int R = configs.size();
+    if (R < 1 || samples.size() != R) Rcpp::stop("need one start object per config");
+    Rcpp::S4 config0 = Rcpp::as<Rcpp::S4>(configs[0]);
+    Rcpp::S4 priors = config0.slot("prior");
+    FlatModel m = flatten_model(dmi);
+    FlatTrials t; t.add(dmi, m.cell_names); t.finish();
+    FlatPrior pp(priors.slot("p_prior"));
+    FlatConfig cfg(configs);
+    StartState st;
+    for (int r = 0; r < R; ++r) st.append(Rcpp::as<Rcpp::S4>(samples[r]));
+    OutBuf out(m.c.npar, cfg.c.nchain, cfg.c.nmc, R);
+    char err[256] = {0};
+    if (ggdmc_b200_run_subject(&m.c, &t.c, &pp.c, &cfg.c, &st.c, &out.c, progress_cb, nullptr, err)) Rcpp::stop(err);
+    Rcpp::Rcout << std::endl;
+    Rcpp::List fits(R);
+    for (int r = 0; r < R; ++r) fits[r] = make_posterior(out.c, m.pnames, cfg.c.thin, r);
+    return fits;
+}
+
+// [[Rcpp::export]]
+Rcpp::List run_batch(const Rcpp::List &configs, const Rcpp::List &dmis, const Rcpp::List &samples)
+{
+    const int R = configs.size(), S = dmis.size();
+    if (R < 1 || samples.size() != R) Rcpp::stop("need one start object per config");
+    Rcpp::S4 config0 = Rcpp::as<Rcpp::S4>(configs[0]);
+    Rcpp::S4 priors = config0.slot("prior");
+    FlatPrior pp(priors.slot("p_prior")), hp(priors.slot("h_prior"));
+    FlatModel m = flatten_model(Rcpp::as<Rcpp::S4>(dmis[0]));
+    FlatTrials t;
+    for (int s = 0; s < S; ++s) t.add(Rcpp::as<Rcpp::S4>(dmis[s]), m.cell_names);
+    t.finish();
+    FlatConfig cfg(configs);
+    std::vector<StartState> starts(S);
+    StartState phi_start;
+    for (int r = 0; r < R; ++r) {
+        Rcpp::List sr = samples[r]; // list(phi = <posterior>, subject_theta = list(<posterior> ...)) of replicate r
+        phi_start.append(Rcpp::as<Rcpp::S4>(sr["phi"]));
+        Rcpp::List subj_r = sr["subject_theta"];
+        for (int s = 0; s < S; ++s) starts[s].append(Rcpp::as<Rcpp::S4>(subj_r[s]));
+    }
+    std::vector<ggdmc_start_t> starts_c;
+    for (auto &s : starts) starts_c.push_back(s.c);
+    const size_t blk = (size_t)R * m.c.npar * cfg.c.nchain * cfg.c.nmc, blk1 = (size_t)R * cfg.c.nchain * cfg.c.nmc;
+    std::vector<double> big_t(blk * S), big_lp(blk1 * S), big_ll(blk1 * S);
+    std::vector<ggdmc_samples_t> outs(S);
+    for (int s = 0; s < S; ++s) {
+        outs[s].npar = m.c.npar; outs[s].nchain = cfg.c.nchain; outs[s].nmc = cfg.c.nmc;
+        outs[s].theta = big_t.data() + s * blk; outs[s].lp = big_lp.data() + s * blk1; outs[s].ll = big_ll.data() + s * blk1;
+    }
+    OutBuf phi_out(hp.c.npar, cfg.c.nchain, cfg.c.nmc, R);
+    char err[256] = {0};
+    if (ggdmc_b200_run(&m.c, &t.c, &pp.c, &hp.c, &cfg.c, &phi_start.c, starts_c.data(), &phi_out.c, outs.data(), progress_cb, nullptr, err))
+        Rcpp::stop(err);
+    Rcpp::Rcout << std::endl;
+    Rcpp::S4 ti = config0.slot("theta_input");
+    const std::vector<std::string> phi_names = Rcpp::as<std::vector<std::string>>(ti.slot("pnames"));
+    Rcpp::List fits(R);
+    for (int r = 0; r < R; ++r) {
+        Rcpp::List theta_out(S);
+        for (int s = 0; s < S; ++s) theta_out[s] = make_posterior(outs[s], m.pnames, cfg.c.thin, r);
+        fits[r] = Rcpp::List::create(Rcpp::Named("phi") = make_posterior(phi_out.c, phi_names, cfg.c.thin, r),
+                                     Rcpp::Named("subject_theta") = theta_out);
+    }
+    return fits;
 }

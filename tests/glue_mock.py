@@ -37,6 +37,7 @@ def lib():
                             ("gh_length", C.c_long, [vp]), ("gh_kind", C.c_int, [vp]), ("gh_real_ptr", C.POINTER(C.c_double), [vp]),
                             ("gh_int_ptr", C.POINTER(C.c_int), [vp]), ("gh_str_at", C.c_char_p, [vp, C.c_long]), ("gh_last_error", C.c_char_p, []),
                             ("gh_run_subject", vp, [vp, vp, vp]), ("gh_run_hyper", vp, [vp, vp, vp]), ("gh_run", vp, [vp, vp, vp]),
+                            ("gh_run_subject_batch", vp, [vp, vp, vp]), ("gh_run_batch", vp, [vp, vp, vp]),
                             ("gh_flatten_model", C.c_int, [vp, C.POINTER(C.c_int), C.c_long, C.POINTER(C.c_int)]),
                             ("gh_flatten_trials", C.c_long, [vp, C.POINTER(C.c_double), C.POINTER(C.c_ushort), C.c_long]),
                             ("gh_start_slice", C.c_long, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long])]:
@@ -183,8 +184,24 @@ def run_hyper(config: api.Config, dmi: api.DMI, samples: api.Posterior) -> api.P
 
 
 def run(config: api.Config, dmis, samples):
-    s = r_list([r_posterior(samples["phi"]), r_list([r_posterior(p) for p in samples["subject_theta"]])], names=["phi", "subject_theta"])
-    o = _check(lib().gh_run(r_config(config), r_list([r_dmi(d) for d in dmis]), s))
+    return _py_hier(_check(lib().gh_run(r_config(config), r_list([r_dmi(d) for d in dmis]), _r_hier(samples))))
+
+
+def _py_hier(o):
     subj = lib().gh_list_get(o, 1)
     return {"phi": py_posterior(lib().gh_list_get(o, 0)),
             "subject_theta": [py_posterior(lib().gh_list_get(subj, i)) for i in range(lib().gh_length(subj))]}
+
+
+def _r_hier(samples):
+    return r_list([r_posterior(samples["phi"]), r_list([r_posterior(p) for p in samples["subject_theta"]])], names=["phi", "subject_theta"])
+
+
+def run_subject_batch(configs, dmi: api.DMI, samples):
+    o = _check(lib().gh_run_subject_batch(r_list([r_config(c) for c in configs]), r_dmi(dmi), r_list([r_posterior(p) for p in samples])))
+    return [py_posterior(lib().gh_list_get(o, r)) for r in range(lib().gh_length(o))]
+
+
+def run_batch(configs, dmis, samples):
+    o = _check(lib().gh_run_batch(r_list([r_config(c) for c in configs]), r_list([r_dmi(d) for d in dmis]), r_list([_r_hier(s) for s in samples])))
+    return [_py_hier(lib().gh_list_get(o, r)) for r in range(lib().gh_length(o))]

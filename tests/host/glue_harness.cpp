@@ -62,6 +62,21 @@ void *gh_run(void *config, void *dmis, void *samples)
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }
 
+void *gh_run_subject_batch(void *configs, void *dmi, void *samples)
+{
+    try {
+        return box(run_subject_batch(Rcpp::List(*static_cast<RObject *>(configs)), Rcpp::S4(*static_cast<RObject *>(dmi)),
+                                     Rcpp::List(*static_cast<RObject *>(samples))));
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void *gh_run_batch(void *configs, void *dmis, void *samples)
+{
+    try {
+        return box(run_batch(Rcpp::List(*static_cast<RObject *>(configs)), Rcpp::List(*static_cast<RObject *>(dmis)),
+                             Rcpp::List(*static_cast<RObject *>(samples))));
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+
 // the glue's flattening rules on their own (no GPU): param_src [n_cell][6][n_acc], trials of one dmi, the start slice
 int gh_flatten_model(void *dmi, int *param_src, long cap, int *dims /* n_acc, n_cell, npar, n_const */)
 {

@@ -143,3 +143,18 @@ def test_rcpp_glue_entry_points_equal_the_python_mirror():
     # run_hyper on a matrix of subject-level estimates
     hyper_dmi = api.DMI(model=api.Model([], [], [], api.NamedVector([], []), np.zeros((0, 0, 0), bool), type="hyper"), data=fx.g["hyper_data"])
     same(G.run_hyper(cfg, hyper_dmi, start["phi"]), api.run_hyper(cfg, hyper_dmi, start["phi"]))
+    # the ncore replicates as one call (what parallel_lapply becomes): equal to one call per replicate
+    cfgs = [api.Config(prior=prior, theta_input=ti, de_input=de, seed=sd) for sd in (4242, 99)]
+    starts = [start, init.initialise_phi(ti, prior, dmis, seed=8)]
+    batch = G.run_batch(cfgs, dmis, starts)
+    same(batch[0]["phi"], ref["phi"])
+    second = api.run(cfgs[1], dmis, starts[1])
+    same(batch[1]["phi"], second["phi"])
+    for a, b in zip(batch[1]["subject_theta"], second["subject_theta"]):
+        same(a, b)
+    cfgs1 = [api.Config(prior=sub_prior, theta_input=cfg1.theta_input, de_input=cfg1.de_input, seed=sd) for sd in (7, 8, 9)]
+    sts = [ref["subject_theta"][0], ref["subject_theta"][1], ref["subject_theta"][2]]
+    fits = G.run_subject_batch(cfgs1, dmis[0], sts)
+    assert len(fits) == 3
+    for c1, s1, f in zip(cfgs1, sts, fits):
+        same(f, api.run_subject(c1, dmis[0], s1))
