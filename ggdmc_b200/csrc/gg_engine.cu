@@ -589,7 +589,7 @@ struct ggdmc_engine {
     struct SubjGroup { Level L; TrialData T; double *ll_part; int index; };
     std::vector<SubjGroup> groups;
     cudaStream_t gstream[kMaxGroups] = {};
-    cudaEvent_t ev_gdone[kMaxGroups] = {};
+    cudaEvent_t ev_gdone[kMaxGroups] = {}, ev_prop[kMaxGroups] = {};
     // optional per-launch timing of the likelihood kernel (bench.py roofline)
     // one DE-MCMC iteration captured as a CUDA graph (fixed launch sequence: every data-dependent
     // decision is taken on the device); GGDMC_B200_NO_GRAPH=1 falls back to plain stream launches
@@ -630,6 +630,7 @@ struct ggdmc_engine {
         if (ev_join) cudaEventDestroy(ev_join);
         for (int g = 1; g < kMaxGroups; ++g) {
             if (ev_gdone[g]) cudaEventDestroy(ev_gdone[g]);
+            if (ev_prop[g - 1]) cudaEventDestroy(ev_prop[g - 1]);
             if (gstream[g]) cudaStreamDestroy(gstream[g]);
         }
         if (side) cudaStreamDestroy(side);
@@ -796,6 +797,7 @@ struct ggdmc_engine {
             if (g > 0) {
                 CUDA_CHECK(cudaStreamCreateWithPriority(&gstream[g], cudaStreamNonBlocking, prio_lo));
                 CUDA_CHECK(cudaEventCreateWithFlags(&ev_gdone[g], cudaEventDisableTiming));
+                CUDA_CHECK(cudaEventCreateWithFlags(&ev_prop[g - 1], cudaEventDisableTiming));
             }
         }
     }
@@ -884,7 +886,10 @@ struct ggdmc_engine {
     }
 
     // ---- one sweep at each level --------------------------------------------------------------
-    void sweep_lba(const SubjGroup &G, cudaStream_t stream, int sweep, int decide_once, int para_idx, cudaEvent_t join = nullptr)
+    // wait_first / rec_first: the groups' FIRST proposal kernels of an iteration run one after the other instead of side by
+    // side, so that group 0's likelihood launch -- the first thing able to fill the GPU -- starts as early as possible
+    void sweep_lba(const SubjGroup &G, cudaStream_t stream, int sweep, int decide_once, int para_idx, cudaEvent_t join = nullptr,
+                   cudaEvent_t wait_first = nullptr, cudaEvent_t rec_first = nullptr)
     {
         const Level &L = G.L;
         const size_t prop_sm = (size_t)kProposeWarps * D * 8;
@@ -896,7 +901,9 @@ struct ggdmc_engine {
             for (int h = 0; h < nhalf; ++h) {
                 const int half = nhalf == 2 ? h : -1;
                 const int nw = half < 0 ? n : L.npop * ((C + 1) / 2); // warps: one per (population, chain) or per (population, slot)
+                if (h == 0 && wait_first) CUDA_CHECK(cudaStreamWaitEvent(stream, wait_first, 0));
                 TR("k_propose", stream, launch_hi(k_propose<kProposeWarps>, (nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream, L, d_iter.p, sweep, -1, half));
+                if (h == 0 && rec_first) CUDA_CHECK(cudaEventRecord(rec_first, stream));
                 timed_like(G, stream, sweep, -1, half);
                 if (join && h == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0)); // the MH test needs this iteration's phi
                 TR("k_accept", stream, launch_hi(k_accept, (n + 127) / 128, 128, 0, stream, L, d_iter.p, sweep, -1, (const double *)G.ll_part, G.T.nsplit));
@@ -921,8 +928,11 @@ struct ggdmc_engine {
         for (size_t g = 0; g < groups.size(); ++g) {
             cudaStream_t st = (conc && g > 0) ? gstream[g] : stream;
             if (st != stream) CUDA_CHECK(cudaStreamWaitEvent(st, ev_fork, 0));
-            for (int p = 0; p < nsweep; ++p)
-                sweep_lba(groups[g], st, p, decide_once, is_pblocked ? p : -1, p == 0 ? join : nullptr);
+            for (int p = 0; p < nsweep; ++p) {
+                const bool first = p == 0 && conc && groups.size() > 1;
+                sweep_lba(groups[g], st, p, decide_once, is_pblocked ? p : -1, p == 0 ? join : nullptr,
+                          first && g > 0 ? ev_prop[g - 1] : nullptr, first && g + 1 < groups.size() ? ev_prop[g] : nullptr);
+            }
             if (st != stream) {
                 CUDA_CHECK(cudaEventRecord(ev_gdone[g], st));
                 CUDA_CHECK(cudaStreamWaitEvent(stream, ev_gdone[g], 0));

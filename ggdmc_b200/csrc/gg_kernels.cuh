@@ -190,24 +190,24 @@ __global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int de
 // lexicographic (key, pos) minimum across the warp
 __device__ __forceinline__ void warp_min_keypos(int &key, int &pos)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        int k2 = __shfl_xor_sync(0xffffffffu, key, o);
-        int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
-        if (k2 < key || (k2 == key && p2 < pos)) { key = k2; pos = p2; }
-    }
+    // keys and positions are non-negative: two warp-wide integer minima (REDUX) instead of five shuffle rounds
+    const int mk = __reduce_min_sync(0xffffffffu, key);
+    const int mp = __reduce_min_sync(0xffffffffu, key == mk ? pos : 0x7fffffff);
+    key = mk;
+    pos = mp;
 }
 
 // get_chains(i, 2), src/de.cpp:54-60: the two smallest shuffle keys among the candidate chains.
 // half < 0: candidates = every chain but i (the reference's rule); half = 0 / 1: candidates = the
 // chains of the OTHER parity (two-half PARALLEL schedule).
-__device__ __forceinline__ void pick_partners(const DrawAddr &a, int C, int i, int half, int lane, int &c0, int &c1)
+// `pre`: this lane's partner block (index = lane) when the caller drew partner and noise blocks in one pass, else null
+__device__ __forceinline__ void pick_partners(const DrawAddr &a, int C, int i, int half, int lane, int &c0, int &c1, const U4 *pre = nullptr)
 {
     const int ncand = half < 0 ? C - 1 : (C + half) / 2;
     const int INTMAX = 0x7fffffff;
     int k1 = INTMAX, p1 = INTMAX, k2 = INTMAX, p2 = INTMAX; // lane-local best two
     for (int blk = lane; blk * 4 < ncand; blk += 32) {
-        U4 w = draw_block(a, U_PARTNER, (uint32_t)blk);
+        U4 w = pre ? *pre : draw_block(a, U_PARTNER, (uint32_t)blk);
         uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -315,7 +315,15 @@ __device__ __forceinline__ void propose_position(const Level &L, int p, int k, i
         tgt = k;
     }
     DrawAddr a = make_addr(L, p, iter, sweep, src);
-    if (!mode) pick_partners(a, C, src, half, lane, c0, c1);
+    // One Philox pass per warp when everything fits: lanes [0, nb) draw the partner-key blocks, lanes [nb, nb + nn) the
+    // noise blocks (a warp instruction costs the same with 10 or with 14 active lanes); lane d then fetches its noise
+    // word by shuffle.  Same addressed draws as the two-pass form below, which stays for populations of > 100 chains.
+    const int nb = mode ? 0 : (((half < 0 ? C - 1 : (C + half) / 2) + 3) >> 2), nn = (D + 3) >> 2;
+    const bool one_pass = nb + nn <= 32 && D <= 32;
+    U4 wb = {0u, 0u, 0u, 0u};
+    if (one_pass && lane < nb + nn) // purpose and block index are data, so both kinds of lanes run the same Philox code together
+        wb = draw_block(a, lane < nb ? U_PARTNER : U_NOISE, (uint32_t)(lane < nb ? lane : lane - nb));
+    if (!mode) pick_partners(a, C, src, half, lane, c0, c1, one_pass ? &wb : nullptr);
     const double *th = L.theta + ((size_t)p * C + src) * D;
     const double *t0 = L.theta + ((size_t)p * C + c0) * D;
     const double *t1 = L.theta + ((size_t)p * C + c1) * D;
@@ -323,11 +331,19 @@ __device__ __forceinline__ void propose_position(const Level &L, int p, int k, i
     // a phi-driven prior is evaluated in k_accept instead: the proposal and its likelihood do not need
     // this iteration's phi, so they can run while the phi sweep is still in flight
     const bool defer = L.prior_ovr != nullptr;
+    uint32_t my_word = 0;
+    if (one_pass) { // lane d needs word d % 4 of noise block d / 4, held by lane nb + d / 4
+        const int from = nb + (lane >> 2);
+        const uint32_t x = __shfl_sync(0xffffffffu, wb.x, from & 31), y = __shfl_sync(0xffffffffu, wb.y, from & 31);
+        const uint32_t z = __shfl_sync(0xffffffffu, wb.z, from & 31), w4 = __shfl_sync(0xffffffffu, wb.w, from & 31);
+        const int q = lane & 3;
+        my_word = q == 0 ? x : (q == 1 ? y : (q == 2 ? z : w4));
+    }
     for (int d = lane; d < D; d += 32) {
         double x = th[d];
         const bool moved = para_idx >= 0 ? (d == para_idx) : (d < L.nmove);
         if (moved) {
-            double u = draw_uniform(a, U_NOISE, (uint32_t)d);
+            double u = one_pass ? word_to_uniform(my_word) : draw_uniform(a, U_NOISE, (uint32_t)d);
             double noise = runif_from(-L.rp, L.rp, u);
             double inc = mode ? noise : __dadd_rn(noise, __dmul_rn(L.gamma, __dsub_rn(t0[d], t1[d])));
             x = __dadd_rn(x, inc);
