@@ -6,11 +6,14 @@
 //                       (src/de.cpp:119-141, 164-184, 394-426, 488-518, 575-603, 627-652)
 //   K2 k_like         : LBA sum-log-likelihood of every proposal (the FP64 hot kernel)
 //                       (@hdr/likelihood.h:73-108, 272-292 + @hdr/lba.h)
-//   K3 k_accept       : Metropolis accept / commit (src/de.cpp:81-108)
-//   K4 k_hyper        : phi-level hyper-likelihood partial sums over the local subjects
-//                       (src/de.cpp:245-270), k_hyper_reduce, k_phi_accept (:397-400, 427-463,
-//                       494-500, 519-549)
-//      k_store        : thinned sample storage (@hdr/theta.h:61-74)
+//   K3 k_accept       : Metropolis accept / commit (src/de.cpp:81-108); in a hierarchy also the log prior of the
+//                       proposal under its phi chain (:599-604, 646-653)
+//   K4 k_phi_half     : one phi half-sweep in one launch: proposal, hyper-likelihood partial sums over the local
+//                       subjects (src/de.cpp:245-270), reduction, exchange with the peer GPUs, MH test
+//                       (:397-400, 427-463, 494-500, 519-549); k_hyper, k_hyper_reduce(_exchange), k_phi_accept are
+//                       the same steps as separate launches (in-place order, NCCL fallback)
+//      k_phi_consts   : per phi chain constants of the truncated-normal prior of the subject level
+//      k_store_advance: thinned sample storage (@hdr/theta.h:61-74) + the device-side iteration counter
 //
 // A "population" is one set of nchain chains: a (replicate, subject) pair at the subject level,
 // a replicate at the phi level.  `step < 0` processes every chain of the sweep at once from the
