@@ -9,19 +9,21 @@ every subject) of BASELINE config 4 -- 1024 synthetic subjects x 768 trials, 78 
 B x v model -- with subjects sharded over the N GPUs (strong scaling: total work fixed).
 
   value     trial-likelihoods/s with data, state and sample storage resident in HBM; the number of
-            trial-likelihoods is counted on the device (migration sweeps evaluate fewer chains)
+            trial-likelihoods is counted on the device (migration sweeps evaluate fewer chains); L2 flushed
+            before every timed iteration, CUDA events, max over ranks
   e2e       the same metric through the reference-facing call `ggdmc_b200_run` (the C-ABI twin of
-            .Call("_ggdmc_run")) with HOST buffers: upload of data + start state, K iterations,
-            download of the K stored samples, all inside the timed region
+            .Call("_ggdmc_run")) with HOST buffers: upload of data + start state, K iterations, every stored
+            sample copied back to the host arrays (streamed behind the sampler), all inside the timed region
   roofline  the LBA likelihood kernel against the FP64 FMA peak measured on this GPU by a DFMA
             microbenchmark (MEASURED_PEAKS.json has no FP64 entry); achieved = 513 algorithmic
             flop per 2-accumulator trial x trial-likelihoods per launch / mean
-            CUDA-event duration of the launches inside the timed region
-  cpu_baseline  the CPU oracle (a -O2 C restatement of the reference's algorithm, kind "port") timed
-            on one host core on a bounded sample of the same workload
+            CUDA-event duration of the launches of a second, single-stream pass over K more iterations
+  cpu_baseline  de_class::run_hchains of the reference's OWN object code (src/de.o behind an R-API shim,
+            oracle/_ref; kind "reference") on one host core on a bounded sample of the same workload, with the
+            -O2 C restatement (the oracle, kind "port") beside it; the port alone where oracle/_ref is absent
 
-`--impl reference` times the reference's CPU path (the same port, one replicate per host core like
-the reference's `ncore` forked replicates, R/sampling.R:26-55) on a bounded sample.
+`--impl reference` times that reference CPU path with one replicate per host core, like the reference's
+`ncore` forked replicates (R/sampling.R:26-55), on a bounded sample; rank 0 only.
 """
 import argparse
 import json
@@ -64,7 +66,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
