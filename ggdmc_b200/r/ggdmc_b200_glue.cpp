@@ -344,3 +344,46 @@ Rcpp::List run_batch(const Rcpp::List &configs, const Rcpp::List &dmis, const Rc
     }
     return fits;
 }
+
+// ---- scoring candidate start values in bulk (initialise_theta / initialise_phi, R/phi.R:141-332) -----------------
+// The reference scores ONE candidate per R -> C++ round trip (ggdmcLikelihood::compute_subject_likelihood + .sumlog,
+// ggdmcPrior::dprior) inside `repeat` loops.  These two routines score all candidates of all chains of all subjects in
+// one call each, so initialise_* reduces to: draw a batch with rprior(), score it, keep the first valid per chain.
+
+// theta: numeric array npar x n_candidate x n_subject (column-major, like R); returns n_candidate x n_subject matrix of
+// sum log-likelihoods under `.sumlog`'s rule (densities <= 0 count as .Machine$double.eps, R/phi.R:3-13)
+// [[Rcpp::export]]
+Rcpp::NumericMatrix sumloglike_init_batch(const Rcpp::List &dmis, const Rcpp::NumericVector &theta)
+{
+    const int S = dmis.size();
+    FlatModel m = flatten_model(Rcpp::as<Rcpp::S4>(dmis[0]));
+    FlatTrials t;
+    for (int s = 0; s < S; ++s) t.add(Rcpp::as<Rcpp::S4>(dmis[s]), m.cell_names);
+    t.finish();
+    Rcpp::IntegerVector d = theta.attr("dim");
+    if (d.size() != 3 || d[0] != m.c.npar || d[2] != S) Rcpp::stop("theta must be npar x n_candidate x n_subject");
+    const int n_cand = d[1];
+    std::vector<double> out((size_t)S * n_cand);
+    char err[256] = {0};
+    // npar x n_candidate x n_subject column-major IS [n_subject][n_candidate][npar] row-major: no copy needed
+    if (ggdmc_b200_sumloglike_init(&m.c, &t.c, &theta[0], n_cand, out.data(), err)) Rcpp::stop(err);
+    return Rcpp::NumericMatrix(n_cand, S, out.data());
+}
+
+// x: npar x n matrix of parameter vectors; p0 / p1: NULL-length (use the prior's own location / scale) or npar x n
+// (the phi-driven case: the hyper-likelihood of theta under candidate phi); returns n sum log-priors
+// [[Rcpp::export]]
+Rcpp::NumericVector sumlogprior_batch(const Rcpp::List &prior, const Rcpp::NumericMatrix &x, const Rcpp::NumericVector &p0,
+                                      const Rcpp::NumericVector &p1)
+{
+    FlatPrior pr(prior);
+    if (x.nrow() != pr.c.npar) Rcpp::stop("x must be npar x n");
+    const int n = x.ncol();
+    const bool ovr = p0.size() > 0;
+    if (ovr && (p0.size() != (R_xlen_t)pr.c.npar * n || p1.size() != p0.size())) Rcpp::stop("p0 / p1 must be npar x n");
+    Rcpp::NumericVector out((R_xlen_t)n);
+    char err[256] = {0};
+    if (ggdmc_b200_sumlogprior(&pr.c, &x[0], ovr ? &p0[0] : nullptr, ovr ? &p1[0] : nullptr, n, &out[0], err)) Rcpp::stop(err);
+    return out;
+}
+

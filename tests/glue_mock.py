@@ -38,6 +38,7 @@ def lib():
                             ("gh_int_ptr", C.POINTER(C.c_int), [vp]), ("gh_str_at", C.c_char_p, [vp, C.c_long]), ("gh_last_error", C.c_char_p, []),
                             ("gh_run_subject", vp, [vp, vp, vp]), ("gh_run_hyper", vp, [vp, vp, vp]), ("gh_run", vp, [vp, vp, vp]),
                             ("gh_run_subject_batch", vp, [vp, vp, vp]), ("gh_run_batch", vp, [vp, vp, vp]),
+                            ("gh_sumloglike_init_batch", vp, [vp, vp]), ("gh_sumlogprior_batch", vp, [vp, vp, vp, vp]),
                             ("gh_flatten_model", C.c_int, [vp, C.POINTER(C.c_int), C.c_long, C.POINTER(C.c_int)]),
                             ("gh_flatten_trials", C.c_long, [vp, C.POINTER(C.c_double), C.POINTER(C.c_ushort), C.c_long]),
                             ("gh_start_slice", C.c_long, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_long])]:
@@ -205,3 +206,16 @@ def run_subject_batch(configs, dmi: api.DMI, samples):
 def run_batch(configs, dmis, samples):
     o = _check(lib().gh_run_batch(r_list([r_config(c) for c in configs]), r_list([r_dmi(d) for d in dmis]), r_list([_r_hier(s) for s in samples])))
     return [_py_hier(lib().gh_list_get(o, r)) for r in range(lib().gh_length(o))]
+
+
+def sumloglike_init_batch(dmis, theta):
+    """theta [npar, n_candidate, n_subject] (R layout) -> [n_candidate, n_subject]."""
+    return _real(_check(lib().gh_sumloglike_init_batch(r_list([r_dmi(d) for d in dmis]), r_real(theta))))
+
+
+def sumlogprior_batch(prior_list: api.NamedList, x, p0=None, p1=None):
+    """x [npar, n] (R layout) -> [n]; p0 / p1 [npar, n] or None."""
+    empty = np.zeros(0)
+    return _real(_check(lib().gh_sumlogprior_batch(r_prior_list(prior_list), r_real(x), r_real(empty if p0 is None else p0),
+                                                   r_real(empty if p1 is None else p1))))
+

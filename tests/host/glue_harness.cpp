@@ -77,6 +77,20 @@ void *gh_run_batch(void *configs, void *dmis, void *samples)
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }
 
+void *gh_sumloglike_init_batch(void *dmis, void *theta)
+{
+    try {
+        return box(sumloglike_init_batch(Rcpp::List(*static_cast<RObject *>(dmis)), Rcpp::NumericVector(*static_cast<RObject *>(theta))));
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void *gh_sumlogprior_batch(void *prior, void *x, void *p0, void *p1)
+{
+    try {
+        return box(sumlogprior_batch(Rcpp::List(*static_cast<RObject *>(prior)), Rcpp::NumericMatrix(*static_cast<RObject *>(x)),
+                                     Rcpp::NumericVector(*static_cast<RObject *>(p0)), Rcpp::NumericVector(*static_cast<RObject *>(p1))));
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+
 // the glue's flattening rules on their own (no GPU): param_src [n_cell][6][n_acc], trials of one dmi, the start slice
 int gh_flatten_model(void *dmi, int *param_src, long cap, int *dims /* n_acc, n_cell, npar, n_const */)
 {

@@ -158,3 +158,30 @@ def test_rcpp_glue_entry_points_equal_the_python_mirror():
     assert len(fits) == 3
     for c1, s1, f in zip(cfgs1, sts, fits):
         same(f, api.run_subject(c1, dmis[0], s1))
+
+
+def test_rcpp_glue_scores_start_value_candidates_in_bulk():
+    """sumloglike_init_batch / sumlogprior_batch of the glue: what an R-side initialise_theta / initialise_phi would call
+    instead of one likelihood round trip per candidate (R/phi.R:166-201, 300-326)."""
+    import glue_mock as G
+    fx, model, dmi_of = fixture_objects(6)
+    S, D, n_cand = 3, fx.ct.npar, 11
+    dmis = [dmi_of(f"pop{s}") for s in range(S)]
+    rng = np.random.default_rng(2)
+    pp = fx.prior("p_prior")
+    cand = init.rprior(pp, S * n_cand, rng).reshape(S, n_cand, D)  # [subject][candidate][par]
+    cand[0, 0, :] = 50.0  # a hopeless candidate: densities underflow to 0 -> the eps floor of .sumlog applies
+    got = G.sumloglike_init_batch(dmis, np.transpose(cand, (2, 1, 0)))  # R array npar x n_candidate x n_subject
+    ref = E.sumloglike(fx.ct, [fx.trials(f"pop{s}") for s in range(S)], cand, init_rule=True)
+    assert got.shape == (n_cand, S) and np.array_equal(got.T, ref) and np.all(np.isfinite(got))
+    od = fx.odata("pop1")
+    for j in (0, 5):
+        o = ob.sumloglike_rinit(fx.om, od, cand[1, j])
+        assert abs(got[j, 1] - o) <= 1e-9 * abs(o)
+    x = cand.reshape(-1, D)
+    lp = G.sumlogprior_batch(api.prior_list(pp), x.T)
+    assert np.array_equal(lp, E.sumlogprior(pp, x))
+    phi = np.abs(rng.normal(1.0, 0.2, size=(x.shape[0], 2 * D)))
+    lp2 = G.sumlogprior_batch(api.prior_list(pp), x.T, phi[:, :D].T, phi[:, D:].T)
+    assert np.array_equal(lp2, E.sumlogprior(pp, x, np.ascontiguousarray(phi[:, :D]), np.ascontiguousarray(phi[:, D:])))
+
