@@ -29,7 +29,10 @@ class Rng(C.Structure):
 
 class Model(C.Structure):
     _fields_ = [("n_acc", C.c_int), ("n_cell", C.c_int), ("npar", C.c_int), ("param_src", c_ip),
-                ("const_val", c_dp), ("posdrift", c_u8p)]
+                ("const_val", c_dp), ("posdrift", c_u8p), ("type", C.c_int)]
+
+
+MODEL_LBA, MODEL_DDM = 0, 1
 
 
 class Data(C.Structure):
@@ -119,14 +122,15 @@ def ptr(a: np.ndarray, t=c_dp):
 class OModel:
     """Keeps the numpy buffers alive next to the C struct."""
 
-    def __init__(self, param_src, const_val, posdrift, npar):
+    def __init__(self, param_src, const_val, posdrift, npar, type=MODEL_LBA):
         self.param_src = np.ascontiguousarray(param_src, dtype=np.int32)
         self.const_val = f64(const_val if len(const_val) else [0.0])
         self.posdrift = np.ascontiguousarray(posdrift, dtype=np.uint8)
-        n_cell, six, n_acc = self.param_src.shape
-        assert six == 6
-        self.c = Model(n_acc, n_cell, int(npar), ptr(self.param_src, c_ip), ptr(self.const_val), ptr(self.posdrift, c_u8p))
-        self.n_acc, self.n_cell, self.npar = n_acc, n_cell, int(npar)
+        n_cell, rows, n_acc = self.param_src.shape
+        assert rows == (10 if type == MODEL_DDM else 6)
+        assert self.posdrift.size == (n_cell if type == MODEL_DDM else n_acc)
+        self.c = Model(n_acc, n_cell, int(npar), ptr(self.param_src, c_ip), ptr(self.const_val), ptr(self.posdrift, c_u8p), int(type))
+        self.n_acc, self.n_cell, self.npar, self.type = n_acc, n_cell, int(npar), int(type)
 
 
 class OData:

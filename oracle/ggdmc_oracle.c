@@ -83,14 +83,15 @@ static double runif_(orc_rng *r, const orc_addr *a, double lo, double hi)
  * A, B, mean_v, sd_v, st0, t0; then row B += row A so the density sees b = A + B. */
 void orc_cell_params(const orc_model *m, const double *theta, int cell, double *P)
 {
-    int na = m->n_acc;
-    const int *src = m->param_src + (size_t)cell * 6 * na;
-    for (int r = 0; r < 6; ++r)
+    int na = m->n_acc, rows = m->type == ORC_MODEL_DDM ? ORC_DDM_ROWS : ORC_LBA_ROWS;
+    const int *src = m->param_src + (size_t)cell * rows * na;
+    for (int r = 0; r < rows; ++r)
         for (int j = 0; j < na; ++j) {
             int s = src[r * na + j];
             P[r * na + j] = s >= 0 ? theta[s] : m->const_val[-1 - s];
         }
-    for (int j = 0; j < na; ++j) P[1 * na + j] += P[0 * na + j];
+    if (m->type != ORC_MODEL_DDM) /* :336-340 only the row NAMED "B" gets += the row above it; the DDM has no such row */
+        for (int j = 0; j < na; ++j) P[1 * na + j] += P[0 * na + j];
 }
 
 /* lba_class::{set_parameters :88-119, validate_parameters :121-146, dlba :560-572, d :213-248,
@@ -149,6 +150,206 @@ int orc_lba_cell(const double *P, int na, const unsigned char *posdrift, const d
     return 1;
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* DDM ("fastdm") first-passage density                                                         */
+/* ------------------------------------------------------------------------------------------- */
+/* ddm::ddm_class of @hdr/ddm.h (anonymous namespace; compiled into src/de.o at -O0 with line
+ * tables, decoded with objdump -d -C -l; member offsets from its DWARF).  The arithmetic is the
+ * fast-dm density of Voss & Voss (2007) / Navarro & Fuss (2009): small- and large-time series for the
+ * lower-boundary density, closed-form integral over the drift variability sv, midpoint rules over the
+ * start-point range sz and the non-decision range st0.  Operation ORDER below follows the object code
+ * so that the restatement is bit-identical to it (checked in tests/test_oracle_cpu.py through
+ * likelihood_class::ddm_likelihood of de.o). */
+typedef struct {
+    double a, v, sv, st0, zr, szr, t_offset; /* m_a @0, m_v @8, m_sv @0x28, m_st0 @0x30, m_zr @0x38, m_szr @0x20, m_t_offset @0x58 */
+    double s;                                /* m_s @0x40 */
+    double int_t0, int_z, sz_eps, st0_eps;   /* TUNE_INT_T0 @0xa0, TUNE_INT_Z @0xa8, TUNE_SZ_EPSILON @0xb8, TUNE_ST0_EPSILON @0xc0 */
+    double a2, v2, sv2;                      /* @0xe8, @0xf0, @0xf8 */
+} ddm_par;
+
+#define DDM_EPSILON 1e-6                 /* ddm::EPSILON, .rodata+0x1b8 */
+#define DDM_PI 3.141592653589793         /* .rodata+0xec8 */
+#define DDM_2PI 6.283185307179586        /* .rodata+0xec0 */
+#define DDM_PI2 9.869604401089358        /* m_pi2 @0xe0, set by the constructor (@hdr/ddm.h:141) */
+
+/* x86 cvttsd2si: NaN and out-of-range values give INT_MIN (the object code converts with it) */
+static int cvt_trunc(double x) { return (x >= -2147483648.0 && x < 2147483648.0) ? (int)x : (-2147483647 - 1); }
+
+/* set_parameters(matrix, is_lower), @hdr/ddm.h:187-226, with set_precision :120-138.
+ * P = column 0 of rows a, d, precision, s, st0, sv, sz, t0, v, z. */
+static void ddm_set(ddm_par *q, const double *P, int is_lower)
+{
+    double s = P[3], scale = (1.0 != s) ? 1.0 / s : 1.0, prec = P[2], tmp;   /* :194-195 */
+    q->s = s;
+    q->st0 = P[4];                                                            /* :201 */
+    q->a = P[0] * scale;                                                      /* :203 */
+    q->sv = P[5] * scale;                                                     /* :204 */
+    q->v = is_lower ? P[8] * scale : (-P[8]) * scale;                         /* :205-206 */
+    q->t_offset = 0.5 * P[4] + P[7];                                          /* :208 */
+    tmp = P[9] / q->a;                                                        /* :216 */
+    q->zr = is_lower ? tmp : 1.0 - tmp;                                       /* :217 */
+    q->szr = P[6] / q->a;                                                     /* :218 */
+    q->int_t0 = exp(prec * -1.03758) * 0.089045;                              /* :130 */
+    q->int_z = exp(prec * -1.022373) * 0.508061;                              /* :131 */
+    q->sz_eps = pow(10.0, -(2.0 + prec));                                     /* :136 */
+    q->st0_eps = pow(10.0, -(2.0 + prec));                                    /* :137 */
+    q->a2 = q->a * q->a; q->v2 = q->v * q->v; q->sv2 = q->sv * q->sv;         /* :223-225 */
+}
+
+/* validate_parameters, @hdr/ddm.h:229-309 (comparisons false on NaN) */
+static int ddm_valid(const ddm_par *q)
+{
+    int ok = 1;
+    if (q->a <= 0) ok = 0;                          /* :232 */
+    if (q->szr < 0 || q->szr > 1.0) ok = 0;         /* :240 */
+    if (q->st0 < 0) ok = 0;                         /* :250 */
+    if (q->sv < 0) ok = 0;                          /* :259 */
+    if (q->t_offset < 0) ok = 0;                    /* :268 */
+    if (q->zr - 0.5 * q->szr <= 0) ok = 0;          /* :278 */
+    if (q->zr + 0.5 * q->szr >= 1.0) ok = 0;        /* :288 */
+    if (q->s <= 0) ok = 0;                          /* :298 */
+    return ok;
+}
+
+/* compute_g_series, @hdr/ddm.h:344-379 */
+static double ddm_series(double ta, double zr, int use_small, int N)
+{
+    double sum = 0.0;
+    if (use_small) {
+        double t3 = ta * ta * ta;                   /* :356 */
+        double norm = 1.0 / sqrt(t3 * DDM_2PI);     /* :357 */
+        int lo = -(N / 2), hi = N / 2;              /* :359-360 */
+        for (int i = lo; i <= hi; ++i) {
+            double d = ((double)i + (double)i) + zr;            /* :364 */
+            sum = exp((-d * d) / (ta + ta)) * d + sum;          /* :365 */
+        }
+        return sum * norm;                          /* :367 */
+    }
+    for (int i = 1; i <= N; ++i) {                  /* :372 */
+        double d = DDM_PI * (double)i;              /* :374 */
+        sum = (double)i * (exp(-0.5 * d * d * ta) * sin(d * zr)) + sum; /* :375 */
+    }
+    return DDM_PI * sum;                            /* :377 */
+}
+
+/* compute_g_factor, @hdr/ddm.h:383-405 */
+static double ddm_factor(const ddm_par *q, double t, double zr, int no_var)
+{
+    double f;
+    if (no_var) {
+        f = exp((-q->a * zr) * q->v - (0.5 * q->v2) * t) / q->a2;                                       /* :388 */
+    } else {
+        double denom = 1.0 + q->sv2 * t;                                                                 /* :396 */
+        double e = (-0.5 * ((q->v2 * t + (q->a * (q->v + q->v)) * zr) - ((q->a2 * zr) * zr) * q->sv2)) / denom; /* :397-398 */
+        f = exp(e) / (q->a2 * sqrt(denom));                                                              /* :401 */
+    }
+    return isfinite(f) ? f : 0.0;                                                                        /* :389, :403 */
+}
+
+/* get_N, @hdr/ddm.h:408-430: number of terms of the small-time and of the large-time series */
+static void ddm_get_n(double t, double ta, double eps, int *n_small, int *n_large)
+{
+    int nl = cvt_trunc(ceil(1.0 / (DDM_PI * sqrt(t)))), ns;                     /* :409 (t, not t / a^2) */
+    if (1.0 > (DDM_PI * ta) * eps) {                                            /* :410 */
+        double x = (log((DDM_PI * ta) * eps) * -2.0) / (DDM_PI2 * ta);          /* :412 */
+        int k = cvt_trunc(ceil(sqrt(x)));                                       /* :413 */
+        if (nl < k) nl = k;                                                     /* :414 std::max */
+    }
+    if (1.0 > (sqrt(ta * DDM_2PI) + sqrt(ta * DDM_2PI)) * eps) {                /* :418 */
+        double lg = log(sqrt(ta * DDM_2PI) * (eps + eps));                      /* :420 */
+        double t1 = sqrt((-2.0 * ta) * lg) + 2.0;                               /* :421 */
+        double t2 = sqrt(ta) + 1.0;                                             /* :422 */
+        ns = cvt_trunc(ceil(t2 < t1 ? t1 : t2));                                /* :423 std::max(t2, t1) */
+    } else
+        ns = 2;                                                                 /* :427 */
+    *n_small = ns;
+    *n_large = nl;
+}
+
+/* integral_v, @hdr/ddm.h:457-485, and g_no_var :433-454 (the sv == 0 branch; same steps, other factor) */
+static double ddm_integral_v(const ddm_par *q, double t, double zr)
+{
+    int no_var, ns, nl, use_small;
+    double ta, factor, eps;
+    if (0 >= t) return 0.0;                          /* :459 / :434 */
+    no_var = q->sv == 0;                             /* :463 */
+    ta = t / q->a2;                                  /* :469 / :439 */
+    factor = ddm_factor(q, t, zr, no_var);           /* :472 / :440 */
+    if (factor == 0) return 0.0;                     /* :474 / :444 */
+    eps = DDM_EPSILON / factor;                      /* :479 / :449 */
+    ddm_get_n(t, ta, eps, &ns, &nl);                 /* :480 / :450 */
+    use_small = ns < nl;                             /* :481 / :451 */
+    return ddm_series(ta, zr, use_small, use_small ? ns : nl) * factor; /* :484 / :453 */
+}
+
+/* integral_z :508-514 and integrate_v_over_zr :488-505 (midpoint rule over the start-point range) */
+static double ddm_integral_z(const ddm_par *q, double t)
+{
+    double lower, upper, width, step, sum = 0.0;
+    int n;
+    if (q->sz_eps > q->szr) return ddm_integral_v(q, t, q->zr);  /* :512 */
+    lower = q->zr - 0.5 * q->szr;                                /* :489 */
+    upper = 0.5 * q->szr + q->zr;                                /* :490 */
+    width = upper - lower;                                       /* :491 */
+    n = cvt_trunc(width / q->int_z);                             /* :492-494 */
+    if (n < 4) n = 4;
+    step = width / (double)n;                                    /* :495 */
+    for (double x = 0.5 * step + lower; upper > x; x += step)    /* :498 */
+        sum = ddm_integral_v(q, t, x) * step + sum;              /* :501 */
+    return sum / q->szr;                                         /* :504 */
+}
+
+/* integral_t0 :537-542 and integrate_z_over_t :517-534 (midpoint rule over the non-decision range) */
+static double ddm_integral_t0(const ddm_par *q, double t)
+{
+    double lower, upper, width, step, sum = 0.0;
+    int n;
+    if (q->st0_eps > q->st0) return ddm_integral_z(q, t);        /* :541 */
+    lower = t - q->st0 * 0.5;                                    /* :518 */
+    upper = 0.5 * q->st0 + t;                                    /* :519 */
+    width = upper - lower;                                       /* :521 */
+    n = cvt_trunc(width / q->int_t0);                            /* :522-523 */
+    if (n < 4) n = 4;
+    step = width / (double)n;                                    /* :524 */
+    for (double x = 0.5 * step + lower; upper > x; x += step)    /* :528 */
+        sum = ddm_integral_z(q, x) * step + sum;                 /* :530 */
+    return sum / q->st0;                                         /* :533 */
+}
+
+/* ddm_likelihood's per-cell body, @hdr/likelihood.h:140-158: set_parameters(matrix, !is_positive_drift[cell]),
+ * validate, then dddm (@hdr/ddm.h:552-560: g(rt) = integral_t0(rt - m_t_offset), :545-549) or 1e-10 for every trial. */
+int orc_ddm_cell(const double *P, int is_upper, const double *rt, int n, double *out)
+{
+    ddm_par q;
+    ddm_set(&q, P, !is_upper);
+    if (!ddm_valid(&q)) {
+        for (int i = 0; i < n; ++i) out[i] = FLOOR_; /* likelihood.h:158 */
+        return 0;
+    }
+    for (int i = 0; i < n; ++i) out[i] = ddm_integral_t0(&q, rt[i] - q.t_offset);
+    return 1;
+}
+
+/* densities of one cell's trials for either model family; returns validity */
+static int cell_density(const orc_model *m, const double *theta, int c, const double *u_st0, const double *rt, int n, double *out)
+{
+    double P[ORC_DDM_ROWS * 16];
+    orc_cell_params(m, theta, c, P);
+    if (m->type == ORC_MODEL_DDM) {
+        double col0[ORC_DDM_ROWS];
+        for (int r = 0; r < ORC_DDM_ROWS; ++r) col0[r] = P[r * m->n_acc]; /* the DDM reads column 0 only (@hdr/ddm.h:194-214) */
+        return orc_ddm_cell(col0, m->posdrift[c] != 0, rt, n, out);
+    }
+    return orc_lba_cell(P, m->n_acc, m->posdrift, u_st0, rt, n, out);
+}
+
+/* the log the sampler takes of one density: LBA plain (@hdr/likelihood.h:288), DDM floored at DBL_MIN (:303) */
+static double log_density(const orc_model *m, double x)
+{
+    if (m->type == ORC_MODEL_DDM) return log(x < DBL_MIN ? DBL_MIN : x); /* std::max(x, DBL_MIN): NaN stays NaN */
+    return log(x);
+}
+
 static void check_grouped(const orc_data *d)
 {
     for (int i = 1; i < d->n_trial; ++i)
@@ -162,15 +363,13 @@ static void check_grouped(const orc_data *d)
  * the st0 draws (all fixtures and benchmark models have st0 = 0 => t0 + 0*U = t0 exactly) */
 void orc_trial_logdens(const orc_model *m, const orc_data *d, const double *theta, double *out)
 {
-    double P[6 * 16];
     check_grouped(d);
     int i = 0;
     while (i < d->n_trial) {
         int c = d->cell[i], j = i;
         while (j < d->n_trial && d->cell[j] == c) ++j;
-        orc_cell_params(m, theta, c, P);
-        orc_lba_cell(P, m->n_acc, m->posdrift, NULL, d->rt + i, j - i, out + i);
-        for (int k = i; k < j; ++k) out[k] = log(out[k]);
+        cell_density(m, theta, c, NULL, d->rt + i, j - i, out + i);
+        for (int k = i; k < j; ++k) out[k] = log_density(m, out[k]);
         i = j;
     }
 }
@@ -180,9 +379,9 @@ void orc_trial_logdens(const orc_model *m, const orc_data *d, const double *thet
  * Draw order per call: n_acc uniforms per non-empty cell (@hdr/lba.h:117). */
 double orc_sumloglike(const orc_model *m, const orc_data *d, const double *theta, orc_rng *r, const orc_addr *base)
 {
-    double P[6 * 16], u[16], dens[4096], *buf = dens, out = 0.0;
-    int na = m->n_acc, i = 0;
-    if (r && r->mode == 0 && r->burn_static_ctor && !r->first_like_done) {
+    double u[16], dens[4096], *buf = dens, out = 0.0;
+    int na = m->n_acc, i = 0, is_lba = m->type != ORC_MODEL_DDM; /* the DDM code draws no uniforms */
+    if (is_lba && r && r->mode == 0 && r->burn_static_ctor && !r->first_like_done) {
         orc_addr a = {0};
         orc_uniform(r, &a);
         orc_uniform(r, &a);
@@ -191,9 +390,8 @@ double orc_sumloglike(const orc_model *m, const orc_data *d, const double *theta
     while (i < d->n_trial) {
         int c = d->cell[i], j = i;
         while (j < d->n_trial && d->cell[j] == c) ++j;
-        orc_cell_params(m, theta, c, P);
         for (int k = 0; k < na; ++k) {
-            if (r) {
+            if (r && is_lba) {
                 orc_addr a = *base;
                 a.purpose = ORC_U_ST0;
                 a.slot = (unsigned)(c * na + k);
@@ -202,8 +400,8 @@ double orc_sumloglike(const orc_model *m, const orc_data *d, const double *theta
                 u[k] = 0.0;
         }
         if (j - i > 4096) buf = (double *)malloc(sizeof(double) * (size_t)(j - i));
-        orc_lba_cell(P, na, m->posdrift, u, d->rt + i, j - i, buf);
-        for (int k = 0; k < j - i; ++k) out += log(buf[k]); /* :284-288 */
+        cell_density(m, theta, c, u, d->rt + i, j - i, buf);
+        for (int k = 0; k < j - i; ++k) out += log_density(m, buf[k]); /* :284-288, :298-303 */
         if (buf != dens) { free(buf); buf = dens; }
         i = j;
     }
@@ -214,7 +412,7 @@ double orc_sumloglike(const orc_model *m, const orc_data *d, const double *theta
  * fixture goldens `log_likelihoods[,1]` were produced by this path (R/phi.R:176-177). */
 double orc_sumloglike_rinit(const orc_model *m, const orc_data *d, const double *theta)
 {
-    double P[6 * 16], out = 0.0;
+    double out = 0.0;
     int i = 0;
     check_grouped(d);
     while (i < d->n_trial) {
@@ -222,8 +420,7 @@ double orc_sumloglike_rinit(const orc_model *m, const orc_data *d, const double 
         double s = 0.0;
         while (j < d->n_trial && d->cell[j] == c) ++j;
         double *buf = (double *)malloc(sizeof(double) * (size_t)(j - i));
-        orc_cell_params(m, theta, c, P);
-        orc_lba_cell(P, m->n_acc, m->posdrift, NULL, d->rt + i, j - i, buf);
+        cell_density(m, theta, c, NULL, d->rt + i, j - i, buf);
         int any = 0;
         for (int k = 0; k < j - i; ++k) if (buf[k] <= 0) any = 1;
         for (int k = 0; k < j - i; ++k) {

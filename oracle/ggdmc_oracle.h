@@ -49,11 +49,18 @@ typedef struct {
     long rec_n, rec_cap;
 } orc_rng;
 
+/* likelihood_class::resolve_string codes (@hdr/likelihood.h:279): "lba" and "fastdm" */
+enum { ORC_MODEL_LBA = 0, ORC_MODEL_DDM = 1 };
+#define ORC_LBA_ROWS 6  /* A, B, mean_v, sd_v, st0, t0 */
+#define ORC_DDM_ROWS 10 /* a, d, precision, s, st0, sv, sz, t0, v, z (alphabetical, like every core-parameter table) */
+
 typedef struct {
     int n_acc, n_cell, npar;
-    const int *param_src;          /* [n_cell][6][n_acc]; >=0: theta index, <0: const_val[-1-k] */
+    const int *param_src;          /* [n_cell][rows][n_acc]; >=0: theta index, <0: const_val[-1-k]; rows = 6 (LBA) or 10 (DDM) */
     const double *const_val;
-    const unsigned char *posdrift; /* [n_acc] */
+    const unsigned char *posdrift; /* LBA: [n_acc] is_positive_drift.  DDM: [n_cell], non-zero = the cell's response is
+                                      the UPPER boundary (the same dmi@is_positive_drift slot, @hdr/likelihood.h:142) */
+    int type;                      /* ORC_MODEL_* */
 } orc_model;
 
 typedef struct {
@@ -103,6 +110,11 @@ void orc_trial_logdens(const orc_model *m, const orc_data *d, const double *thet
 double orc_sumloglike(const orc_model *m, const orc_data *d, const double *theta, orc_rng *r, const orc_addr *base);
 /* R init path (R/phi.R:3-13): densities <= 0 floored at DBL_EPSILON before the log */
 double orc_sumloglike_rinit(const orc_model *m, const orc_data *d, const double *theta);
+
+/* --- DDM ("fastdm") density (@hdr/ddm.h as compiled into src/de.o; @hdr/likelihood.h:129-161, 295-305) ----------- */
+/* One cell: P = column 0 of the 10 rows (a, d, precision, s, st0, sv, sz, t0, v, z); returns
+ * validate_parameters(); out[i] = g(rt[i]) if valid, else 1e-10 (likelihood.h:158). */
+int orc_ddm_cell(const double *P, int is_upper, const double *rt, int n, double *out);
 
 /* --- priors (@hdr/prior.h, @hdr/tnorm.h) ------------------------------------------------------ */
 double orc_tnorm_d(double x, double mean, double sd, double lower, double upper, int log_p);

@@ -19,7 +19,13 @@
 // ---- opaque storage with the reference's class names (so the symbols in de.o resolve) -------------
 class theta_class { public: alignas(16) unsigned char raw[2592]; };                         // theta_phi: 2592 B
 namespace prior { class prior_class { public: alignas(16) unsigned char raw[592]; }; }      // 592 B
-namespace likelihood { class likelihood_class { public: alignas(16) unsigned char raw[416]; }; } // 416 B
+namespace likelihood {
+class likelihood_class { // 416 B
+  public:
+    alignas(16) unsigned char raw[416];
+    void ddm_likelihood(const std::vector<double> &theta, bool debug); // @hdr/likelihood.h:129-161, body in de.o (weak symbol)
+};
+} // namespace likelihood
 namespace design { class design_class { public: alignas(16) unsigned char raw[448]; }; }    // 448 B
 namespace tnorm {
 struct tnorm_class { double m_mean, m_sd, m_lower, m_upper; bool m_lower_tail, m_log_p; double m_denom, m_log_denom; };
@@ -93,13 +99,21 @@ typedef std::vector<std::string> VS;
 typedef std::vector<double> VD;
 typedef std::vector<unsigned> VU;
 
+// 0 = "lba" (6 core rows, posdrift per accumulator), 1 = "fastdm" (10 core rows, posdrift per cell = upper-boundary flag);
+// set with ref2_set_model_type before building objects
+int g_model_type = 0;
+int core_rows() { return g_model_type == 1 ? 10 : 6; }
+const char *model_str() { return g_model_type == 1 ? "fastdm" : "lba"; }
+
 design::design_class *build_design(int n_acc, int n_cell, const int *param_src, const double *const_val)
 {
+    const int rows = core_rows();
     auto *d = new design::design_class();
     std::memset(d->raw, 0, sizeof(d->raw));
     unsigned char *r = d->raw;
-    *reinterpret_cast<size_t *>(r + 0) = 6;                                              // m_n_core_parameter @0
-    put<VS>(r, 8, VS{"A", "B", "mean_v", "sd_v", "st0", "t0"});                          // m_core_parameter_names @8
+    *reinterpret_cast<size_t *>(r + 0) = (size_t)rows;                                   // m_n_core_parameter @0
+    put<VS>(r, 8, g_model_type == 1 ? VS{"a", "d", "precision", "s", "st0", "sv", "sz", "t0", "v", "z"}
+                                    : VS{"A", "B", "mean_v", "sd_v", "st0", "t0"});      // m_core_parameter_names @8
     put<VS>(r, 32, VS((size_t)n_acc, "acc"));                                            // m_accumulator_names @32
     put<VS>(r, 56, VS((size_t)n_cell, "cell"));                                          // m_cell_names @56
     put<VS>(r, 80);                                                                      // m_parameter_x_condition_names @80
@@ -113,15 +127,15 @@ design::design_class *build_design(int n_acc, int n_cell, const int *param_src, 
     put<std::vector<VU>>(r, 248);                                                        // m_node_1_index @248
     put<VS>(r, 272);                                                                     // m_free_parameter_names @272
     *reinterpret_cast<size_t *>(r + 296) = 0;                                            // m_n_free_parameter @296
-    put<std::string>(r, 304, "lba");                                                     // m_model_str @304
+    put<std::string>(r, 304, model_str());                                               // m_model_str @304
     typedef std::vector<std::vector<std::vector<VU>>> Map4;
     put<Map4>(r, 336);                                                                   // m_tmp_param_map @336
-    Map4 pm((size_t)n_acc, std::vector<std::vector<VU>>((size_t)n_cell, std::vector<VU>(6, VU(2, 0u))));
-    std::vector<std::vector<VD>> mat((size_t)n_cell, std::vector<VD>(6, VD((size_t)n_acc, 0.0)));
+    Map4 pm((size_t)n_acc, std::vector<std::vector<VU>>((size_t)n_cell, std::vector<VU>((size_t)rows, VU(2, 0u))));
+    std::vector<std::vector<VD>> mat((size_t)n_cell, std::vector<VD>((size_t)rows, VD((size_t)n_acc, 0.0)));
     for (int c = 0; c < n_cell; ++c)
-        for (int row = 0; row < 6; ++row)
+        for (int row = 0; row < rows; ++row)
             for (int j = 0; j < n_acc; ++j) {
-                int s = param_src[((size_t)c * 6 + row) * n_acc + j];
+                int s = param_src[((size_t)c * rows + row) * n_acc + j];
                 if (s >= 0) {
                     pm[j][c][row][0] = (unsigned)s; // [0] = index into theta, [1] = is_free (design_light.h:323, 329-330)
                     pm[j][c][row][1] = 1u;
@@ -144,14 +158,15 @@ likelihood::likelihood_class *build_like(design::design_class *d, int n_acc, int
     put<std::shared_ptr<design::design_class>>(r, 0, d, [](design::design_class *) {});   // m_model @0
     std::vector<VD> rts((size_t)n_cell);
     for (int i = 0; i < n_trial; ++i) rts[cell[i]].push_back(rt[i]);
-    std::vector<bool> empty((size_t)n_cell), pd((size_t)n_acc);
+    const int n_pd = g_model_type == 1 ? n_cell : n_acc; // the DDM path indexes m_is_positive_drift by CELL (@hdr/likelihood.h:142)
+    std::vector<bool> empty((size_t)n_cell), pd((size_t)n_pd);
     for (int c = 0; c < n_cell; ++c) empty[c] = rts[c].empty();
-    for (int j = 0; j < n_acc; ++j) pd[j] = posdrift[j] != 0;
+    for (int j = 0; j < n_pd; ++j) pd[j] = posdrift[j] != 0;
     put<std::vector<VD>>(r, 16, rts);                                                     // m_data_rt @16
     put<std::vector<VD>>(r, 40, rts);                                                     // m_rt @40
     put<std::vector<VD>>(r, 64, std::vector<VD>((size_t)n_cell));                         // m_density @64
     put<VS>(r, 88);                                                                       // m_data_cell_names @88
-    put<std::string>(r, 112, "lba");                                                      // m_model_str @112
+    put<std::string>(r, 112, model_str());                                                // m_model_str @112
     put<std::vector<bool>>(r, 144, empty);                                                // m_is_empty_cell @144
     put<std::vector<bool>>(r, 184, pd);                                                   // m_is_positive_drift @184
     set_mat(r + 224, 0, 0, false, amalloc(1));                                            // m_theta_data @224
@@ -286,6 +301,26 @@ void read_back(const ThetaBuf &b, double *theta, double *lp, double *ll, double 
 } // namespace
 
 extern "C" {
+
+void ref2_set_model_type(int type) { g_model_type = type == 1 ? 1 : 0; }
+
+// likelihood_class::ddm_likelihood of de.o (@hdr/likelihood.h:129-161) on a hand-built "fastdm" likelihood object:
+// design_class::set_parameter_values, ddm_class::set_parameters / validate_parameters / dddm all run from de.o.
+// Trials must be grouped by ascending cell; out[i] = m_density[cell][k] of trial i (1e-10 for invalid cells).
+void ref2_ddm_density(int n_acc, int n_cell, const int *param_src, const double *const_val, const unsigned char *is_upper,
+                      const double *rt, const unsigned short *cell, int n_trial, const double *theta, int npar, double *out)
+{
+    const int saved = g_model_type;
+    g_model_type = 1;
+    design::design_class *d = build_design(n_acc, n_cell, param_src, const_val);
+    likelihood::likelihood_class *l = build_like(d, n_acc, n_cell, is_upper, rt, cell, n_trial);
+    g_model_type = saved;
+    l->ddm_likelihood(std::vector<double>(theta, theta + npar), false);
+    const std::vector<VD> &dens = *reinterpret_cast<std::vector<VD> *>(l->raw + 64); // m_density @64
+    int i = 0;
+    for (int c = 0; c < n_cell; ++c)
+        for (double x : dens[c]) out[i++] = x;
+}
 
 // One sweep of the reference's 1-level sampler on chains theta[nchain][npar] (updated in place):
 // kind 0 = de_class::crossover (src/de.cpp:111-155), kind 1 = de_class::migration (:157-199);
