@@ -24,6 +24,8 @@ c_u64p = C.POINTER(C.c_uint64)
 
 OK, ERR_ARG, ERR_CUDA, ERR_COMM, ERR_CHAINS = 0, 1, 2, 3, 4
 SCHEDULE_REFERENCE, SCHEDULE_PARALLEL, SCHEDULE_SIMULTANEOUS = 0, 1, 2
+MODEL_LBA, MODEL_DDM = 0, 1  # enum ggdmc_model_type
+MODEL_TYPES = {"lba": MODEL_LBA, "fastdm": MODEL_DDM}  # model@type strings (@hdr/likelihood.h:279)
 
 
 class GgdmcError(RuntimeError):
@@ -34,7 +36,7 @@ class GgdmcError(RuntimeError):
 
 class ModelT(C.Structure):
     _fields_ = [("n_acc", C.c_int32), ("n_cell", C.c_int32), ("npar", C.c_int32), ("n_const", C.c_int32),
-                ("param_src", c_i32p), ("const_val", c_dp), ("posdrift", c_u8p)]
+                ("param_src", c_i32p), ("const_val", c_dp), ("posdrift", c_u8p), ("type", C.c_int32)]
 
 
 class TrialsT(C.Structure):

@@ -183,7 +183,7 @@ def _posterior(out: E.PopSamples, r: int, pnames: List[str], thin: int) -> Poste
 def _flatten_dmi(dmi):
     model = slot(dmi, "model")
     mtype = _strs(slot(model, "type"))[0]
-    if mtype != "lba":
+    if mtype not in B.MODEL_TYPES:  # "lba" -> lba_likelihood, "fastdm" -> ddm_likelihood (@hdr/likelihood.h:279-305)
         raise B.GgdmcError(B.ERR_ARG, "Undefined model type")  # @hdr/likelihood.h:312
     ct = build_cell_table(model, slot(dmi, "node_1_index"), slot(dmi, "is_positive_drift"))
     return ct, flatten_data(slot(dmi, "data"), ct.cell_names)

@@ -1,0 +1,183 @@
+// ggdmc_b200 -- DDM ("fastdm") first-passage density of one trial.
+//
+// Replaces ddm::ddm_class::{set_parameters, set_precision, validate_parameters, g -> integral_t0 ->
+// integral_z -> integral_v -> g_no_var, get_N, compute_g_factor, compute_g_series} (@hdr/ddm.h:120-138,
+// 187-309, 344-549; anonymous namespace, compiled into src/de.o, decoded from its object code) and the
+// per-cell body of likelihood_class::ddm_likelihood (@hdr/likelihood.h:140-158).
+//
+// The reference keeps one ddm_class object, resets its 32 members for every cell of every likelihood
+// call and walks the cell's trials.  Here everything that does not depend on the trial -- the scaled
+// parameters, their squares, the integration step widths and thresholds derived from `precision`, and
+// the verdict of validate_parameters -- is computed once per (chain, cell) into a shared-memory table
+// (DdmCell); a trial gathers its cell's row and evaluates
+//     g(rt) = integral over the non-decision range st0 ( integral over the start-point range sz (
+//             closed-form integral over drift variability sv of the lower-boundary density ) )
+// with the reference's midpoint rules and its choice between the small-time and the large-time series
+// (Navarro & Fuss 2009; term counts from get_N).  Operation order follows the object code; what differs
+// from the CPU is only the last-ulp behaviour of exp / sin / log / pow and FMA contraction.
+//
+// The header also compiles as plain C++ (GG_HD empty) so tests can check it on the host against the oracle.
+#pragma once
+#include "gg_math.cuh"
+#include <stdint.h>
+
+// the series evaluation is called from inside both midpoint rules: one out-of-line copy instead of four inlined ones
+#ifdef __CUDACC__
+#define GG_DDM_FN __device__ __noinline__
+#else
+#define GG_DDM_FN inline
+#endif
+
+namespace gg {
+
+constexpr int kDdmRows = 10; // a, d, precision, s, st0, sv, sz, t0, v, z (alphabetical core names, like the LBA's six)
+constexpr int kLbaRows = 6;
+
+struct DdmCell {
+    double a, v, sv, st0, zr, szr, t_offset; // m_a, m_v, m_sv, m_st0, m_zr, m_szr, m_t_offset
+    double int_t0, int_z, var_eps;           // TUNE_INT_T0, TUNE_INT_Z, TUNE_SZ_EPSILON == TUNE_ST0_EPSILON
+    double a2, v2, sv2;                      // @hdr/ddm.h:223-225
+    int valid, no_var;                       // validate_parameters(); sv == 0
+    int pad[4];
+};
+static_assert(sizeof(DdmCell) == 128, "DdmCell is two 64-byte lines");
+
+constexpr double kDdmEpsilon = 1e-6;            // ddm::EPSILON, de.o .rodata+0x1b8
+constexpr double kPi = 3.141592653589793;       // .rodata+0xec8
+constexpr double kTwoPi = 6.283185307179586;    // .rodata+0xec0
+constexpr double kPiSq = 9.869604401089358;     // m_pi2, @hdr/ddm.h:141
+
+// the object code converts with cvttsd2si: NaN and out-of-range values give INT_MIN
+GG_HD int ddm_trunc(double x) { return (x >= -2147483648.0 && x < 2147483648.0) ? (int)x : (-2147483647 - 1); }
+
+// set_parameters(matrix, is_lower) @hdr/ddm.h:187-226 + set_precision :120-138 + validate_parameters :229-309.
+// P = column 0 of the ten rows; is_upper = dmi@is_positive_drift of the cell (@hdr/likelihood.h:142 passes its negation).
+GG_HD void ddmcell_build(DdmCell &q, const double *P, bool is_upper)
+{
+    const double s = P[3], scale = (1.0 != s) ? 1.0 / s : 1.0, prec = P[2]; // :194-195
+    q.st0 = P[4];
+    q.a = P[0] * scale;                               // :203
+    q.sv = P[5] * scale;                              // :204
+    q.v = is_upper ? (-P[8]) * scale : P[8] * scale;  // :205-206
+    q.t_offset = 0.5 * P[4] + P[7];                   // :208
+    const double zr0 = P[9] / q.a;                    // :216
+    q.zr = is_upper ? 1.0 - zr0 : zr0;                // :217
+    q.szr = P[6] / q.a;                               // :218
+    q.int_t0 = exp(prec * -1.03758) * 0.089045;       // :130
+    q.int_z = exp(prec * -1.022373) * 0.508061;       // :131
+    q.var_eps = pow(10.0, -(2.0 + prec));             // :136-137
+    q.a2 = q.a * q.a;
+    q.v2 = q.v * q.v;
+    q.sv2 = q.sv * q.sv;
+    q.no_var = q.sv == 0;
+    bool ok = true; // comparisons are false on NaN, like the reference's
+    if (q.a <= 0) ok = false;                         // :232
+    if (q.szr < 0 || q.szr > 1.0) ok = false;         // :240
+    if (q.st0 < 0) ok = false;                        // :250
+    if (q.sv < 0) ok = false;                         // :259
+    if (q.t_offset < 0) ok = false;                   // :268
+    if (q.zr - 0.5 * q.szr <= 0) ok = false;          // :278
+    if (q.zr + 0.5 * q.szr >= 1.0) ok = false;        // :288
+    if (s <= 0) ok = false;                           // :298
+    q.valid = ok;
+    q.pad[0] = q.pad[1] = q.pad[2] = q.pad[3] = 0;
+}
+
+// compute_g_series, @hdr/ddm.h:344-379
+GG_HD double ddm_series(double ta, double zr, bool use_small, int N)
+{
+    double sum = 0.0;
+    if (use_small) {
+        const double t3 = ta * ta * ta;
+        const double norm = 1.0 / sqrt(t3 * kTwoPi);
+        const double two_ta = ta + ta;
+        const int hi = N / 2, lo = -(N / 2);
+        for (int i = lo; i <= hi; ++i) {
+            const double d = ((double)i + (double)i) + zr;
+            sum = exp((-d * d) / two_ta) * d + sum;
+        }
+        return sum * norm;
+    }
+    for (int i = 1; i <= N; ++i) {
+        const double d = kPi * (double)i;
+        sum = (double)i * (exp(-0.5 * d * d * ta) * sin(d * zr)) + sum;
+    }
+    return kPi * sum;
+}
+
+// compute_g_factor, @hdr/ddm.h:383-405
+GG_HD double ddm_factor(const DdmCell &q, double t, double zr)
+{
+    double f;
+    if (q.no_var) {
+        f = exp((-q.a * zr) * q.v - (0.5 * q.v2) * t) / q.a2;
+    } else {
+        const double denom = 1.0 + q.sv2 * t;
+        const double e = (-0.5 * ((q.v2 * t + (q.a * (q.v + q.v)) * zr) - ((q.a2 * zr) * zr) * q.sv2)) / denom;
+        f = exp(e) / (q.a2 * sqrt(denom));
+    }
+    return isfinite(f) ? f : 0.0;
+}
+
+// integral_v (@hdr/ddm.h:457-485) and g_no_var (:433-454): the two share every step but the factor
+GG_DDM_FN double ddm_integral_v(const DdmCell &q, double t, double zr)
+{
+    if (0 >= t) return 0.0;
+    const double ta = t / q.a2;
+    const double factor = ddm_factor(q, t, zr);
+    if (factor == 0) return 0.0;
+    const double eps = kDdmEpsilon / factor;
+    // get_N, :408-430
+    int nl = ddm_trunc(ceil(1.0 / (kPi * sqrt(t))));
+    const double pe = (kPi * ta) * eps;
+    if (1.0 > pe) {
+        const int k = ddm_trunc(ceil(sqrt((log(pe) * -2.0) / (kPiSq * ta))));
+        if (nl < k) nl = k;
+    }
+    int ns = 2;
+    const double rt2 = sqrt(ta * kTwoPi);
+    if (1.0 > (rt2 + rt2) * eps) {
+        const double lg = log(rt2 * (eps + eps));
+        const double t1 = sqrt((-2.0 * ta) * lg) + 2.0;
+        const double t2 = sqrt(ta) + 1.0;
+        ns = ddm_trunc(ceil(t2 < t1 ? t1 : t2));
+    }
+    const bool use_small = ns < nl;
+    return ddm_series(ta, zr, use_small, use_small ? ns : nl) * factor;
+}
+
+// integral_z (@hdr/ddm.h:508-514) with integrate_v_over_zr (:488-505)
+GG_HD double ddm_integral_z(const DdmCell &q, double t)
+{
+    if (q.var_eps > q.szr) return ddm_integral_v(q, t, q.zr);
+    const double lower = q.zr - 0.5 * q.szr, upper = 0.5 * q.szr + q.zr, width = upper - lower;
+    int n = ddm_trunc(width / q.int_z);
+    if (n < 4) n = 4;
+    const double step = width / (double)n;
+    double sum = 0.0;
+    for (double x = 0.5 * step + lower; upper > x; x += step) sum = ddm_integral_v(q, t, x) * step + sum;
+    return sum / q.szr;
+}
+
+// g (@hdr/ddm.h:545-549) -> integral_t0 (:537-542) with integrate_z_over_t (:517-534)
+GG_HD double ddm_g(const DdmCell &q, double rt)
+{
+    const double t = rt - q.t_offset;
+    if (q.var_eps > q.st0) return ddm_integral_z(q, t);
+    const double lower = t - q.st0 * 0.5, upper = 0.5 * q.st0 + t, width = upper - lower;
+    int n = ddm_trunc(width / q.int_t0);
+    if (n < 4) n = 4;
+    const double step = width / (double)n;
+    double sum = 0.0;
+    for (double x = 0.5 * step + lower; upper > x; x += step) sum = ddm_integral_z(q, x) * step + sum;
+    return sum / q.st0;
+}
+
+// density of one trial as likelihood_class::ddm_likelihood stores it: 1e-10 for every trial of an invalid cell
+// (@hdr/likelihood.h:158), else dddm (@hdr/ddm.h:552-560)
+GG_HD double ddm_density(const DdmCell &q, double rt) { return q.valid ? ddm_g(q, rt) : kFloor; }
+
+// what sumloglike takes the log of: std::max(density, DBL_MIN) (@hdr/likelihood.h:303); NaN stays NaN
+GG_HD double ddm_floor(double x) { return x < DBL_MIN ? DBL_MIN : x; }
+
+} // namespace gg

@@ -229,11 +229,14 @@ struct ModelDev {
     DBuf<double> const_val;
     DBuf<uint8_t> posdrift;
     DevModel d{};
+    int type = GGDMC_MODEL_LBA; // enum ggdmc_model_type: which likelihood kernels the host launches
     void upload(const ggdmc_model_t *m)
     {
         require(m && m->n_acc >= 1 && m->n_acc <= 16 && m->n_cell >= 1 && m->npar >= 1, "bad model dimensions");
         require(m->n_cell < 65535, "too many cells");
-        const size_t n = (size_t)m->n_cell * 6 * m->n_acc;
+        require(m->type == GGDMC_MODEL_LBA || m->type == GGDMC_MODEL_DDM, "Undefined model type"); // @hdr/likelihood.h:312
+        const bool ddm = m->type == GGDMC_MODEL_DDM;
+        const size_t n = (size_t)m->n_cell * (ddm ? GGDMC_DDM_ROWS : GGDMC_LBA_ROWS) * m->n_acc;
         for (size_t i = 0; i < n; ++i) {
             const int s = m->param_src[i];
             require(s >= 0 ? s < m->npar : (-1 - s) < m->n_const, "param_src out of range");
@@ -242,9 +245,10 @@ struct ModelDev {
         std::vector<double> cv(m->const_val, m->const_val + std::max(m->n_const, 0));
         if (cv.empty()) cv.push_back(0.0);
         const_val.upload(cv);
-        posdrift.upload(m->posdrift, m->n_acc);
+        posdrift.upload(m->posdrift, ddm ? m->n_cell : m->n_acc); // the DDM path indexes it by cell (@hdr/likelihood.h:142)
         d.n_acc = m->n_acc; d.n_cell = m->n_cell; d.npar = m->npar; d.n_const = m->n_const;
         d.param_src = param_src.p; d.const_val = const_val.p; d.posdrift = posdrift.p;
+        type = m->type;
     }
 };
 
@@ -500,9 +504,35 @@ void launch_like_n(const Level &L, const DevModel &M, const TrialData &T, const 
     }
 }
 
-void launch_like(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
+// model type "fastdm": same grid and arguments as k_like; 128 threads x 4 blocks/SM (the series and midpoint-rule
+// loops want registers, not occupancy)
+void launch_like_ddm(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
+                     double *ll_part, cudaStream_t st, const int *prio)
+{
+    constexpr int BLOCK = 128, MINB = 4;
+    const int per_pop = step >= 0 ? 1 : (half < 0 ? L.nchain : (L.nchain + 1) / 2);
+    dim3 grid(L.npop * per_pop, T.nsplit);
+    const size_t sm = ((size_t)M.n_cell * sizeof(DdmCell) + (size_t)(BLOCK / 32) * 8 + 15) & ~(size_t)15;
+    require(sm <= 220 * 1024, "cell table does not fit in shared memory");
+    allow_smem(k_like_ddm<BLOCK, MINB>, sm);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    at[0].val.priority = prio ? *prio : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = prio ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_like_ddm<BLOCK, MINB>, L, M, T, d_iter, sweep, step, half, ll_part));
+}
+
+void launch_like(const Level &L, const ModelDev &MD, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
                  double *ll_part, cudaStream_t st, const int *prio = nullptr)
 {
+    const DevModel &M = MD.d;
+    if (MD.type == GGDMC_MODEL_DDM) {
+        launch_like_ddm(L, M, T, d_iter, sweep, step, half, ll_part, st, prio);
+        return;
+    }
     switch (M.n_acc) {
     case 2: launch_like_n<2>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
     case 3: launch_like_n<3>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
@@ -859,7 +889,7 @@ struct ggdmc_engine {
             // ramp / drain fall under another group's likelihood
             int prio = std::min(prio_lo, prio_hi + 1 + std::max(half, 0) * (int)groups.size() + G.index);
             const bool staged = hi_small && groups.size() > 1 && stream_tag(stream) != 1;
-            TR("k_like", stream, launch_like(L, model.d, G.T, d_iter.p, sweep, step, half, G.ll_part, stream, staged ? &prio : nullptr));
+            TR("k_like", stream, launch_like(L, model, G.T, d_iter.p, sweep, step, half, G.ll_part, stream, staged ? &prio : nullptr));
             return;
         }
         if (prof_used + 2 > prof_ev.size()) {
@@ -870,7 +900,7 @@ struct ggdmc_engine {
             }
         }
         CUDA_CHECK(cudaEventRecord(prof_ev[prof_used], stream));
-        launch_like(L, model.d, G.T, d_iter.p, sweep, step, half, G.ll_part, stream);
+        launch_like(L, model, G.T, d_iter.p, sweep, step, half, G.ll_part, stream);
         CUDA_CHECK(cudaEventRecord(prof_ev[prof_used + 1], stream));
         prof_used += 2;
     }
@@ -1282,9 +1312,9 @@ int ggdmc_b200_engine_time_likelihood(ggdmc_engine_t *engine, int32_t reps, floa
     k_sweep_begin<<<L.npop, 128, (size_t)2 * e.C * sizeof(int), e.stream>>>(L, e.d_iter.p, 0, 1, -1);
     k_propose<kProposeWarps><<<(L.npop * e.C + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, (size_t)kProposeWarps * e.D * 8, e.stream>>>(L, e.d_iter.p, 0, -1, -1);
     L.mig_prob = saved;
-    launch_like(L, e.model.d, e.trials.d, e.d_iter.p, 0, -1, -1, e.ll_part.p, e.stream); // warm-up
+    launch_like(L, e.model, e.trials.d, e.d_iter.p, 0, -1, -1, e.ll_part.p, e.stream); // warm-up
     CUDA_CHECK(cudaEventRecord(e.ev0, e.stream));
-    for (int i = 0; i < reps; ++i) launch_like(L, e.model.d, e.trials.d, e.d_iter.p, 0, -1, -1, e.ll_part.p, e.stream);
+    for (int i = 0; i < reps; ++i) launch_like(L, e.model, e.trials.d, e.d_iter.p, 0, -1, -1, e.ll_part.p, e.stream);
     CUDA_CHECK(cudaEventRecord(e.ev1, e.stream));
     CUDA_CHECK(cudaStreamSynchronize(e.stream));
     e.launches += 3 + reps;
@@ -1299,7 +1329,7 @@ int ggdmc_b200_engine_time_likelihood(ggdmc_engine_t *engine, int32_t reps, floa
         TrialData T = e.trials.d;
         T.btrace = bt.p + 2;
         k_stamp<<<1, 1, 0, e.stream>>>(bt.p);
-        launch_like(L, e.model.d, T, e.d_iter.p, 0, -1, -1, e.ll_part.p, e.stream);
+        launch_like(L, e.model, T, e.d_iter.p, 0, -1, -1, e.ll_part.p, e.stream);
         k_stamp<<<1, 1, 0, e.stream>>>(bt.p + 1);
         CUDA_CHECK(cudaStreamSynchronize(e.stream));
         std::vector<unsigned long long> h(5 * nblk + 2);
@@ -1430,11 +1460,16 @@ int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *t
     DBuf<double> d_theta, d_out;
     d_theta.upload(theta, (size_t)n_theta * model->npar);
     d_out.alloc((size_t)n_theta * std::max(ntr, 1));
-    const size_t sm = ((size_t)M.d.n_cell * M.d.n_acc * sizeof(CellAcc) + (size_t)M.d.n_cell * (1 + M.d.n_acc) + 15) & ~(size_t)15;
-    allow_smem(k_trial_logdens<128>, sm);
+    const bool ddm = M.type == GGDMC_MODEL_DDM;
+    const size_t sm = ddm ? (size_t)M.d.n_cell * sizeof(DdmCell)
+                          : ((size_t)M.d.n_cell * M.d.n_acc * sizeof(CellAcc) + (size_t)M.d.n_cell * (1 + M.d.n_acc) + 15) & ~(size_t)15;
+    require(sm <= 220 * 1024, "cell table does not fit in shared memory");
+    if (ddm) allow_smem(k_trial_logdens_ddm<128>, sm);
+    else allow_smem(k_trial_logdens<128>, sm);
     if (ntr > 0) {
         dim3 grid(n_theta, std::min(64, (ntr + 127) / 128));
-        k_trial_logdens<128><<<grid, 128, sm>>>(M.d, T.rt.p, T.cell.p, ntr, d_theta.p, d_out.p);
+        if (ddm) k_trial_logdens_ddm<128><<<grid, 128, sm>>>(M.d, T.rt.p, T.cell.p, ntr, d_theta.p, d_out.p);
+        else k_trial_logdens<128><<<grid, 128, sm>>>(M.d, T.rt.p, T.cell.p, ntr, d_theta.p, d_out.p);
         CUDA_CHECK(cudaGetLastError());
         std::vector<double> h((size_t)n_theta * ntr);
         CUDA_CHECK(cudaMemcpy(h.data(), d_out.p, h.size() * 8, cudaMemcpyDeviceToHost));
@@ -1471,7 +1506,7 @@ void sumloglike_impl(const ggdmc_model_t *model, const ggdmc_trials_t *trials, c
     Level L{};
     L.npop = S; L.nchain = n_theta; L.npar = D; L.n_rep = 1; L.prop = d_theta.p; L.target = d_target.p;
     L.mode = d_mode.p; L.seed = d_seed.p;
-    launch_like(L, M.d, T.d, d_iter.p, 0, -1, -1, d_part.p, 0);
+    launch_like(L, M, T.d, d_iter.p, 0, -1, -1, d_part.p, 0);
     std::vector<double> h(n * T.d.nsplit);
     CUDA_CHECK(cudaMemcpy(h.data(), d_part.p, h.size() * 8, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; ++i) {

@@ -6,6 +6,8 @@
 //                       (src/de.cpp:119-141, 164-184, 394-426, 488-518, 575-603, 627-652)
 //   K2 k_like         : LBA sum-log-likelihood of every proposal (the FP64 hot kernel)
 //                       (@hdr/likelihood.h:73-108, 272-292 + @hdr/lba.h)
+//      k_like_ddm     : the same launch for model type "fastdm": DDM sum-log-likelihood
+//                       (@hdr/likelihood.h:129-161, 295-305 + @hdr/ddm.h)
 //   K3 k_accept       : Metropolis accept / commit (src/de.cpp:81-108); in a hierarchy also the log prior of the
 //                       proposal under its phi chain (:599-604, 646-653)
 //   K4 k_phi_half     : one phi half-sweep in one launch: proposal, hyper-likelihood partial sums over the local
@@ -24,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "gg_lba.cuh"
+#include "gg_ddm.cuh"
 #include "gg_rng.cuh"
 
 namespace gg {
@@ -32,7 +35,7 @@ struct DevModel {
     int n_acc, n_cell, npar, n_const;
     const int *param_src;
     const double *const_val;
-    const uint8_t *posdrift;
+    const uint8_t *posdrift; // LBA: [n_acc].  DDM: [n_cell], non-zero = upper-boundary response (the host picks the kernels by model type)
 };
 
 struct DevPrior {
@@ -633,6 +636,56 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
     }
 }
 
+// DDM twin of like_one (model type "fastdm"): sum over one trial chunk of log(max(g(rt), DBL_MIN))
+// (@hdr/likelihood.h:295-305) for ONE proposal.  The per-(chain, cell) table holds what ddm_class::set_parameters,
+// set_precision and validate_parameters produce (gg_ddm.cuh); a thread evaluates one trial at a time -- the series
+// length and the two midpoint rules make the cost of a trial data dependent, so trials are dealt round-robin.
+template <int BLOCK>
+__device__ __forceinline__ void like_one_ddm(const Level &L, const DevModel &M, const TrialData &T, int p, int chain, int split,
+                                             double *ll_part, unsigned char *sm_raw)
+{
+    const int C = L.nchain, D = L.npar, na = M.n_acc;
+    const int s = p / L.n_rep;
+    const int ntr = T.count[s];
+    const int64_t t_off = T.offset[s];
+    const int t_begin = split * T.chunk;
+    double *part = ll_part + ((size_t)p * C + chain) * T.nsplit + split;
+    DdmCell *ent = reinterpret_cast<DdmCell *>(sm_raw);
+    double *red = reinterpret_cast<double *>(ent + M.n_cell);
+    const double *th = L.prop + ((size_t)p * C + chain) * D;
+    for (int c = threadIdx.x; c < M.n_cell; c += BLOCK) {
+        const int *src = M.param_src + (size_t)c * kDdmRows * na; // column 0 of every row (@hdr/ddm.h:194-214)
+        double P[kDdmRows];
+#pragma unroll
+        for (int r = 0; r < kDdmRows; ++r) {
+            const int k = src[r * na];
+            P[r] = k >= 0 ? th[k] : M.const_val[-1 - k];
+        }
+        ddmcell_build(ent[c], P, M.posdrift[c] != 0);
+    }
+    __syncthreads();
+    if (t_begin >= ntr) {
+        if (threadIdx.x == 0) *part = 0.0;
+        return;
+    }
+    const int t_end = min(ntr, t_begin + T.chunk);
+    const double *rt = T.rt + t_off;
+    const uint16_t *cl = T.cell + t_off;
+    LogProd acc;
+    acc.init();
+    const double zf = T.zero_floor;
+    for (int t = t_begin + threadIdx.x; t < t_end; t += BLOCK) {
+        double pdf = ddm_density(ent[cl[t]], rt[t]);
+        if (zf > 0.0 && pdf <= 0.0) pdf = zf;
+        acc.mul(ddm_floor(pdf));
+    }
+    double v = block_sum<BLOCK>(acc.value(), red);
+    if (threadIdx.x == 0) {
+        *part = v;
+        if (T.counter) atomicAdd(T.counter, (unsigned long long)(t_end - t_begin));
+    }
+}
+
 // Grid.  step >= 0 (REFERENCE schedule): block x = population, its chain is sweep position `step`.
 // step < 0, half < 0: block x = (population, chain).  step < 0, half = 0 / 1 (PARALLEL schedule): block x =
 // (population, slot) with (nchain + 1) / 2 slots; a crossover population evaluates chain 2 slot + half, a
@@ -675,6 +728,45 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, Trial
     }
 }
 
+// k_like for model type "fastdm": same grid, same arguments, same block -> (population, chain) mapping
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_like_ddm(Level L, DevModel M, TrialData T, const uint32_t *d_iter, int sweep, int step,
+                                                           int half, double *ll_part /* [npop][C][nsplit] */)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int C = L.nchain;
+    (void)d_iter; // the DDM density consumes no draws (@hdr/ddm.h has no Rf_runif), so neither iteration nor sweep is needed
+    (void)sweep;
+    int p, chain0, stride = C, nchain_blk = 1;
+    if (step >= 0) {
+        p = blockIdx.x;
+        chain0 = step;
+        if (L.mode[p]) {
+            if (step >= L.mig_n[p]) return;
+            chain0 = L.mig_list[p * C + step];
+        }
+    } else if (half < 0) {
+        p = blockIdx.x / C;
+        chain0 = blockIdx.x - p * C;
+    } else {
+        const int nslot = (C + 1) / 2;
+        p = blockIdx.x / nslot;
+        const int slot = blockIdx.x - p * nslot;
+        if (L.mode[p] == 0) {
+            chain0 = 2 * slot + half;
+        } else {
+            if (half != 0) return;
+            chain0 = slot;
+            stride = nslot;
+            nchain_blk = 2;
+        }
+    }
+    for (int i = 0, chain = chain0; i < nchain_blk && chain < C; ++i, chain += stride) {
+        if (L.target[p * C + chain] >= 0) like_one_ddm<BLOCK>(L, M, T, p, chain, blockIdx.y, ll_part, sm_raw);
+        if (nchain_blk > 1) __syncthreads();
+    }
+}
+
 // per-trial log densities of one subject for n_theta parameter vectors (parity / init entry point)
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_trial_logdens(DevModel M, const double *rt, const uint16_t *cl, int ntr,
@@ -690,6 +782,30 @@ __global__ void __launch_bounds__(BLOCK) k_trial_logdens(DevModel M, const doubl
         const int c = cl[t];
         out[(size_t)k * ntr + t] = log(n1pdf_any<0>(bad[c], rt[t], ent + c * na, na));
     }
+}
+
+// the same for the DDM: log(max(density, DBL_MIN)) of every trial (@hdr/likelihood.h:303)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_trial_logdens_ddm(DevModel M, const double *rt, const uint16_t *cl, int ntr,
+                                                             const double *theta, double *out)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int na = M.n_acc, D = M.npar, k = blockIdx.x;
+    DdmCell *ent = reinterpret_cast<DdmCell *>(sm_raw);
+    const double *th = theta + (size_t)k * D;
+    for (int c = threadIdx.x; c < M.n_cell; c += BLOCK) {
+        const int *src = M.param_src + (size_t)c * kDdmRows * na;
+        double P[kDdmRows];
+#pragma unroll
+        for (int r = 0; r < kDdmRows; ++r) {
+            const int i = src[r * na];
+            P[r] = i >= 0 ? th[i] : M.const_val[-1 - i];
+        }
+        ddmcell_build(ent[c], P, M.posdrift[c] != 0);
+    }
+    __syncthreads();
+    for (int t = blockIdx.y * BLOCK + threadIdx.x; t < ntr; t += gridDim.y * BLOCK)
+        out[(size_t)k * ntr + t] = log(ddm_floor(ddm_density(ent[cl[t]], rt[t])));
 }
 
 // ------------------------------------------------------------------------------------------------

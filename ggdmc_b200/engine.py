@@ -27,7 +27,8 @@ def _model(ct: CellTable) -> _Keep:
     ps = np.ascontiguousarray(ct.param_src, dtype=np.int32)
     cv = B.f64(ct.const_val if len(ct.const_val) else [0.0])
     pd = np.ascontiguousarray(ct.posdrift, dtype=np.uint8)
-    m = B.ModelT(ct.n_acc, ct.n_cell, ct.npar, len(ct.const_val), B.ptr(ps, B.c_i32p), B.ptr(cv), B.ptr(pd, B.c_u8p))
+    mtype = B.MODEL_TYPES[getattr(ct, "type", "lba")]
+    m = B.ModelT(ct.n_acc, ct.n_cell, ct.npar, len(ct.const_val), B.ptr(ps, B.c_i32p), B.ptr(cv), B.ptr(pd, B.c_u8p), mtype)
     return _Keep(m, ps, cv, pd)
 
 

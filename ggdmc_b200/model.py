@@ -17,6 +17,10 @@ import numpy as np
 # core LBA parameter rows, alphabetical (design_class::set_parameter_values,
 # @hdr/design_light.h:314-344)
 LBA_CORE = ("A", "B", "mean_v", "sd_v", "st0", "t0")
+# core DDM parameter rows, alphabetical like every core table; ddm_class::set_parameters reads them by
+# row index (@hdr/ddm.h:194-214: a = 0, d = 1, precision = 2, s = 3, st0 = 4, sv = 5, sz = 6, t0 = 7, v = 8, z = 9)
+DDM_CORE = ("a", "d", "precision", "s", "st0", "sv", "sz", "t0", "v", "z")
+CORE_OF_TYPE = {"lba": LBA_CORE, "fastdm": DDM_CORE}
 
 # prior::DistributionType (@hdr/prior.h:186)
 DIST_TNORM, DIST_BETA_LU, DIST_GAMMA_L, DIST_LNORM_L, DIST_CAUCHY, DIST_UNIF, DIST_NORM = 1, 2, 3, 4, 5, 6, 7
@@ -29,6 +33,14 @@ def slot(obj: Any, name: str) -> Any:
     if isinstance(obj, dict):
         return obj[name]
     return getattr(obj, name)
+
+
+def _has_slot(obj: Any, name: str) -> bool:
+    try:
+        slot(obj, name)
+        return True
+    except (AttributeError, KeyError):
+        return False
 
 
 def _scalar(x) -> Any:
@@ -44,25 +56,31 @@ def _strings(x) -> List[str]:
 
 @dataclass
 class CellTable:
-    """Flattened model: the per-cell 6 x n_acc parameter source table.
+    """Flattened model: the per-cell rows x n_acc parameter source table.
 
     ``param_src[c, r, j] >= 0`` is an index into theta; ``< 0`` refers to
     ``const_val[-1 - k]``.  Column j = 0 is the responding accumulator
-    (``dmi@node_1_index``), rows follow :data:`LBA_CORE`.
+    (``dmi@node_1_index``), rows follow :data:`LBA_CORE` (type "lba") or
+    :data:`DDM_CORE` (type "fastdm").
     """
 
     n_acc: int
     n_cell: int
     npar: int
-    param_src: np.ndarray  # int32 [n_cell, 6, n_acc]
+    param_src: np.ndarray  # int32 [n_cell, rows, n_acc]
     const_val: np.ndarray  # float64
-    posdrift: np.ndarray  # uint8 [n_acc]
+    posdrift: np.ndarray  # uint8; "lba": [n_acc] is_positive_drift, "fastdm": [n_cell] upper-boundary response
     pnames: List[str]
     cell_names: List[str]
+    type: str = "lba"
 
 
 def build_cell_table(model: Any, node_1_index: Any, is_positive_drift: Any) -> CellTable:
     """model_boolean + node_1_index + constants + pnames -> param_src."""
+    mtype = _strings(slot(model, "type"))[0] if _has_slot(model, "type") else "lba"
+    if mtype not in CORE_OF_TYPE:
+        raise ValueError("Undefined model type")  # @hdr/likelihood.h:312
+    core_rows = CORE_OF_TYPE[mtype]
     pxc = _strings(slot(model, "parameter_x_condition_names"))
     pnames = _strings(slot(model, "pnames"))
     cell_names = _strings(slot(model, "cell_names"))
@@ -78,13 +96,13 @@ def build_cell_table(model: Any, node_1_index: Any, is_positive_drift: Any) -> C
         raise ValueError("model_boolean dimensions disagree with names")
     core_of = [name.split(".", 1)[0] for name in pxc]
     for nm in core_of:
-        if nm not in LBA_CORE:
-            raise ValueError(f"unknown core parameter {nm!r}; this engine implements the LBA (type 'lba')")
-    src = np.zeros((n_cell, 6, n_acc), dtype=np.int32)
+        if nm not in core_rows:
+            raise ValueError(f"unknown core parameter {nm!r} for model type {mtype!r}")
+    src = np.zeros((n_cell, len(core_rows), n_acc), dtype=np.int32)
     for c in range(n_cell):
         for j in range(n_acc):
             acc = int(n1[c, j])
-            for r, core in enumerate(LBA_CORE):
+            for r, core in enumerate(core_rows):
                 ks = [k for k in range(n_pxc) if core_of[k] == core and mb[c, k, acc]]
                 if len(ks) != 1:
                     raise ValueError(f"cell {cell_names[c]} acc {acc}: {len(ks)} sources for {core}")
@@ -96,9 +114,12 @@ def build_cell_table(model: Any, node_1_index: Any, is_positive_drift: Any) -> C
                 else:
                     raise ValueError(f"{name} is neither a free parameter nor a constant")
     pd = np.asarray(is_positive_drift).astype(np.uint8).ravel()
-    if pd.size != n_acc:
+    if mtype == "fastdm":  # ddm_likelihood indexes it by cell (@hdr/likelihood.h:142): TRUE = upper-boundary response
+        if pd.size != n_cell:
+            raise ValueError("is_positive_drift length != number of cells (model type 'fastdm')")
+    elif pd.size != n_acc:
         raise ValueError("is_positive_drift length != number of accumulators")
-    return CellTable(n_acc, n_cell, len(pnames), src, cvals.copy(), pd, pnames, cell_names)
+    return CellTable(n_acc, n_cell, len(pnames), src, cvals.copy(), pd, pnames, cell_names, mtype)
 
 
 @dataclass

@@ -21,7 +21,10 @@
 
 namespace {
 
-const char *kCore[6] = {"A", "B", "mean_v", "sd_v", "st0", "t0"}; // @hdr/design_light.h:314-344 row order
+// core-parameter rows in the order design_class::set_parameter_values fills them (@hdr/design_light.h:314-344):
+// alphabetical; ddm_class::set_parameters reads the DDM's by index (@hdr/ddm.h:194-214)
+const char *kCoreLba[GGDMC_LBA_ROWS] = {"A", "B", "mean_v", "sd_v", "st0", "t0"};
+const char *kCoreDdm[GGDMC_DDM_ROWS] = {"a", "d", "precision", "s", "st0", "sv", "sz", "t0", "v", "z"};
 
 struct FlatModel {
     std::vector<int32_t> param_src;
@@ -35,7 +38,11 @@ struct FlatModel {
 FlatModel flatten_model(const Rcpp::S4 &dmi)
 {
     Rcpp::S4 model = dmi.slot("model");
-    if (Rcpp::as<std::string>(model.slot("type")) != "lba") Rcpp::stop("Undefined model type");
+    const std::string type = Rcpp::as<std::string>(model.slot("type"));
+    if (type != "lba" && type != "fastdm") Rcpp::stop("Undefined model type"); // @hdr/likelihood.h:312
+    const bool ddm = type == "fastdm";
+    const int rows = ddm ? GGDMC_DDM_ROWS : GGDMC_LBA_ROWS;
+    const char *const *kCore = ddm ? kCoreDdm : kCoreLba;
     FlatModel m;
     std::vector<std::string> pxc = Rcpp::as<std::vector<std::string>>(model.slot("parameter_x_condition_names"));
     m.pnames = Rcpp::as<std::vector<std::string>>(model.slot("pnames"));
@@ -48,11 +55,11 @@ FlatModel flatten_model(const Rcpp::S4 &dmi)
     const int n_cell = dim[0], n_pxc = dim[1], n_acc = dim[2];
     Rcpp::IntegerMatrix n1 = dmi.slot("node_1_index");
     Rcpp::LogicalVector pd = dmi.slot("is_positive_drift");
-    m.param_src.assign((size_t)n_cell * 6 * n_acc, 0);
+    m.param_src.assign((size_t)n_cell * rows * n_acc, 0);
     for (int c = 0; c < n_cell; ++c)
         for (int j = 0; j < n_acc; ++j) {
             const int acc = n1(c, j);
-            for (int r = 0; r < 6; ++r) {
+            for (int r = 0; r < rows; ++r) {
                 int found = -1;
                 for (int k = 0; k < n_pxc; ++k) {
                     const std::string core = pxc[k].substr(0, pxc[k].find('.'));
@@ -65,10 +72,14 @@ FlatModel flatten_model(const Rcpp::S4 &dmi)
                 if (src < 0)
                     for (size_t q = 0; q < cnames.size(); ++q)
                         if (cnames[q] == pxc[found]) src = -1 - (int)q;
-                m.param_src[((size_t)c * 6 + r) * n_acc + j] = src;
+                m.param_src[((size_t)c * rows + r) * n_acc + j] = src;
             }
         }
-    for (int j = 0; j < n_acc; ++j) m.posdrift.push_back(pd[j] ? 1 : 0);
+    // "lba": one flag per accumulator; "fastdm": one per cell, TRUE = upper-boundary response (@hdr/likelihood.h:142)
+    const int n_pd = ddm ? n_cell : n_acc;
+    if (pd.size() != n_pd) Rcpp::stop("is_positive_drift has the wrong length for this model type");
+    for (int j = 0; j < n_pd; ++j) m.posdrift.push_back(pd[j] ? 1 : 0);
+    m.c.type = ddm ? GGDMC_MODEL_DDM : GGDMC_MODEL_LBA;
     m.c.n_acc = n_acc; m.c.n_cell = n_cell; m.c.npar = (int)m.pnames.size(); m.c.n_const = (int)m.const_val.size();
     m.c.param_src = m.param_src.data(); m.c.const_val = m.const_val.data(); m.c.posdrift = m.posdrift.data();
     return m;

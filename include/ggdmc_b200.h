@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GGDMC_B200_ABI_VERSION 1
+#define GGDMC_B200_ABI_VERSION 2
 
 enum ggdmc_status {
     GGDMC_OK = 0,
@@ -57,6 +57,13 @@ enum ggdmc_dist {
  * Migration sweeps move all selected chains at once in PARALLEL and SIMULTANEOUS. */
 enum ggdmc_schedule { GGDMC_SCHEDULE_REFERENCE = 0, GGDMC_SCHEDULE_PARALLEL = 1, GGDMC_SCHEDULE_SIMULTANEOUS = 2 };
 
+/* model@type as likelihood_class::resolve_string reads it (@hdr/likelihood.h:279): "lba" -> lba_likelihood
+ * (:73-108), "fastdm" -> ddm_likelihood (:129-161).  ("hyper" is ggdmc_b200_run_hyper; anything else is the
+ * reference's "Undefined model type", :312.) */
+enum ggdmc_model_type { GGDMC_MODEL_LBA = 0, GGDMC_MODEL_DDM = 1 };
+#define GGDMC_LBA_ROWS 6  /* A, B, mean_v, sd_v, st0, t0 */
+#define GGDMC_DDM_ROWS 10 /* a, d, precision, s, st0, sv, sz, t0, v, z */
+
 /* dmi@model + dmi@node_1_index + dmi@is_positive_drift, flattened (SURVEY.md A.1;
  * replaces design_class, @hdr/design_light.h:77-344).  One model is shared by all subjects. */
 typedef struct ggdmc_model {
@@ -64,10 +71,14 @@ typedef struct ggdmc_model {
     int32_t n_cell;           /* design cells */
     int32_t npar;             /* free parameters of one subject (length of theta) */
     int32_t n_const;
-    const int32_t *param_src; /* [n_cell][6][n_acc]; rows A,B,mean_v,sd_v,st0,t0; column 0 = the
-                                 responding accumulator; >= 0: index into theta, < 0: const_val[-1-k] */
+    const int32_t *param_src; /* [n_cell][rows][n_acc]; rows = the model family's core parameters in alphabetical
+                                 order (6 for the LBA, 10 for the DDM, above); column 0 = the responding
+                                 accumulator (the only column the DDM reads, @hdr/ddm.h:194-214);
+                                 >= 0: index into theta, < 0: const_val[-1-k] */
     const double *const_val;  /* [n_const] */
-    const uint8_t *posdrift;  /* [n_acc] is_positive_drift */
+    const uint8_t *posdrift;  /* dmi@is_positive_drift.  LBA: [n_acc].  DDM: [n_cell], non-zero = the cell's
+                                 response is the upper boundary (@hdr/likelihood.h:142 indexes it by cell) */
+    int32_t type;             /* enum ggdmc_model_type */
 } ggdmc_model_t;
 
 /* dmi@data of every subject (replaces likelihood_class::m_rt, @hdr/likelihood.h:10).  Trials may
@@ -155,8 +166,9 @@ int ggdmc_b200_run(const ggdmc_model_t *model, const ggdmc_trials_t *trials, con
 /* ---- density entry points (what ggdmcLikelihood / ggdmcPrior expose to R; used by
  *      initialise_theta, R/phi.R:166-201, and by the parity tests) ---------------------------- */
 
-/* likelihood_class::lba_likelihood (@hdr/likelihood.h:73-108): log n1PDF of every trial of ONE
- * subject for n_theta parameter vectors; out[n_theta][n_trial] in the caller's trial order. */
+/* likelihood_class::lba_likelihood / ddm_likelihood (@hdr/likelihood.h:73-108, 129-161): log density of
+ * every trial of ONE subject for n_theta parameter vectors as sumloglike takes it (:288 LBA: log(n1PDF);
+ * :303 DDM: log(max(density, DBL_MIN))); out[n_theta][n_trial] in the caller's trial order. */
 int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta,
                              int32_t n_theta, double *out, char err[256]);
 

@@ -251,11 +251,29 @@ def time_sumloglike(m: OModel, d: OData, thetas, reps: int) -> float:
 
 # ---- tier-2: the reference's own sampler object code (oracle/ref_harness2.cpp) ---------------------
 def _model_args(m: OModel):
+    ref_lib().ref2_set_model_type(int(m.type))  # "lba" or "fastdm" objects (oracle/ref_harness2.cpp)
     return [m.n_acc, m.n_cell, ptr(m.param_src, c_ip), ptr(m.const_val), ptr(m.posdrift, c_u8p)]
 
 
 def _prior_args(p: OPrior):
     return [ptr(p.p0), ptr(p.p1), ptr(p.lower), ptr(p.upper), ptr(p.dist, c_ip), ptr(p.log_p, c_u8p)]
+
+
+def ddm_cell(P, is_upper: bool, rt) -> tuple:
+    """orc_ddm_cell: densities of one DDM cell (P = a, d, precision, s, st0, sv, sz, t0, v, z); returns (valid, dens)."""
+    P, rt = f64(P), f64(rt)
+    out = np.zeros(len(rt))
+    ok = lib().orc_ddm_cell(ptr(P), int(bool(is_upper)), ptr(rt), len(rt), ptr(out))
+    return bool(ok), out
+
+
+def ref2_ddm_density(m: OModel, d: OData, theta) -> np.ndarray:
+    """likelihood_class::ddm_likelihood of src/de.o: density of every trial of d (cell-grouped order = d's order)."""
+    th = f64(theta)
+    out = np.zeros(len(d.rt))
+    ref_lib().ref2_ddm_density(m.n_acc, m.n_cell, ptr(m.param_src, c_ip), ptr(m.const_val), ptr(m.posdrift, c_u8p), ptr(d.rt),
+                               ptr(d.cell, c_u16p), len(d.rt), ptr(th), len(th), ptr(out))
+    return out
 
 
 def ref2_prime() -> None:

@@ -58,3 +58,15 @@ void hm_norm_cdf_lowlatency(const double *z, int n, double *cdf)
     for (int i = 0; i < n; ++i) cdf[i] = gg::fm::norm_cdf_lowlatency(z[i]);
 }
 }
+
+#include "../../ggdmc_b200/csrc/gg_ddm.cuh"
+extern "C" {
+// P = column 0 of the ten DDM rows (a, d, precision, s, st0, sv, sz, t0, v, z); returns validate_parameters()
+int hm_ddm_cell(const double *P, int is_upper, const double *rt, int n, double *out)
+{
+    gg::DdmCell q;
+    gg::ddmcell_build(q, P, is_upper != 0);
+    for (int i = 0; i < n; ++i) out[i] = gg::ddm_density(q, rt[i]);
+    return q.valid;
+}
+}

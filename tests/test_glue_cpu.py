@@ -53,7 +53,7 @@ def test_glue_surfaces_library_errors_as_r_errors():
     cfg = api.Config(prior=prior, theta_input=api.ThetaInput(nmc=3, nchain=2, thin=1, nparameter=D, pnames=fx.ct.pnames),
                      de_input=api.DEInput(nparameter=D, nchain=2), seed=1)
     bad = dmi_of("sub")
-    bad.model = api.Model(model.parameter_x_condition_names, model.pnames, model.cell_names, model.constants, model.model_boolean, type="fastdm")
+    bad.model = api.Model(model.parameter_x_condition_names, model.pnames, model.cell_names, model.constants, model.model_boolean, type="ddm2")
     with pytest.raises(RuntimeError, match="Undefined model type"):  # raised by the glue itself, like @hdr/likelihood.h:312
         G.run_subject(cfg, bad, st)
     with pytest.raises(RuntimeError, match="Require three or more chains."):  # src/de.cpp:7-10, checked before any device work

@@ -368,7 +368,7 @@ def test_cabi_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.ggdmc_b200_abi_version() == 1
+    assert L.ggdmc_b200_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():
