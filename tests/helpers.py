@@ -88,3 +88,77 @@ def fixture_objects(k):
         return api.DMI(model=model, data=data, node_1_index=g["node_1_index"], is_positive_drift=g["is_positive_drift"])
 
     return fx, model, dmi_of
+
+
+# ---- DDM ("fastdm") test model: stimulus S (s1, s2) x response R (r1, r2); drift rate by stimulus; r2 = upper boundary ----
+DDM_PNAMES = ["a", "st0", "sv", "sz", "t0", "v.s1", "v.s2", "z"]
+DDM_CONST = {"d": 0.0, "precision": 3.0, "s": 1.0}
+
+
+def ddm_model(precision=3.0, s=1.0):
+    """(CellTable, OModel) of a 4-cell DDM: rows a, d, precision, s, st0, sv, sz, t0, v, z (ggdmc_b200.model.DDM_CORE);
+    free parameters DDM_PNAMES (alphabetical like the reference's pnames), constants d, precision, s."""
+    from ggdmc_b200.model import DDM_CORE
+    cells = ["s1.r1", "s1.r2", "s2.r1", "s2.r2"]
+    cnames = list(DDM_CONST)
+    src = np.zeros((4, 10, 2), dtype=np.int32)
+    for c in range(4):
+        for r, core in enumerate(DDM_CORE):
+            name = f"v.s{c // 2 + 1}" if core == "v" else core
+            src[c, r, :] = DDM_PNAMES.index(name) if name in DDM_PNAMES else -1 - cnames.index(name)
+    const = np.array([0.0, precision, s])
+    upper = np.array([0, 1, 0, 1], dtype=np.uint8)
+    ct = CellTable(2, 4, len(DDM_PNAMES), src, const, upper, list(DDM_PNAMES), cells, "fastdm")
+    return ct, ob.OModel(src, const, upper, ct.npar, type=ob.MODEL_DDM)
+
+
+def ddm_theta(rng: np.random.Generator, kind: int) -> np.ndarray:
+    """A plausible parameter vector in DDM_PNAMES order.  kind 0: no variability; 1: + sv; 2: + sz; 3: + st0."""
+    a = rng.uniform(0.6, 2.2)
+    th = dict(a=a, st0=0.0, sv=0.0, sz=0.0, t0=rng.uniform(0.1, 0.3), z=a * rng.uniform(0.35, 0.65))
+    th["v.s1"], th["v.s2"] = rng.normal(-1.5, 1.0), rng.normal(1.5, 1.0)
+    if kind >= 1:
+        th["sv"] = rng.uniform(0.05, 1.5)
+    if kind >= 2:
+        th["sz"] = a * rng.uniform(0.02, 0.3)
+    if kind >= 3:
+        th["st0"] = rng.uniform(0.02, 0.25)
+    return np.array([th[n] for n in DDM_PNAMES])
+
+
+def ddm_simulate(theta: np.ndarray, n_per_stim: int, rng: np.random.Generator, dt=1e-3, s=1.0):
+    """Euler-Maruyama simulation of the 4-cell model above (test data only): returns (rt, cell) grouped by cell."""
+    p = dict(zip(DDM_PNAMES, theta))
+    rts, cells = [], []
+    for stim in range(2):
+        v = p[f"v.s{stim + 1}"] + p["sv"] * rng.standard_normal(n_per_stim)
+        x = p["z"] + p["sz"] * (rng.uniform(size=n_per_stim) - 0.5)
+        t = np.zeros(n_per_stim)
+        done = np.zeros(n_per_stim, dtype=bool)
+        resp = np.zeros(n_per_stim, dtype=int)
+        for _ in range(20000):
+            live = ~done
+            if not live.any():
+                break
+            x[live] += v[live] * dt + s * np.sqrt(dt) * rng.standard_normal(live.sum())
+            t[live] += dt
+            up, lo = live & (x >= p["a"]), live & (x <= 0)
+            resp[up] = 1
+            done |= up | lo
+        rt = t + p["t0"] + p["st0"] * rng.uniform(size=n_per_stim)
+        keep = done
+        rts.append(rt[keep])
+        cells.append((2 * stim + resp[keep]).astype(np.uint16))
+    rt, cell = np.concatenate(rts), np.concatenate(cells)
+    order = np.argsort(cell, kind="stable")
+    return rt[order], cell[order]
+
+
+def ddm_prior(kind="sub"):
+    """Uniform priors over DDM_PNAMES wide enough for the generators above: (PriorTable, OPrior)."""
+    lo = np.array([0.2, 0.0, 0.0, 0.0, 0.0, -6.0, -6.0, 0.05])
+    hi = np.array([4.0, 0.5, 3.0, 1.0, 0.6, 6.0, 6.0, 3.5])
+    n = len(lo)
+    dist, logp = np.full(n, 6, np.int32), np.ones(n, np.uint8)
+    return (PriorTable(n, lo.copy(), hi.copy(), np.zeros(n), np.zeros(n), dist, logp, list(DDM_PNAMES)),
+            ob.OPrior(lo, hi, np.zeros(n), np.zeros(n), dist, logp))

@@ -1,0 +1,192 @@
+"""CPU tests of the DDM ("fastdm") path: the oracle's restatement of ddm_class against the reference's own object
+code (likelihood_class::ddm_likelihood and de_class::run_chains of src/de.o), against the published series it
+implements, and the engine's device header compiled for the host against the oracle.  No GPU needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from helpers import ddm_model, ddm_prior, ddm_simulate, ddm_theta
+from test_oracle_cpu import hostmath, needs_ref  # noqa: F401  (fixture + marker)
+
+DBL_MIN = 2.2250738585072014e-308
+
+
+def _grid_data(rng, n=240):
+    cell = np.sort(rng.integers(0, 4, n)).astype(np.uint16)
+    rt = np.concatenate([rng.uniform(0.15, 0.5, n // 3), rng.uniform(0.3, 1.5, n - 2 * (n // 3)), rng.uniform(1.0, 6.0, n // 3)])
+    return ob.OData(rng.permutation(rt), cell)
+
+
+def _same(a, b):
+    return (a == b) | (np.isnan(a) & np.isnan(b))
+
+
+def _oracle_density(om, d, theta):
+    out = np.zeros(len(d.rt))
+    for c in range(om.n_cell):
+        idx = np.where(d.cell == c)[0]
+        P = np.zeros(10 * om.n_acc)
+        ob.lib().orc_cell_params(C.byref(om.c), ob.ptr(ob.f64(theta)), c, ob.ptr(P))
+        ok, dens = ob.ddm_cell(P.reshape(10, om.n_acc)[:, 0], bool(om.posdrift[c]), d.rt[idx])
+        out[idx] = dens
+    return out
+
+
+def _edge_thetas(rng):
+    """Parameter vectors that hit validate_parameters' eight rules, rt <= t0, and extreme but valid corners."""
+    base = ddm_theta(rng, 3)
+    names = ["a", "st0", "sv", "sz", "t0", "v.s1", "v.s2", "z"]
+    out = []
+    for nm, val in (("a", -1.0), ("a", 0.0), ("st0", -0.1), ("sv", -0.5), ("sz", -0.1), ("sz", 10.0), ("t0", -1.0), ("z", 0.0),
+                    ("z", 50.0), ("z", float("nan")), ("a", float("nan")), ("t0", 5.9), ("sv", 40.0), ("v.s1", 25.0), ("v.s2", -25.0),
+                    ("a", 0.05), ("a", 30.0), ("st0", 1e-9), ("sz", 1e-9), ("t0", float("inf"))):
+        th = base.copy()
+        th[names.index(nm)] = val
+        if nm == "a" and np.isfinite(val) and val > 0:
+            th[names.index("z")] = 0.5 * val
+            th[names.index("sz")] = 0.1 * val
+        out.append(th)
+    return out
+
+
+@needs_ref
+@pytest.mark.parametrize("precision,s", [(3.0, 1.0), (2.5, 1.0), (3.0, 0.1), (2.0, 2.0)])
+def test_ddm_density_bitwise_vs_reference_object_code(precision, s):
+    """likelihood_class::ddm_likelihood of src/de.o (design_class::set_parameter_values, ddm_class::set_parameters,
+    validate_parameters, dddm -- @hdr/likelihood.h:129-161, @hdr/ddm.h) on a hand-built "fastdm" object vs orc_ddm_cell:
+    every trial density bit-identical, for all four variability combinations and both boundaries."""
+    ct, om = ddm_model(precision, s)
+    rng = np.random.default_rng(int(precision * 10 + s * 100))
+    d = _grid_data(rng)
+    n_pos = 0
+    for it in range(80):
+        th = ddm_theta(rng, it % 4)
+        if s != 1.0:  # a, v, sv are divided by s (@hdr/ddm.h:203-206): keep the scaled model in the same regime
+            for i in (0, 2, 5, 6):
+                th[i] *= s
+            th[[3, 7]] *= 1.0  # sz, z are NOT rescaled by the reference (:216-218 divide by the scaled a)
+            th[7] = th[0] / s * 0.5
+            th[3] = min(th[3], 0.2 * th[0] / s)
+        ref = ob.ref2_ddm_density(om, d, th)
+        mine = _oracle_density(om, d, th)
+        assert np.all(_same(ref, mine)), (it, th, np.argwhere(~_same(ref, mine))[:3])
+        n_pos += int(np.sum(ref > 1e-6))
+    assert n_pos > 20 * len(d.rt)  # the comparison is not about floors
+
+
+@needs_ref
+def test_ddm_edge_cases_bitwise_vs_reference_object_code():
+    """Invalid cells (every rule of validate_parameters, NaN passing the comparisons), rt below the non-decision time,
+    extreme drifts / boundaries: the restatement takes the reference's branch every time."""
+    ct, om = ddm_model()
+    rng = np.random.default_rng(3)
+    d = _grid_data(rng)
+    n_floor = 0
+    for th in _edge_thetas(rng):
+        ref = ob.ref2_ddm_density(om, d, th)
+        mine = _oracle_density(om, d, th)
+        assert np.all(_same(ref, mine)), (th, np.argwhere(~_same(ref, mine))[:3])
+        n_floor += int(np.all(ref == 1e-10))
+    assert n_floor >= 8  # invalid cells: every trial 1e-10 (@hdr/likelihood.h:158)
+
+
+def _navarro_fuss_lower(t, v, a, w, terms=400):
+    """Lower-boundary first-passage density, large-time series (Navarro & Fuss 2009, eq. 5/6), no variabilities."""
+    k = np.arange(1, terms + 1)[:, None]
+    return (np.pi / a**2) * np.exp(-v * a * w - v * v * t / 2) * np.sum(k * np.exp(-(k * np.pi) ** 2 * t / (2 * a * a)) * np.sin(k * np.pi * w), axis=0)
+
+
+def test_ddm_density_matches_published_series():
+    """Without variabilities the density is the Navarro-Fuss series; the reference truncates it at an absolute error of
+    1e-6 (ddm::EPSILON).  Upper boundary = lower boundary with (v, w) -> (-v, 1 - w)."""
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        a, v, t0 = rng.uniform(0.6, 2.5), rng.normal(0, 2), rng.uniform(0.1, 0.3)
+        z = a * rng.uniform(0.3, 0.7)
+        rt = t0 + rng.uniform(0.05, 3.0, 50)
+        P = [a, 0.0, 3.0, 1.0, 0.0, 0.0, 0.0, t0, v, z]
+        ok, lo = ob.ddm_cell(P, False, rt)
+        ok2, up = ob.ddm_cell(P, True, rt)
+        assert ok and ok2
+        assert np.all(np.abs(lo - _navarro_fuss_lower(rt - t0, v, a, z / a)) <= 2e-6)
+        assert np.all(np.abs(up - _navarro_fuss_lower(rt - t0, -v, a, 1 - z / a)) <= 2e-6)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_ddm_defective_densities_integrate_to_one(kind):
+    """Size-independent property: P(lower) + P(upper) = 1, with every variability switched on in turn."""
+    rng = np.random.default_rng(20 + kind)
+    for _ in range(3):
+        th = ddm_theta(rng, kind)
+        a, st0, sv, sz, t0, v1, v2, z = th
+        t = np.linspace(t0 + 1e-4, t0 + st0 + 14.0, 14001 if kind < 3 else 4001)
+        P = [a, 0.0, 3.0, 1.0, st0, sv, sz, t0, v1 * 0.4, z]
+        lo, up = ob.ddm_cell(P, False, t)[1], ob.ddm_cell(P, True, t)[1]
+        total = np.trapezoid(lo + up, t)
+        assert abs(total - 1.0) < 5e-3, (th, total)
+
+
+def test_ddm_device_math_on_host_matches_oracle(hostmath):
+    """gg_ddm.cuh compiled for the host (same libm, no FMA contraction) vs the oracle: valid flags equal, densities to
+    <= 1e-13 relative (bit-identical in practice), edge cases included."""
+    H = hostmath
+    rng = np.random.default_rng(5)
+    d = _grid_data(rng, 120)
+    rt = ob.f64(d.rt)
+    thetas = [ddm_theta(rng, k % 4) for k in range(60)] + _edge_thetas(rng)
+    n_exact = n_tot = 0
+    for th in thetas:
+        a, st0, sv, sz, t0, v1, v2, z = th
+        for upper in (False, True):
+            P = ob.f64([a, 0.0, 3.0, 1.0, st0, sv, sz, t0, v1, z])
+            ok, want = ob.ddm_cell(P, upper, rt)
+            got = np.zeros(len(rt))
+            ok_h = H.hm_ddm_cell(ob.ptr(P), int(upper), ob.ptr(rt), len(rt), ob.ptr(got))
+            assert bool(ok_h) == ok
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+            fin = ~np.isnan(want)
+            assert np.all(np.abs(got[fin] - want[fin]) <= 1e-13 * np.abs(want[fin])), th
+            n_exact += int(np.sum(_same(got, want)))
+            n_tot += len(rt)
+    assert n_exact >= 0.999 * n_tot
+
+
+def _ddm_subject_state(om, d, oprior, nchain, rng, kind=1):
+    th = np.stack([ddm_theta(rng, kind) for _ in range(nchain)])
+    center = th[0]
+    th = center[None, :] * (1.0 + 0.03 * rng.standard_normal(th.shape))
+    lp = np.array([ob.sumlogprior(oprior, t) for t in th])
+    ll = np.array([ob.lib().orc_sumloglike(C.byref(om.c), C.byref(d.c), ob.ptr(ob.f64(t)), None, None) for t in th])
+    return th, lp, ll
+
+
+@needs_ref
+@pytest.mark.parametrize("pblocked", [False, True])
+def test_ddm_run_chains_bitwise_vs_reference_object_code(pblocked):
+    """de_class::run_chains of src/de.o on a "fastdm" likelihood object -- sumloglike's DDM branch
+    (@hdr/likelihood.h:295-305: log(max(density, DBL_MIN))) included -- vs orc_run_subject: stored samples bit-identical
+    and the same number of uniforms consumed (the DDM density draws none)."""
+    ob.ref2_prime()
+    ct, om = ddm_model()
+    rng = np.random.default_rng(41)
+    truth = ddm_theta(rng, 1)
+    rt, cell = ddm_simulate(truth, 60, rng)
+    d = ob.OData(rt, cell)
+    pt, op = ddm_prior()
+    D = ct.npar
+    nchain, nmc, thin = 3 * D, 4, 2
+    ob.lib().orc_sumloglike.restype = C.c_double
+    th, lp, ll = _ddm_subject_state(om, d, op, nchain, rng)
+    u = ob.ref2_set_stream(rng.uniform(size=400000))
+    ot, olp, oll = ob.ref2_run_chains(D, om, d, op, th, lp, ll, nmc, thin, sub_migration_prob=0.3, is_pblocked=pblocked)
+    used = ob.ref_lib().ref_uniform_stream_pos()
+    ob.ref_lib().ref2_set_model_type(0)
+    pop = ob.OPop(th, lp, ll, nmc, thin)
+    r = ob.make_rng(stream=u)
+    ob.run_subject(ob.make_de(D, nchain, sub_migration_prob=0.3, is_pblocked=pblocked), pop, op, om, d, r, 0, (nmc - 1) * thin)
+    assert r.pos == used
+    assert np.array_equal(ot, pop.out_theta) and np.array_equal(olp, pop.out_lp) and np.array_equal(oll, pop.out_ll)
+    assert not np.array_equal(ot[0], ot[-1])
+    assert np.all(np.isfinite(oll[-1]))
