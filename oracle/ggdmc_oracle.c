@@ -266,6 +266,15 @@ static void ddm_get_n(double t, double ta, double eps, int *n_small, int *n_larg
     *n_large = nl;
 }
 
+/* work counters for the measurement tools (tools/exp_ddm.py turns them into algorithmic flops per trial):
+ * series evaluations that got past the t > 0 and factor != 0 tests, and the terms they summed */
+static long long g_ddm_evals, g_ddm_small_terms, g_ddm_large_terms;
+void orc_ddm_counters(long long out[3], int reset)
+{
+    out[0] = g_ddm_evals; out[1] = g_ddm_small_terms; out[2] = g_ddm_large_terms;
+    if (reset) g_ddm_evals = g_ddm_small_terms = g_ddm_large_terms = 0;
+}
+
 /* integral_v, @hdr/ddm.h:457-485, and g_no_var :433-454 (the sv == 0 branch; same steps, other factor) */
 static double ddm_integral_v(const ddm_par *q, double t, double zr)
 {
@@ -279,6 +288,8 @@ static double ddm_integral_v(const ddm_par *q, double t, double zr)
     eps = DDM_EPSILON / factor;                      /* :479 / :449 */
     ddm_get_n(t, ta, eps, &ns, &nl);                 /* :480 / :450 */
     use_small = ns < nl;                             /* :481 / :451 */
+    ++g_ddm_evals;
+    if (use_small) g_ddm_small_terms += ns > 0 ? 2 * (ns / 2) + 1 : 0; else g_ddm_large_terms += nl > 0 ? nl : 0;
     return ddm_series(ta, zr, use_small, use_small ? ns : nl) * factor; /* :484 / :453 */
 }
 

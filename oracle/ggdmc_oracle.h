@@ -115,6 +115,8 @@ double orc_sumloglike_rinit(const orc_model *m, const orc_data *d, const double 
 /* One cell: P = column 0 of the 10 rows (a, d, precision, s, st0, sv, sz, t0, v, z); returns
  * validate_parameters(); out[i] = g(rt[i]) if valid, else 1e-10 (likelihood.h:158). */
 int orc_ddm_cell(const double *P, int is_upper, const double *rt, int n, double *out);
+/* measurement aid: {series evaluations, small-time terms, large-time terms} since the last reset */
+void orc_ddm_counters(long long out[3], int reset);
 
 /* --- priors (@hdr/prior.h, @hdr/tnorm.h) ------------------------------------------------------ */
 double orc_tnorm_d(double x, double mean, double sd, double lower, double upper, int log_p);
