@@ -13,8 +13,10 @@
 //     g(rt) = integral over the non-decision range st0 ( integral over the start-point range sz (
 //             closed-form integral over drift variability sv of the lower-boundary density ) )
 // with the reference's midpoint rules and its choice between the small-time and the large-time series
-// (Navarro & Fuss 2009; term counts from get_N).  Operation order follows the object code; what differs
-// from the CPU is only the last-ulp behaviour of exp / sin / log / pow and FMA contraction.
+// (Navarro & Fuss 2009; term counts from get_N).  The term counts and the integration grids -- everything that decides
+// WHICH numbers are added -- follow the object code; the terms themselves are produced with fewer special-function calls
+// (reciprocals instead of divisions, recurrences for the large-time series), which moves results by a few ulp
+// (tests: <= 1e-10 relative on the log density against the oracle, itself bit-identical to the reference's machine code).
 //
 // The header also compiles as plain C++ (GG_HD empty) so tests can check it on the host against the oracle.
 #pragma once
@@ -37,8 +39,9 @@ struct DdmCell {
     double a, v, sv, st0, zr, szr, t_offset; // m_a, m_v, m_sv, m_st0, m_zr, m_szr, m_t_offset
     double int_t0, int_z, var_eps;           // TUNE_INT_T0, TUNE_INT_Z, TUNE_SZ_EPSILON == TUNE_ST0_EPSILON
     double a2, v2, sv2;                      // @hdr/ddm.h:223-225
+    double inv_a2;                           // 1 / a^2: t / a^2 and the factor's division become multiplications
     int valid, no_var;                       // validate_parameters(); sv == 0
-    int pad[4];
+    int pad[2];
 };
 static_assert(sizeof(DdmCell) == 128, "DdmCell is two 64-byte lines");
 
@@ -46,6 +49,7 @@ constexpr double kDdmEpsilon = 1e-6;            // ddm::EPSILON, de.o .rodata+0x
 constexpr double kPi = 3.141592653589793;       // .rodata+0xec8
 constexpr double kTwoPi = 6.283185307179586;    // .rodata+0xec0
 constexpr double kPiSq = 9.869604401089358;     // m_pi2, @hdr/ddm.h:141
+constexpr double kInvPi = 0.3183098861837907;
 
 // the object code converts with cvttsd2si: NaN and out-of-range values give INT_MIN
 GG_HD int ddm_trunc(double x) { return (x >= -2147483648.0 && x < 2147483648.0) ? (int)x : (-2147483647 - 1); }
@@ -69,6 +73,7 @@ GG_HD void ddmcell_build(DdmCell &q, const double *P, bool is_upper)
     q.a2 = q.a * q.a;
     q.v2 = q.v * q.v;
     q.sv2 = q.sv * q.sv;
+    q.inv_a2 = 1.0 / q.a2;
     q.no_var = q.sv == 0;
     bool ok = true; // comparisons are false on NaN, like the reference's
     if (q.a <= 0) ok = false;                         // :232
@@ -80,27 +85,80 @@ GG_HD void ddmcell_build(DdmCell &q, const double *P, bool is_upper)
     if (q.zr + 0.5 * q.szr >= 1.0) ok = false;        // :288
     if (s <= 0) ok = false;                           // :298
     q.valid = ok;
-    q.pad[0] = q.pad[1] = q.pad[2] = q.pad[3] = 0;
+    q.pad[0] = q.pad[1] = 0;
 }
 
-// compute_g_series, @hdr/ddm.h:344-379
+// 1 / sqrt(x) and sin / cos of pi x: the device has cheaper dedicated forms (MUFU.RSQ64H seed + Newton; exact argument
+// reduction for multiples of pi); the host build used by the CPU tests spells them with libm
+GG_HD double ddm_rsqrt(double x)
+{
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+GG_HD void ddm_sincospi(double x, double *s, double *c)
+{
+#ifdef __CUDA_ARCH__
+    sincospi(x, s, c);
+#else
+    *s = sin(kPi * x);
+    *c = cos(kPi * x);
+#endif
+}
+
+// ddm_trunc(ceil(sqrt(x))) -- the form every term count of get_N has -- without the FP64 square root: a float root
+// gives the candidate, two FP64 comparisons make it the smallest k with k^2 >= x.  Outside [0, 1e12) (term counts no
+// sampler state produces) the reference's own expression is evaluated, so NaN / overflow keep their INT_MIN meaning.
+GG_HD int ddm_ceil_sqrt(double x)
+{
+    if (!(x >= 0.0 && x < 1e12)) return ddm_trunc(ceil(sqrt(x)));
+    int k = (int)ceilf(sqrtf((float)x));
+    const double kd = (double)k;
+    if (k > 0 && (kd - 1.0) * (kd - 1.0) >= x) --k;
+    else if (kd * kd < x) ++k;
+    return k;
+}
+
+// compute_g_series, @hdr/ddm.h:344-379.  Same sums as the reference, fewer special-function calls:
+//  * small-time series: the division by 2 t/a^2 of every term becomes one reciprocal;
+//  * large-time series sum_i i exp(-(pi i)^2 ta / 2) sin(pi i zr): exp(.)_i = q^(i^2) with q = exp(-pi^2 ta / 2) is
+//    advanced by two multiplications per term (ratio q^(2i+1)), sin(pi i zr) by the three-term recurrence
+//    s_(i+1) = 2 cos(pi zr) s_i - s_(i-1) -- one exp and one sincospi per evaluation instead of one exp and one sin per
+//    term.  The recurrences' error grows like i^2 ulp; beyond 48 terms (never chosen for a t the small-time series
+//    handles in a handful) the terms are evaluated one by one like the reference does.
 GG_HD double ddm_series(double ta, double zr, bool use_small, int N)
 {
     double sum = 0.0;
     if (use_small) {
-        const double t3 = ta * ta * ta;
-        const double norm = 1.0 / sqrt(t3 * kTwoPi);
-        const double two_ta = ta + ta;
+        const double norm = ddm_rsqrt((ta * ta * ta) * kTwoPi);
+        const double m_inv_two_ta = -0.5 / ta;
         const int hi = N / 2, lo = -(N / 2);
         for (int i = lo; i <= hi; ++i) {
             const double d = ((double)i + (double)i) + zr;
-            sum = exp((-d * d) / two_ta) * d + sum;
+            sum = exp((d * d) * m_inv_two_ta) * d + sum;
         }
         return sum * norm;
     }
+    if (N > 48) {
+        for (int i = 1; i <= N; ++i) {
+            const double d = kPi * (double)i;
+            sum = (double)i * (exp(-0.5 * d * d * ta) * sin(d * zr)) + sum;
+        }
+        return kPi * sum;
+    }
+    double s, c;
+    ddm_sincospi(zr, &s, &c);
+    const double q = exp((-0.5 * kPiSq) * ta), q2 = q * q, two_c = c + c;
+    double e = q, r = q2 * q, s_prev = 0.0;
     for (int i = 1; i <= N; ++i) {
-        const double d = kPi * (double)i;
-        sum = (double)i * (exp(-0.5 * d * d * ta) * sin(d * zr)) + sum;
+        sum = ((double)i * e) * s + sum;
+        e *= r;
+        r *= q2;
+        const double s_next = two_c * s - s_prev;
+        s_prev = s;
+        s = s_next;
     }
     return kPi * sum;
 }
@@ -110,11 +168,11 @@ GG_HD double ddm_factor(const DdmCell &q, double t, double zr)
 {
     double f;
     if (q.no_var) {
-        f = exp((-q.a * zr) * q.v - (0.5 * q.v2) * t) / q.a2;
+        f = exp((-q.a * zr) * q.v - (0.5 * q.v2) * t) * q.inv_a2;
     } else {
         const double denom = 1.0 + q.sv2 * t;
         const double e = (-0.5 * ((q.v2 * t + (q.a * (q.v + q.v)) * zr) - ((q.a2 * zr) * zr) * q.sv2)) / denom;
-        f = exp(e) / (q.a2 * sqrt(denom));
+        f = exp(e) * (q.inv_a2 * ddm_rsqrt(denom));
     }
     return isfinite(f) ? f : 0.0;
 }
@@ -123,24 +181,30 @@ GG_HD double ddm_factor(const DdmCell &q, double t, double zr)
 GG_DDM_FN double ddm_integral_v(const DdmCell &q, double t, double zr)
 {
     if (0 >= t) return 0.0;
-    const double ta = t / q.a2;
+    const double ta = t * q.inv_a2;
     const double factor = ddm_factor(q, t, zr);
     if (factor == 0) return 0.0;
     const double eps = kDdmEpsilon / factor;
-    // get_N, :408-430
-    int nl = ddm_trunc(ceil(1.0 / (kPi * sqrt(t))));
+    // get_N, :408-430: nl = max(ceil(1 / (pi sqrt t)), ceil(sqrt(-2 log(pi ta eps) / (pi^2 ta)))) terms of the large-time
+    // series, ns = ceil(max(sqrt ta + 1, sqrt(-2 ta log(2 eps sqrt(2 pi ta))) + 2)) of the small-time one (ceil and max
+    // commute, and ceil(x + integer) = ceil(x) + integer)
+    int nl = ddm_trunc(ceil(ddm_rsqrt(t) * kInvPi));
     const double pe = (kPi * ta) * eps;
     if (1.0 > pe) {
-        const int k = ddm_trunc(ceil(sqrt((log(pe) * -2.0) / (kPiSq * ta))));
+        const int k = ddm_ceil_sqrt((log(pe) * -2.0) / (kPiSq * ta));
         if (nl < k) nl = k;
     }
     int ns = 2;
     const double rt2 = sqrt(ta * kTwoPi);
     if (1.0 > (rt2 + rt2) * eps) {
-        const double lg = log(rt2 * (eps + eps));
-        const double t1 = sqrt((-2.0 * ta) * lg) + 2.0;
-        const double t2 = sqrt(ta) + 1.0;
-        ns = ddm_trunc(ceil(t2 < t1 ? t1 : t2));
+        const double x1 = (-2.0 * ta) * log(rt2 * (eps + eps));
+        if (ta > 1e-30 && ta < 1e12 && x1 > 1e-30 && x1 < 1e12) {
+            const int k1 = ddm_ceil_sqrt(x1) + 2, k2 = ddm_ceil_sqrt(ta) + 1;
+            ns = k2 < k1 ? k1 : k2;
+        } else { // roots that vanish next to the added integer, overflow, NaN: the reference's expression as it stands
+            const double t1 = sqrt(x1) + 2.0, t2 = sqrt(ta) + 1.0;
+            ns = ddm_trunc(ceil(t2 < t1 ? t1 : t2));
+        }
     }
     const bool use_small = ns < nl;
     return ddm_series(ta, zr, use_small, use_small ? ns : nl) * factor;

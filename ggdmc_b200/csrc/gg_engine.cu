@@ -311,13 +311,15 @@ struct TrialsDev {
         return true;
     }
 
-    void upload(const ggdmc_trials_t *t, int n_cell, bool keep_order)
+    // sort_rt (model type "fastdm"): within a cell the trials are additionally ordered by response time, so that the
+    // 32 trials of a warp need similar series lengths and take the same small-time / large-time branch
+    void upload(const ggdmc_trials_t *t, int n_cell, bool keep_order, bool sort_rt = false)
     {
         require(t && t->n_subject >= 1, "no subjects");
         S = t->n_subject;
         std::vector<int64_t> off(S);
         h_count.resize(S);
-        if (!keep_order && upload_direct(t, n_cell, off)) return;
+        if (!keep_order && !sort_rt && upload_direct(t, n_cell, off)) return;
         std::vector<double> hrt;
         std::vector<uint16_t> hcl;
         if (keep_order) order.resize(S);
@@ -339,12 +341,18 @@ struct TrialsDev {
                 if (i > 0 && t->cell[b + i] < t->cell[b + i - 1]) sorted = false;
             }
             std::vector<int> idx;
-            if (!sorted || keep_order) {
+            if (!sorted || keep_order || sort_rt) {
                 idx.resize(n);
                 std::vector<int> start((size_t)n_cell + 1, 0);
                 for (int i = 0; i < n; ++i) ++start[t->cell[b + i] + 1];
                 for (int c = 0; c < n_cell; ++c) start[c + 1] += start[c];
+                const std::vector<int> first(start);
                 for (int i = 0; i < n; ++i) idx[start[t->cell[b + i]]++] = i;
+                if (sort_rt) {
+                    const double *r = t->rt + b;
+                    for (int c = 0; c < n_cell; ++c)
+                        std::stable_sort(idx.begin() + first[c], idx.begin() + first[c + 1], [r](int x, int y) { return r[x] < r[y]; });
+                }
             }
             off[s] = pos;
             h_count[s] = n;
@@ -744,7 +752,7 @@ struct ggdmc_engine {
         require(pp && pp->npar == D, "p_prior length != model npar");
         p_prior.upload(pp);
         pt.lap("  model");
-        trials.upload(t, m->n_cell, false);
+        trials.upload(t, m->n_cell, false, m->type == GGDMC_MODEL_DDM);
         pt.lap("  trials");
         S = t->n_subject;
         trials.set_chunking((int64_t)R * S * C);
@@ -1455,7 +1463,7 @@ int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *t
     ModelDev M;
     M.upload(model);
     TrialsDev T;
-    T.upload(trials, model->n_cell, true);
+    T.upload(trials, model->n_cell, true, model->type == GGDMC_MODEL_DDM);
     const int ntr = T.h_count[0];
     DBuf<double> d_theta, d_out;
     d_theta.upload(theta, (size_t)n_theta * model->npar);
@@ -1488,7 +1496,7 @@ void sumloglike_impl(const ggdmc_model_t *model, const ggdmc_trials_t *trials, c
     ModelDev M;
     M.upload(model);
     TrialsDev T;
-    T.upload(trials, model->n_cell, false);
+    T.upload(trials, model->n_cell, false, model->type == GGDMC_MODEL_DDM);
     T.d.zero_floor = zero_floor;
     const int S = T.S, D = model->npar;
     T.set_chunking((int64_t)S * n_theta);
