@@ -512,12 +512,12 @@ void launch_like_n(const Level &L, const DevModel &M, const TrialData &T, const 
     }
 }
 
-// model type "fastdm": same grid and arguments as k_like; 128 threads x 4 blocks/SM (the series and midpoint-rule
-// loops want registers, not occupancy)
-void launch_like_ddm(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
-                     double *ll_part, cudaStream_t st, const int *prio)
+// model type "fastdm": same grid and arguments as k_like.  Launch shape (threads per block, minimum resident blocks per
+// SM) picked by measurement (profiles/r01_k_like_ddm.md); GGDMC_B200_DDM_VARIANT overrides it for experiments.
+template <int BLOCK, int MINB>
+void launch_like_ddm_t(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
+                       double *ll_part, cudaStream_t st, const int *prio)
 {
-    constexpr int BLOCK = 128, MINB = 4;
     const int per_pop = step >= 0 ? 1 : (half < 0 ? L.nchain : (L.nchain + 1) / 2);
     dim3 grid(L.npop * per_pop, T.nsplit);
     const size_t sm = ((size_t)M.n_cell * sizeof(DdmCell) + (size_t)(BLOCK / 32) * 8 + 15) & ~(size_t)15;
@@ -531,6 +531,24 @@ void launch_like_ddm(const Level &L, const DevModel &M, const TrialData &T, cons
     cfg.attrs = at;
     cfg.numAttrs = prio ? 1 : 0;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_like_ddm<BLOCK, MINB>, L, M, T, d_iter, sweep, step, half, ll_part));
+}
+
+constexpr int kDdmDefaultVariant = 1; // 128 threads x 6 blocks/SM (80 registers): +20 % over 4 blocks, 8 blocks (64 registers) spill too much
+void launch_like_ddm(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
+                     double *ll_part, cudaStream_t st, const int *prio)
+{
+    static const int v = [] {
+        const char *e = std::getenv("GGDMC_B200_DDM_VARIANT");
+        const int x = e ? std::atoi(e) : kDdmDefaultVariant;
+        return (x < 0 || x > 4) ? kDdmDefaultVariant : x;
+    }();
+    switch (v) {
+    case 1: launch_like_ddm_t<128, 6>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 2: launch_like_ddm_t<128, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 3: launch_like_ddm_t<64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 4: launch_like_ddm_t<64, 16>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    default: launch_like_ddm_t<128, 4>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio);
+    }
 }
 
 void launch_like(const Level &L, const ModelDev &MD, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,

@@ -80,30 +80,36 @@ def sweep_model():
 DDM_PNAMES = ["a", "st0", "sv", "sz", "t0", "v.s1", "v.s2", "z"]
 
 
-def ddm_model(precision: float = 3.0, s: float = 1.0):
+def ddm_model(precision: float = 3.0, s: float = 1.0, fixed=()):
     """A 4-cell DDM design (model type "fastdm"): stimulus S (s1, s2) x response R (r1, r2), drift rate by stimulus,
-    r2 = upper boundary; free parameters DDM_PNAMES, constants d = 0, precision, s.  Rows follow model.DDM_CORE.
+    r2 = upper boundary; free parameters DDM_PNAMES minus `fixed` (names held at the constant 0, the usual way to switch a
+    variability off), further constants d = 0, precision, s.  Rows follow model.DDM_CORE.
     Returns (cell table, p_vector, uniform prior)."""
     from .model import DDM_CORE
-    cnames = ["d", "precision", "s"]
+    pnames = [n for n in DDM_PNAMES if n not in fixed]
+    cnames = ["d", "precision", "s"] + [n for n in DDM_PNAMES if n in fixed]
     src = np.zeros((4, len(DDM_CORE), 2), dtype=np.int32)
     for c in range(4):
         for r, core in enumerate(DDM_CORE):
             name = f"v.s{c // 2 + 1}" if core == "v" else core
-            src[c, r, :] = DDM_PNAMES.index(name) if name in DDM_PNAMES else -1 - cnames.index(name)
-    ct = CellTable(2, 4, len(DDM_PNAMES), src, np.array([0.0, precision, s]), np.array([0, 1, 0, 1], dtype=np.uint8),
-                   list(DDM_PNAMES), ["s1.r1", "s1.r2", "s2.r1", "s2.r2"], "fastdm")
-    p_vector = np.array([1.2, 0.1, 0.6, 0.2, 0.2, -1.8, 1.8, 0.6])
-    lo = np.array([0.2, 0.0, 0.0, 0.0, 0.0, -6.0, -6.0, 0.05])
-    hi = np.array([4.0, 0.5, 3.0, 1.0, 0.6, 6.0, 6.0, 3.5])
-    n = len(lo)
-    prior = PriorTable(n, lo, hi, np.zeros(n), np.zeros(n), np.full(n, 6, dtype=np.int32), np.ones(n, dtype=np.uint8), list(DDM_PNAMES))
-    return ct, p_vector, prior
+            src[c, r, :] = pnames.index(name) if name in pnames else -1 - cnames.index(name)
+    const = np.array([0.0, precision, s] + [0.0] * (len(cnames) - 3))
+    ct = CellTable(2, 4, len(pnames), src, const, np.array([0, 1, 0, 1], dtype=np.uint8), list(pnames),
+                   ["s1.r1", "s1.r2", "s2.r1", "s2.r2"], "fastdm")
+    full = dict(zip(DDM_PNAMES, [1.2, 0.1, 0.6, 0.2, 0.2, -1.8, 1.8, 0.6]))
+    lo = dict(zip(DDM_PNAMES, [0.2, 0.0, 0.0, 0.0, 0.0, -6.0, -6.0, 0.05]))
+    hi = dict(zip(DDM_PNAMES, [4.0, 0.5, 3.0, 1.0, 0.6, 6.0, 6.0, 3.5]))
+    n = len(pnames)
+    prior = PriorTable(n, np.array([lo[k] for k in pnames]), np.array([hi[k] for k in pnames]), np.zeros(n), np.zeros(n),
+                       np.full(n, 6, dtype=np.int32), np.ones(n, dtype=np.uint8), list(pnames))
+    return ct, np.array([full[k] for k in pnames]), prior
 
 
-def ddm_simulate(theta: np.ndarray, n_per_stim: int, rng: np.random.Generator, dt: float = 1e-3, s: float = 1.0) -> Trials:
-    """Euler-Maruyama simulation of ddm_model()'s design (synthetic inputs only): trials grouped by cell."""
-    p = dict(zip(DDM_PNAMES, theta))
+def ddm_simulate(theta: np.ndarray, n_per_stim: int, rng: np.random.Generator, dt: float = 1e-3, s: float = 1.0, pnames=None) -> Trials:
+    """Euler-Maruyama simulation of ddm_model()'s design (synthetic inputs only): trials grouped by cell.
+    `pnames` names the entries of theta (default DDM_PNAMES); parameters not named are 0."""
+    p = dict.fromkeys(DDM_PNAMES, 0.0)
+    p.update(zip(pnames or DDM_PNAMES, theta))
     rts, cells = [], []
     for stim in range(2):
         v = p[f"v.s{stim + 1}"] + p["sv"] * rng.standard_normal(n_per_stim)

@@ -17,19 +17,16 @@ F_SMALL, F_LARGE = 37.0, 60.0             # one small-time term (exp + div), one
 F_TRIAL = 30.0                            # rt - t_offset, log (or its running-product twin), sum
 
 only = sys.argv[1] if len(sys.argv) > 1 else None
-ct, p_vector, prior = W.ddm_model()
-om = ob.OModel(ct.param_src, ct.const_val, ct.posdrift, ct.npar, type=ob.MODEL_DDM)
 rng = np.random.default_rng(20260105)
-nchain = 3 * ct.npar
 peak = E.measure_fp64_tflops()
 print(f"FP64 FMA peak measured on this GPU: {peak:.2f} TFLOP/s")
 for name, zero, S, reps in (("no variability", ("st0", "sv", "sz"), 256, 10), ("sv", ("st0", "sz"), 256, 10), ("sv+sz+st0", (), 32, 3)):
     if only and only != name:
         continue
-    truth = p_vector.copy()
-    for z in zero:
-        truth[W.DDM_PNAMES.index(z)] = 0.0
-    pool = W.ddm_simulate(truth, 6000, rng)
+    ct, truth, prior = W.ddm_model(fixed=zero)  # a variability that is off is a constant 0, not a free parameter
+    om = ob.OModel(ct.param_src, ct.const_val, ct.posdrift, ct.npar, type=ob.MODEL_DDM)
+    nchain = 3 * ct.npar
+    pool = W.ddm_simulate(truth, 6000, rng, pnames=ct.pnames)
     subjects = []
     for s_ in range(S):
         idx = np.sort(rng.choice(len(pool.rt), 768, replace=False))
