@@ -9,7 +9,8 @@
  * tests/testthat/Group1/data/lba_data[2-6].rda (the .npz files under tests/golden/, made by
  * tests/golden/make_golden.py), (2) against the reference's own object code src/de.o linked into
  * oracle/_ref/libggdmc_ref.so (lba_class::dlba, tnorm_class, de_class::get_chains/get_subchains,
- * de_class::crossover/migration under an injected uniform stream).
+ * de_class::crossover/migration under an injected uniform stream; for the DDM ("fastdm") family:
+ * likelihood_class::ddm_likelihood and de_class::run_chains on a "fastdm" likelihood object -- bit-identical).
  */
 #ifndef GGDMC_ORACLE_H
 #define GGDMC_ORACLE_H
