@@ -162,3 +162,23 @@ def ddm_prior(kind="sub"):
     dist, logp = np.full(n, 6, np.int32), np.ones(n, np.uint8)
     return (PriorTable(n, lo.copy(), hi.copy(), np.zeros(n), np.zeros(n), dist, logp, list(DDM_PNAMES)),
             ob.OPrior(lo, hi, np.zeros(n), np.zeros(n), dist, logp))
+
+
+def ddm_objects(rt=None, cell=None):
+    """The reference-style `model` / `dmi` objects (ggdmc_b200.api mirrors) of the 4-cell DDM design above:
+    model_boolean [ncell x n_pxc x n_acc] with one TRUE per (cell, core parameter, accumulator), type "fastdm",
+    dmi@is_positive_drift per CELL (upper-boundary response)."""
+    pxc = ["a", "d", "precision", "s", "st0", "sv", "sz", "t0", "v.s1", "v.s2", "z"]
+    cells = ["s1.r1", "s1.r2", "s2.r1", "s2.r2"]
+    mb = np.zeros((4, len(pxc), 2), dtype=bool)
+    for c in range(4):
+        for k, name in enumerate(pxc):
+            mb[c, k, :] = (name == f"v.s{c // 2 + 1}") if name.startswith("v.") else True
+    model = api.Model(parameter_x_condition_names=pxc, pnames=list(DDM_PNAMES), cell_names=cells,
+                      constants=api.NamedVector(list(DDM_CONST.values()), list(DDM_CONST)), model_boolean=mb, type="fastdm",
+                      npar=len(DDM_PNAMES))
+    node_1 = np.array([[0, 1], [1, 0], [0, 1], [1, 0]])
+    data = None
+    if rt is not None:
+        data = api.NamedList({cells[c]: np.asarray(rt)[np.asarray(cell) == c] for c in np.unique(cell)})
+    return model, api.DMI(model=model, data=data, node_1_index=node_1, is_positive_drift=np.array([False, True, False, True]))

@@ -98,7 +98,7 @@ int gh_flatten_model(void *dmi, int *param_src, long cap, int *dims /* n_acc, n_
         FlatModel m = flatten_model(Rcpp::S4(*static_cast<RObject *>(dmi)));
         if ((long)m.param_src.size() > cap) return -2;
         for (size_t i = 0; i < m.param_src.size(); ++i) param_src[i] = m.param_src[i];
-        dims[0] = m.c.n_acc; dims[1] = m.c.n_cell; dims[2] = m.c.npar; dims[3] = m.c.n_const;
+        dims[0] = m.c.n_acc; dims[1] = m.c.n_cell; dims[2] = m.c.npar; dims[3] = m.c.n_const + 1000 * m.c.type; // model type in the thousands
         return 0;
     } catch (const std::exception &e) { g_err = e.what(); return -1; }
 }

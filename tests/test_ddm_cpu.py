@@ -191,3 +191,26 @@ def test_ddm_run_chains_bitwise_vs_reference_object_code(pblocked):
     assert np.array_equal(ot, pop.out_theta) and np.array_equal(olp, pop.out_lp) and np.array_equal(oll, pop.out_ll)
     assert not np.array_equal(ot[0], ot[-1])
     assert np.all(np.isfinite(oll[-1]))
+
+
+def test_ddm_model_objects_flatten_to_the_cell_table():
+    """model@type "fastdm": build_cell_table (Python mirror) and the Rcpp glue's flatten_model (compiled against the Rcpp
+    stand-in) turn model_boolean + constants + pnames into the 10-row table the engine takes, is_positive_drift per cell."""
+    import glue_mock as G
+    from ggdmc_b200.model import build_cell_table
+    from helpers import ddm_objects
+    ct, om = ddm_model()
+    rng = np.random.default_rng(2)
+    d = _grid_data(rng, 60)
+    model, dmi = ddm_objects(d.rt, d.cell)
+    got = build_cell_table(model, dmi.node_1_index, dmi.is_positive_drift)
+    assert got.type == "fastdm" and got.param_src.shape == (4, 10, 2)
+    assert np.array_equal(got.param_src, ct.param_src) and np.array_equal(got.posdrift, ct.posdrift)
+    assert np.array_equal(got.const_val, ct.const_val) and got.pnames == ct.pnames
+    n = ct.param_src.size
+    buf, dims = (C.c_int * n)(), (C.c_int * 4)()
+    assert G.lib().gh_flatten_model(G.r_dmi(dmi), buf, n, dims) == 0, G.lib().gh_last_error()
+    assert list(dims) == [ct.n_acc, ct.n_cell, ct.npar, 3 + 1000 * 1]  # 3 constants, type GGDMC_MODEL_DDM
+    assert np.array_equal(np.array(buf[:]).reshape(ct.param_src.shape), ct.param_src)
+    with pytest.raises(ValueError, match="is_positive_drift"):  # per-accumulator flags are the LBA's convention
+        build_cell_table(model, dmi.node_1_index, np.array([True, True]))

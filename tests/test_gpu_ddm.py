@@ -209,3 +209,70 @@ def test_undefined_model_type_is_an_error():
     err = C.create_string_buffer(256)
     rc = B.lib().ggdmc_b200_trial_logdens(C.byref(m.c), C.byref(t.c), B.ptr(th), 1, B.ptr(out), err)
     assert rc == B.ERR_ARG and b"Undefined model type" in err.value
+
+
+def test_ddm_full_size_properties():
+    """Size-independent properties at a size the oracle does not finish in seconds (64 subjects x 2048 trials x 24
+    parameter vectors, drift variability on): the sum over trials is additive over a split of a subject's trials and
+    invariant under a permutation of them (the engine regroups by cell and response time on upload), a subject's sums do
+    not depend on its neighbours, and three spot checks against the oracle."""
+    from ggdmc_b200 import workloads as W
+    rng = np.random.default_rng(77)
+    ct, truth, prior = W.ddm_model(fixed=("st0", "sz"))
+    om = ob.OModel(ct.param_src, ct.const_val, ct.posdrift, ct.npar, type=ob.MODEL_DDM)
+    pool = W.ddm_simulate(truth, 8000, rng, pnames=ct.pnames)
+    S, K, n = 64, 24, 2048
+    subj = []
+    for _ in range(S):
+        idx = rng.choice(len(pool.rt), n, replace=False)
+        subj.append(Trials(pool.rt[idx].copy(), pool.cell[idx].copy()))  # deliberately NOT grouped by cell
+    theta = truth[None, None, :] * (1.0 + 0.03 * rng.uniform(-1, 1, size=(S, K, ct.npar)))
+    full = E.sumloglike(ct, subj, theta)
+    assert np.all(np.isfinite(full))
+    halves_a = [Trials(t.rt[: n // 3].copy(), t.cell[: n // 3].copy()) for t in subj]   # ragged split
+    halves_b = [Trials(t.rt[n // 3:].copy(), t.cell[n // 3:].copy()) for t in subj]
+    split = E.sumloglike(ct, halves_a, theta) + E.sumloglike(ct, halves_b, theta)
+    assert np.all(np.abs(split - full) <= 1e-11 * np.abs(full))
+    perm = [rng.permutation(n) for _ in range(S)]
+    shuffled = E.sumloglike(ct, [Trials(t.rt[p].copy(), t.cell[p].copy()) for t, p in zip(subj, perm)], theta)
+    assert np.array_equal(shuffled, full)  # same device order after the upload's (cell, rt) ordering -> same bits
+    alone = E.sumloglike(ct, subj[5:6], theta[5:6])
+    assert np.array_equal(alone[0], full[5])
+    for s, c in ((0, 0), (17, 9), (63, 23)):
+        ref = ob.sumloglike(om, ob.OData(subj[s].rt, subj[s].cell), theta[s, c])
+        assert abs(full[s, c] - ref) <= 1e-10 * abs(ref)
+
+
+def test_ddm_through_reference_interface():
+    """model@type "fastdm" through the Python mirror of the reference interface: initialise_theta scores its candidates
+    with the DDM likelihood under the R-side rule, run_subject returns a posterior with the reference's slots, feeding it
+    back continues from its last slice, and the same call through the engine layer gives the same bits."""
+    from ggdmc_b200 import api, init
+    from helpers import DDM_PNAMES, ddm_objects
+    rng = np.random.default_rng(23)
+    ct, om = ddm_model()
+    truth = ddm_theta(rng, 1)
+    rt, cell = ddm_simulate(truth, 80, rng)
+    model, dmi = ddm_objects(rt, cell)
+    pt, op = ddm_prior()
+    D, nchain, nmc, thin = ct.npar, 3 * ct.npar, 5, 2
+    prior = api.Prior(nparameter=D, pnames=list(DDM_PNAMES), p_prior=api.prior_list(pt))
+    ti = api.ThetaInput(nmc=nmc, nchain=nchain, thin=thin, nparameter=D, pnames=list(DDM_PNAMES))
+    de = api.DEInput(sub_migration_prob=0.06, nparameter=D, nchain=nchain)
+    cfg = api.Config(prior=prior, theta_input=ti, de_input=de, seed=11)
+    st = init.initialise_theta(ti, prior, dmi, seed=3)
+    od = ob.OData(rt, cell)
+    assert np.all(np.isfinite(st.theta[:, :, 0])) and np.all(np.isfinite(st.log_likelihoods[:, 0]))
+    for c in range(nchain):  # trial-by-trial form of the R rule (DESIGN.md): a density <= 0 counts as .Machine$double.eps
+        ld = ob.trial_logdens(om, od, st.theta[:, c, 0])
+        ref = np.where(ld <= LOG_DBL_MIN, np.log(np.finfo(float).eps), ld).sum()
+        assert abs(st.log_likelihoods[c, 0] - ref) <= 1e-9 * abs(ref)
+    fit = api.run_subject(cfg, dmi, st)
+    assert fit.theta.shape == (D, nchain, nmc) and fit.pnames == list(DDM_PNAMES) and fit.nmc == nmc and fit.thin == thin
+    assert np.array_equal(fit.theta[:, :, 0], st.theta[:, :, 0]) and not np.array_equal(fit.theta[:, :, 0], fit.theta[:, :, -1])
+    again = api.run_subject(cfg, dmi, fit)
+    assert np.array_equal(again.theta[:, :, 0], fit.theta[:, :, -1])
+    tun = E.Tuning(nmc=nmc, nchain=nchain, thin=thin, nparameter=D, sub_migration_prob=0.06, seeds=[11])
+    start = E.PopState(st.theta[:, :, 0].T[None].copy(), st.summed_log_prior[:, 0][None].copy(), st.log_likelihoods[:, 0][None].copy())
+    out = E.run_subject(ct, Trials(od.rt.copy(), od.cell.copy()), pt, tun, start)
+    assert np.array_equal(np.transpose(out.theta[0], (2, 1, 0)), fit.theta)
