@@ -237,7 +237,7 @@ def test_ddm_full_size_properties():
     shuffled = E.sumloglike(ct, [Trials(t.rt[p].copy(), t.cell[p].copy()) for t, p in zip(subj, perm)], theta)
     assert np.array_equal(shuffled, full)  # same device order after the upload's (cell, rt) ordering -> same bits
     alone = E.sumloglike(ct, subj[5:6], theta[5:6])
-    assert np.array_equal(alone[0], full[5])
+    assert np.all(np.abs(alone[0] - full[5]) <= 1e-13 * np.abs(full[5]))  # a lone subject is split into more trial chunks
     for s, c in ((0, 0), (17, 9), (63, 23)):
         ref = ob.sumloglike(om, ob.OData(subj[s].rt, subj[s].cell), theta[s, c])
         assert abs(full[s, c] - ref) <= 1e-10 * abs(ref)
