@@ -101,7 +101,7 @@ def test_reference_errors_surface():
     with pytest.raises(B.GgdmcError, match="three or more chains"):
         api.run_subject(cfg, dmi_of("sub"), st)
     bad = dmi_of("sub")
-    bad.model = api.Model(model.parameter_x_condition_names, model.pnames, model.cell_names, model.constants, model.model_boolean, type="fastdm")
+    bad.model = api.Model(model.parameter_x_condition_names, model.pnames, model.cell_names, model.constants, model.model_boolean, type="ddm2")
     with pytest.raises(B.GgdmcError, match="Undefined model type"):
         api.run_subject(cfg, bad, st)
 
