@@ -214,3 +214,47 @@ def test_ddm_model_objects_flatten_to_the_cell_table():
     assert np.array_equal(np.array(buf[:]).reshape(ct.param_src.shape), ct.param_src)
     with pytest.raises(ValueError, match="is_positive_drift"):  # per-accumulator flags are the LBA's convention
         build_cell_table(model, dmi.node_1_index, np.array([True, True]))
+
+
+@needs_ref
+def test_ddm_run_hchains_bitwise_vs_reference_object_code():
+    """de_class::run_hchains of src/de.o (src/de.cpp:272-383) with "fastdm" likelihood objects for every subject --
+    phi step, subject steps under phi-driven truncated-normal priors, migration at both levels -- vs orc_run_hier:
+    every stored sample of phi and of every subject bit-identical, same number of uniforms consumed."""
+    ob.ref2_prime()
+    ct, om = ddm_model()
+    rng = np.random.default_rng(8)
+    S, D = 3, ct.npar
+    center = ddm_theta(rng, 1)
+    truths = [center * (1.0 + 0.05 * rng.standard_normal(D)) for _ in range(S)]
+    datas = [ob.OData(*ddm_simulate(t, 40, rng)) for t in truths]
+    lower = np.array([0.0, 0.0, 0.0, 0.0, 0.0, -20.0, -20.0, 0.0])
+    p0, p1 = center.copy(), 0.3 * np.abs(center) + 0.1
+    opp = ob.OPrior(p0, p1, lower, np.full(D, np.inf), np.full(D, 1, np.int32), np.ones(D, np.uint8))
+    ohp = ob.OPrior(np.concatenate([center - 3.0, np.full(D, 0.01)]), np.concatenate([center + 3.0, np.full(D, 3.0)]), np.zeros(2 * D),
+                    np.zeros(2 * D), np.full(2 * D, 6, np.int32), np.ones(2 * D, np.uint8))
+    nchain, nmc, thin = 2 * 2 * D, 3, 2
+    phi0 = np.concatenate([p0, p1])[None, :] * (1.0 + 0.05 * rng.standard_normal((nchain, 2 * D)))
+    subj = []
+    for s in range(S):
+        th = truths[s][None, :] * (1.0 + 0.03 * rng.standard_normal((nchain, D)))
+        lp = np.array([ob.sumlogprior(opp, th[c], phi0[c, :D], phi0[c, D:]) for c in range(nchain)])
+        ll = np.array([ob.sumloglike(om, datas[s], th[c]) for c in range(nchain)])
+        subj.append((th, lp, ll))
+    lp0 = np.array([ob.sumlogprior(ohp, phi0[c]) for c in range(nchain)])
+    ll0 = np.array([sum(ob.sumlogprior(opp, subj[s][0][c], phi0[c, :D], phi0[c, D:]) for s in range(S)) for c in range(nchain)])
+    kw = dict(pop_migration_prob=0.3, sub_migration_prob=0.3)
+    u = ob.ref2_set_stream(rng.uniform(size=1500000))
+    (pt, plp, pll), subs = ob.ref2_run_hchains(2 * D, om, datas, opp, ohp, (phi0, lp0, ll0), subj, nmc, thin, **kw)
+    used = ob.ref_lib().ref_uniform_stream_pos()
+    ob.ref_lib().ref2_set_model_type(0)
+    phi = ob.OPop(phi0, lp0, ll0, nmc, thin)
+    pops = [ob.OPop(*s, nmc, thin) for s in subj]
+    r = ob.make_rng(stream=u)
+    ob.run_hier(ob.make_de(2 * D, nchain, **kw), phi, pops, opp, ohp, om, datas, r, (nmc - 1) * thin)
+    assert r.pos == used
+    assert np.array_equal(pt, phi.out_theta) and np.array_equal(plp, phi.out_lp) and np.array_equal(pll, phi.out_ll)
+    for s in range(S):
+        assert np.array_equal(subs[s][0], pops[s].out_theta) and np.array_equal(subs[s][1], pops[s].out_lp)
+        assert np.array_equal(subs[s][2], pops[s].out_ll)
+    assert not np.array_equal(pt[0], pt[-1])
