@@ -21,7 +21,6 @@
 // The header also compiles as plain C++ (GG_HD empty) so tests can check it on the host against the oracle.
 #pragma once
 #include "gg_math.cuh"
-#include "gg_fastmath.cuh"
 #include <stdint.h>
 
 // the series evaluation is called from inside both midpoint rules: one out-of-line copy instead of four inlined ones
@@ -123,7 +122,6 @@ GG_HD int ddm_ceil_sqrt(double x)
 }
 
 // compute_g_series, @hdr/ddm.h:344-379.  Same sums as the reference, fewer special-function calls:
-//  * every exponential is fm::exp_cm (gg_fastmath.cuh: coefficients as constant-bank operands, <= 1 ulp);
 //  * small-time series: the division by 2 t/a^2 of every term becomes one reciprocal;
 //  * large-time series sum_i i exp(-(pi i)^2 ta / 2) sin(pi i zr): exp(.)_i = q^(i^2) with q = exp(-pi^2 ta / 2) is
 //    advanced by two multiplications per term (ratio q^(2i+1)), sin(pi i zr) by the three-term recurrence
@@ -139,7 +137,7 @@ GG_HD double ddm_series(double ta, double zr, bool use_small, int N)
         const int hi = N / 2, lo = -(N / 2);
         for (int i = lo; i <= hi; ++i) {
             const double d = ((double)i + (double)i) + zr;
-            sum = fm::exp_cm((d * d) * m_inv_two_ta) * d + sum;
+            sum = exp((d * d) * m_inv_two_ta) * d + sum;
         }
         return sum * norm;
     }
@@ -152,7 +150,7 @@ GG_HD double ddm_series(double ta, double zr, bool use_small, int N)
     }
     double s, c;
     ddm_sincospi(zr, &s, &c);
-    const double q = fm::exp_cm((-0.5 * kPiSq) * ta), q2 = q * q, two_c = c + c;
+    const double q = exp((-0.5 * kPiSq) * ta), q2 = q * q, two_c = c + c;
     double e = q, r = q2 * q, s_prev = 0.0;
     for (int i = 1; i <= N; ++i) {
         sum = ((double)i * e) * s + sum;
@@ -170,11 +168,11 @@ GG_HD double ddm_factor(const DdmCell &q, double t, double zr)
 {
     double f;
     if (q.no_var) {
-        f = fm::exp_cm((-q.a * zr) * q.v - (0.5 * q.v2) * t) * q.inv_a2;
+        f = exp((-q.a * zr) * q.v - (0.5 * q.v2) * t) * q.inv_a2;
     } else {
         const double denom = 1.0 + q.sv2 * t;
         const double e = (-0.5 * ((q.v2 * t + (q.a * (q.v + q.v)) * zr) - ((q.a2 * zr) * zr) * q.sv2)) / denom;
-        f = fm::exp_cm(e) * (q.inv_a2 * ddm_rsqrt(denom));
+        f = exp(e) * (q.inv_a2 * ddm_rsqrt(denom));
     }
     return isfinite(f) ? f : 0.0;
 }

@@ -53,10 +53,6 @@ void hm_norm_pair(const double *z, int n, double *cdf, double *pdf)
     }
 }
 double hm_rcp_pos(double d) { return gg::fm::rcp_pos(d); }
-void hm_exp_cm(const double *x, int n, double *out)
-{
-    for (int i = 0; i < n; ++i) out[i] = gg::fm::exp_cm(x[i]);
-}
 void hm_norm_cdf_lowlatency(const double *z, int n, double *cdf)
 {
     for (int i = 0; i < n; ++i) cdf[i] = gg::fm::norm_cdf_lowlatency(z[i]);
