@@ -276,3 +276,36 @@ def test_ddm_through_reference_interface():
     start = E.PopState(st.theta[:, :, 0].T[None].copy(), st.summed_log_prior[:, 0][None].copy(), st.log_likelihoods[:, 0][None].copy())
     out = E.run_subject(ct, Trials(od.rt.copy(), od.cell.copy()), pt, tun, start)
     assert np.array_equal(np.transpose(out.theta[0], (2, 1, 0)), fit.theta)
+
+
+def test_ddm_single_subject_posterior_recovers_generating_values():
+    """Check 3 for the DDM, in the form that does not repeat what the LBA tests establish (schedule equivalence is a
+    property of the sampler, tests/test_gpu_posterior.py; chain-for-chain identity with the oracle is the trajectory test
+    above): a 6-parameter DDM fit (600 simulated trials, 18 chains, 4 replicates, default schedule) converges
+    (R-hat < 1.05), the replicates agree with each other, and the generating values lie inside every marginal."""
+    from ggdmc_b200 import workloads as W
+    from test_gpu_posterior import rhat, summaries
+    ct, truth, prior = W.ddm_model(fixed=("st0", "sz"))
+    om = ob.OModel(ct.param_src, ct.const_val, ct.posdrift, ct.npar, type=ob.MODEL_DDM)
+    oprior = ob.OPrior(prior.p0, prior.p1, prior.lower, prior.upper, prior.dist, prior.log_p)
+    rng = np.random.default_rng(404)
+    tr = W.ddm_simulate(truth, 300, rng, pnames=ct.pnames)
+    od = ob.OData(tr.rt, tr.cell)
+    D, C, R, thin = ct.npar, 3 * ct.npar, 4, 4
+    th = truth[None, None, :] * (1.0 + 0.1 * rng.standard_normal((R, C, D)))
+    lp = np.array([[ob.sumlogprior(oprior, t) for t in th[r]] for r in range(R)])
+    ll = E.sumloglike(ct, [tr] * R, th)
+    st = E.PopState(th, lp, ll)
+    burn = E.run_subject(ct, tr, prior, E.Tuning(nmc=251, nchain=C, thin=thin, nparameter=D, sub_migration_prob=0.06,
+                                                  seeds=[200 + r for r in range(R)]), st)
+    fit = E.run_subject(ct, tr, prior, E.Tuning(nmc=601, nchain=C, thin=thin, nparameter=D, seeds=[1200 + r for r in range(R)]),
+                        E.PopState(burn.theta[:, -1], burn.lp[:, -1], burn.ll[:, -1]))
+    x = fit.theta[:, 1:]  # [R, n, C, D]
+    assert np.all(np.isfinite(x)) and np.all(np.isfinite(fit.ll))
+    assert max(rhat(x[r]).max() for r in range(R)) < 1.05
+    s = np.stack([summaries(x[r]) for r in range(R)])  # [R, 4, D]
+    sd = x.reshape(-1, D).std(0)
+    assert np.all(np.abs(s - s.mean(0)) <= 0.35 * sd), (s, sd)  # replicate-to-replicate spread of mean / quantiles
+    flat = x.reshape(-1, D)
+    lo, hi = np.quantile(flat, 0.0005, axis=0), np.quantile(flat, 0.9995, axis=0)
+    assert np.all((truth > lo) & (truth < hi)), (truth, lo, hi)
