@@ -62,6 +62,7 @@ void hm_norm_cdf_lowlatency(const double *z, int n, double *cdf)
 #include "../../ggdmc_b200/csrc/gg_ddm.cuh"
 extern "C" {
 // P = column 0 of the ten DDM rows (a, d, precision, s, st0, sv, sz, t0, v, z); returns validate_parameters()
+int hm_ddm_ceil_sqrt(double x) { return gg::ddm_ceil_sqrt(x); }
 int hm_ddm_cell(const double *P, int is_upper, const double *rt, int n, double *out)
 {
     gg::DdmCell q;

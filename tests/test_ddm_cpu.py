@@ -258,3 +258,28 @@ def test_ddm_run_hchains_bitwise_vs_reference_object_code():
         assert np.array_equal(subs[s][0], pops[s].out_theta) and np.array_equal(subs[s][1], pops[s].out_lp)
         assert np.array_equal(subs[s][2], pops[s].out_ll)
     assert not np.array_equal(pt[0], pt[-1])
+
+
+def test_ddm_integer_ceil_sqrt_equals_the_reference_expression(hostmath):
+    """gg::ddm_ceil_sqrt (float root + two FP64 comparisons) against ceil(sqrt(x)) as get_N writes it (@hdr/ddm.h:413,
+    421-423): equal everywhere except within one rounding of a perfect square from above -- where sqrt() rounds down onto
+    the integer and the reference's ceil stays one short of the exact answer -- and with the reference's INT_MIN for NaN,
+    negative and huge arguments."""
+    H = hostmath
+    H.hm_ddm_ceil_sqrt.argtypes = [C.c_double]
+    H.hm_ddm_ceil_sqrt.restype = C.c_int
+    rng = np.random.default_rng(12)
+    xs = np.concatenate([rng.uniform(0, 50, 20000), 10.0 ** rng.uniform(-300, 11.9, 20000), rng.integers(0, 2000, 4000).astype(float) ** 2,
+                         [0.0, 1e-320, 1.0, 4.0, 1e12, 1e13, 1e300, np.inf, -1.0, -1e-300, np.nan]])
+    squares = rng.integers(1, 100000, 4000).astype(float) ** 2
+    xs = np.concatenate([xs, np.nextafter(squares, 0), np.nextafter(squares, np.inf)])
+    n_diff = 0
+    for x in xs:
+        got = H.hm_ddm_ceil_sqrt(float(x))
+        r = np.ceil(np.sqrt(x)) if x >= 0 else np.nan
+        want = int(r) if np.isfinite(r) and abs(r) < 2 ** 31 else -2 ** 31
+        if got != want:  # only just above a perfect square k^2, where the exact answer is k + 1 and sqrt() rounds to k
+            k = round(float(np.sqrt(x)))
+            assert got == want + 1 == k + 1 and x > k * k and np.sqrt(x) == k, (x, got, want)
+            n_diff += 1
+    assert n_diff <= 4000  # the nextafter(k^2, inf) probes
