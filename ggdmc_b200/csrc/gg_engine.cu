@@ -540,9 +540,12 @@ void launch_like_ddm(const Level &L, const DevModel &M, const TrialData &T, cons
     static const int v = [] {
         const char *e = std::getenv("GGDMC_B200_DDM_VARIANT");
         const int x = e ? std::atoi(e) : kDdmDefaultVariant;
-        return (x < 0 || x > 4) ? kDdmDefaultVariant : x;
+        return (x < 0 || x > 7) ? kDdmDefaultVariant : x;
     }();
     switch (v) {
+    case 5: launch_like_ddm_t<128, 5>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 6: launch_like_ddm_t<256, 3>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
+    case 7: launch_like_ddm_t<96, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
     case 1: launch_like_ddm_t<128, 6>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
     case 2: launch_like_ddm_t<128, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
     case 3: launch_like_ddm_t<64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;

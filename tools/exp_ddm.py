@@ -16,12 +16,12 @@ F_EVAL_NOVAR, F_EVAL_VAR = 205.0, 231.0   # one series evaluation without its te
 F_SMALL, F_LARGE = 37.0, 60.0             # one small-time term (exp + div), one large-time term (exp + sin)
 F_TRIAL = 30.0                            # rt - t_offset, log (or its running-product twin), sum
 
-only = sys.argv[1] if len(sys.argv) > 1 else None
+only = sys.argv[1:] or None  # regime names to run (default: all three)
 rng = np.random.default_rng(20260105)
 peak = E.measure_fp64_tflops()
 print(f"FP64 FMA peak measured on this GPU: {peak:.2f} TFLOP/s")
 for name, zero, S, reps in (("no variability", ("st0", "sv", "sz"), 256, 10), ("sv", ("st0", "sz"), 256, 10), ("sv+sz+st0", (), 32, 3)):
-    if only and only != name:
+    if only and name not in only:
         continue
     ct, truth, prior = W.ddm_model(fixed=zero)  # a variability that is off is a constant 0, not a free parameter
     om = ob.OModel(ct.param_src, ct.const_val, ct.posdrift, ct.npar, type=ob.MODEL_DDM)
@@ -47,6 +47,7 @@ for name, zero, S, reps in (("no variability", ("st0", "sv", "sz"), 256, 10), ("
     for s_, c in pairs:
         ob.sumloglike(om, od[s_], theta[s_, c])
     t_port = time.perf_counter() - t0
+    parity = max(abs(ll[s_, c] - ob.sumloglike(om, od[s_], theta[s_, c])) / abs(ll[s_, c]) for s_, c in pairs)
     ob.lib().orc_ddm_counters(cnt, 1)
     n_s = 768 * len(pairs)
     evals, small, large = cnt[0] / n_s, cnt[1] / n_s, cnt[2] / n_s
@@ -55,7 +56,7 @@ for name, zero, S, reps in (("no variability", ("st0", "sv", "sz"), 256, 10), ("
     line = (f"{name:>14s}: {S} subjects x 768 trials x {nchain} chains: {ms:9.3f} ms per launch, {rate:.3e} trial-likelihoods/s; "
             f"per trial {evals:.1f} series evaluations, {small:.1f} small-time + {large:.1f} large-time terms = {flop:.0f} flop "
             f"-> {flop * rate / 1e12:.2f} TFLOP/s algorithmic = {flop * rate / 1e12 / peak:.3f} of peak; "
-            f"oracle port (-O2, 1 core): {n_s / t_port:.3e}/s")
+            f"oracle port (-O2, 1 core): {n_s / t_port:.3e}/s; sums vs oracle: max rel diff {parity:.1e}")
     if ob.ref_lib() is not None:
         ob.ref2_ddm_density(om, od[pairs[0][0]], theta[pairs[0]])  # warm-up: the static ddm_obj is built on the first call
         t0 = time.perf_counter()
