@@ -23,7 +23,8 @@
 #include "gg_math.cuh"
 #include <stdint.h>
 
-// the series evaluation is called from inside both midpoint rules: one out-of-line copy instead of four inlined ones
+// the start-point rule (with the series evaluation inside it) is called from two places of the non-decision rule: one
+// out-of-line copy
 #ifdef __CUDACC__
 #define GG_DDM_FN __device__ __noinline__
 #else
@@ -39,9 +40,8 @@ struct DdmCell {
     double a, v, sv, st0, zr, szr, t_offset; // m_a, m_v, m_sv, m_st0, m_zr, m_szr, m_t_offset
     double int_t0, int_z, var_eps;           // TUNE_INT_T0, TUNE_INT_Z, TUNE_SZ_EPSILON == TUNE_ST0_EPSILON
     double a2, v2, sv2;                      // @hdr/ddm.h:223-225
-    double inv_a2;                           // 1 / a^2: t / a^2 and the factor's division become multiplications
+    double inv_a2, ln_inv_a2;                // 1 / a^2 (t / a^2 and the factor's division become multiplications) and its log
     int valid, no_var;                       // validate_parameters(); sv == 0
-    int pad[2];
 };
 static_assert(sizeof(DdmCell) == 128, "DdmCell is two 64-byte lines");
 
@@ -50,6 +50,8 @@ constexpr double kPi = 3.141592653589793;       // .rodata+0xec8
 constexpr double kTwoPi = 6.283185307179586;    // .rodata+0xec0
 constexpr double kPiSq = 9.869604401089358;     // m_pi2, @hdr/ddm.h:141
 constexpr double kInvPi = 0.3183098861837907;
+constexpr double kLnPi = 1.1447298858494002, kLn2Pi = 1.8378770664093453, kLn2 = 0.6931471805599453;
+constexpr double kLnEpsilon = -13.815510557964274; // log(1e-6)
 
 // the object code converts with cvttsd2si: NaN and out-of-range values give INT_MIN
 GG_HD int ddm_trunc(double x) { return (x >= -2147483648.0 && x < 2147483648.0) ? (int)x : (-2147483647 - 1); }
@@ -74,6 +76,7 @@ GG_HD void ddmcell_build(DdmCell &q, const double *P, bool is_upper)
     q.v2 = q.v * q.v;
     q.sv2 = q.sv * q.sv;
     q.inv_a2 = 1.0 / q.a2;
+    q.ln_inv_a2 = log(q.inv_a2);
     q.no_var = q.sv == 0;
     bool ok = true; // comparisons are false on NaN, like the reference's
     if (q.a <= 0) ok = false;                         // :232
@@ -85,7 +88,6 @@ GG_HD void ddmcell_build(DdmCell &q, const double *P, bool is_upper)
     if (q.zr + 0.5 * q.szr >= 1.0) ok = false;        // :288
     if (s <= 0) ok = false;                           // :298
     q.valid = ok;
-    q.pad[0] = q.pad[1] = 0;
 }
 
 // 1 / sqrt(x) and sin / cos of pi x: the device has cheaper dedicated forms (MUFU.RSQ64H seed + Newton; exact argument
@@ -163,64 +165,83 @@ GG_HD double ddm_series(double ta, double zr, bool use_small, int N)
     return kPi * sum;
 }
 
-// compute_g_factor, @hdr/ddm.h:383-405
-GG_HD double ddm_factor(const DdmCell &q, double t, double zr)
+// integral_z (@hdr/ddm.h:508-514) with integrate_v_over_zr (:488-505), integral_v (:457-485) / g_no_var (:433-454),
+// compute_g_factor (:383-405) and get_N (:408-430) folded into one function so that what depends on t alone is computed
+// once per t and not once per start-point abscissa:
+//  * t / a^2, ceil(1 / (pi sqrt t)), sqrt(2 pi ta), ceil(sqrt ta) + 1, the factor's zr-independent multiplier
+//    c = 1 / (a^2 sqrt(1 + sv^2 t));
+//  * the LOGARITHMS.  get_N needs log(pi ta eps) and log(2 eps sqrt(2 pi ta)) with eps = 1e-6 / factor and
+//    factor = exp(e) c, so log eps = log 1e-6 - e - log c: with log(ta) and log(c) taken once per t, no logarithm is left
+//    inside the abscissa loop (the conditions `1 > ...` are still tested on the products themselves, like the reference's;
+//    a sum that rounding pushes across 0 falls back to the reference's expression).  This moves the argument of a term
+//    count's ceil by ~1e-14 relative instead of ~1e-16.
+// The reference's midpoint rule is kept exactly: max(4, trunc(width / step)) abscissae, x accumulated by += step,
+// `upper > x` as the loop test.  Without start-point variability the "rule" is one abscissa of weight 1.
+GG_DDM_FN double ddm_integral_z(const DdmCell &q, double t)
 {
-    double f;
-    if (q.no_var) {
-        f = exp((-q.a * zr) * q.v - (0.5 * q.v2) * t) * q.inv_a2;
-    } else {
-        const double denom = 1.0 + q.sv2 * t;
-        const double e = (-0.5 * ((q.v2 * t + (q.a * (q.v + q.v)) * zr) - ((q.a2 * zr) * zr) * q.sv2)) / denom;
-        f = exp(e) * (q.inv_a2 * ddm_rsqrt(denom));
+    double x = q.zr, upper = INFINITY, step = INFINITY, weight = 1.0, divisor = 1.0;
+    if (!(q.var_eps > q.szr)) { // :512
+        const double lower = q.zr - 0.5 * q.szr;
+        upper = 0.5 * q.szr + q.zr;
+        const double width = upper - lower;
+        int n = ddm_trunc(width / q.int_z);
+        if (n < 4) n = 4;
+        step = width / (double)n;
+        weight = step;
+        divisor = q.szr;
+        x = 0.5 * step + lower;
     }
-    return isfinite(f) ? f : 0.0;
-}
-
-// integral_v (@hdr/ddm.h:457-485) and g_no_var (:433-454): the two share every step but the factor
-GG_DDM_FN double ddm_integral_v(const DdmCell &q, double t, double zr)
-{
-    if (0 >= t) return 0.0;
+    // every abscissa contributes 0 when 0 >= t (:459 / :434); a NaN t ends as 0 through the factor's isfinite test (:389, :403)
+    if (!(t > 0)) return 0.0 / divisor;
     const double ta = t * q.inv_a2;
-    const double factor = ddm_factor(q, t, zr);
-    if (factor == 0) return 0.0;
-    const double eps = kDdmEpsilon / factor;
-    // get_N, :408-430: nl = max(ceil(1 / (pi sqrt t)), ceil(sqrt(-2 log(pi ta eps) / (pi^2 ta)))) terms of the large-time
-    // series, ns = ceil(max(sqrt ta + 1, sqrt(-2 ta log(2 eps sqrt(2 pi ta))) + 2)) of the small-time one (ceil and max
-    // commute, and ceil(x + integer) = ceil(x) + integer)
-    int nl = ddm_trunc(ceil(ddm_rsqrt(t) * kInvPi));
-    const double pe = (kPi * ta) * eps;
-    if (1.0 > pe) {
-        const int k = ddm_ceil_sqrt((log(pe) * -2.0) / (kPiSq * ta));
-        if (nl < k) nl = k;
-    }
-    int ns = 2;
+    const double lt = log(ta);
+    const double log_pi_ta = lt + kLnPi;
     const double rt2 = sqrt(ta * kTwoPi);
-    if (1.0 > (rt2 + rt2) * eps) {
-        const double x1 = (-2.0 * ta) * log(rt2 * (eps + eps));
-        if (ta > 1e-30 && ta < 1e12 && x1 > 1e-30 && x1 < 1e12) {
-            const int k1 = ddm_ceil_sqrt(x1) + 2, k2 = ddm_ceil_sqrt(ta) + 1;
-            ns = k2 < k1 ? k1 : k2;
-        } else { // roots that vanish next to the added integer, overflow, NaN: the reference's expression as it stands
-            const double t1 = sqrt(x1) + 2.0, t2 = sqrt(ta) + 1.0;
-            ns = ddm_trunc(ceil(t2 < t1 ? t1 : t2));
-        }
+    const double log_2rt2 = 0.5 * (lt + kLn2Pi) + kLn2;
+    const int nl0 = ddm_trunc(ceil(ddm_rsqrt(t) * kInvPi));
+    const bool ta_ok = ta > 1e-30 && ta < 1e12;
+    const int k2p1 = ta_ok ? ddm_ceil_sqrt(ta) + 1 : 0;
+    double denom = 1.0, c = q.inv_a2, log_c = q.ln_inv_a2;
+    if (!q.no_var) {
+        denom = 1.0 + q.sv2 * t;
+        c = q.inv_a2 * ddm_rsqrt(denom);
+        log_c = q.ln_inv_a2 - 0.5 * log(denom);
     }
-    const bool use_small = ns < nl;
-    return ddm_series(ta, zr, use_small, use_small ? ns : nl) * factor;
-}
+    const double v2t = q.v2 * t, two_av = q.a * (q.v + q.v);
 
-// integral_z (@hdr/ddm.h:508-514) with integrate_v_over_zr (:488-505)
-GG_HD double ddm_integral_z(const DdmCell &q, double t)
-{
-    if (q.var_eps > q.szr) return ddm_integral_v(q, t, q.zr);
-    const double lower = q.zr - 0.5 * q.szr, upper = 0.5 * q.szr + q.zr, width = upper - lower;
-    int n = ddm_trunc(width / q.int_z);
-    if (n < 4) n = 4;
-    const double step = width / (double)n;
     double sum = 0.0;
-    for (double x = 0.5 * step + lower; upper > x; x += step) sum = ddm_integral_v(q, t, x) * step + sum;
-    return sum / q.szr;
+    for (; upper > x; x += step) {
+        const double e_arg = q.no_var ? (-q.a * x) * q.v - (0.5 * q.v2) * t
+                                      : (-0.5 * ((v2t + two_av * x) - ((q.a2 * x) * x) * q.sv2)) / denom;
+        double factor = exp(e_arg) * c;
+        if (!isfinite(factor)) factor = 0.0;
+        double val = 0.0;
+        if (factor != 0) {
+            const double eps = kDdmEpsilon / factor;
+            const double le = kLnEpsilon - (e_arg + log_c);
+            int nl = nl0;
+            if (1.0 > (kPi * ta) * eps) {
+                const double L = log_pi_ta + le;
+                const int k = L < 0 ? ddm_ceil_sqrt((L * -2.0) / (kPiSq * ta)) : 1;
+                if (nl < k) nl = k;
+            }
+            int ns = 2;
+            if (1.0 > (rt2 + rt2) * eps) {
+                const double x1 = (-2.0 * ta) * (log_2rt2 + le);
+                if (ta_ok && x1 > 1e-30 && x1 < 1e12) {
+                    const int k1 = ddm_ceil_sqrt(x1) + 2;
+                    ns = k2p1 < k1 ? k1 : k2p1;
+                } else { // vanishing / overflowing roots, a sum rounded across 0, NaN: the reference's expression as it stands
+                    const double t1 = sqrt((-2.0 * ta) * log(rt2 * (eps + eps))) + 2.0, t2 = sqrt(ta) + 1.0;
+                    ns = ddm_trunc(ceil(t2 < t1 ? t1 : t2));
+                }
+            }
+            const bool use_small = ns < nl;
+            val = ddm_series(ta, x, use_small, use_small ? ns : nl) * factor;
+        }
+        sum = val * weight + sum;
+    }
+    return sum / divisor;
 }
 
 // g (@hdr/ddm.h:545-549) -> integral_t0 (:537-542) with integrate_z_over_t (:517-534)
