@@ -23,8 +23,8 @@
 #include "gg_math.cuh"
 #include <stdint.h>
 
-// the start-point rule (with the series evaluation inside it) is called from two places of the non-decision rule: one
-// out-of-line copy
+// the one-abscissa evaluation and the start-point rule are each called from two places of the non-decision rule: one
+// out-of-line copy of each
 #ifdef __CUDACC__
 #define GG_DDM_FN __device__ __noinline__
 #else
@@ -165,9 +165,56 @@ GG_HD double ddm_series(double ta, double zr, bool use_small, int N)
     return kPi * sum;
 }
 
-// integral_z (@hdr/ddm.h:508-514) with integrate_v_over_zr (:488-505), integral_v (:457-485) / g_no_var (:433-454),
-// compute_g_factor (:383-405) and get_N (:408-430) folded into one function so that what depends on t alone is computed
-// once per t and not once per start-point abscissa:
+// compute_g_factor, @hdr/ddm.h:383-405
+GG_HD double ddm_factor(const DdmCell &q, double t, double zr)
+{
+    double f;
+    if (q.no_var) {
+        f = exp((-q.a * zr) * q.v - (0.5 * q.v2) * t) * q.inv_a2;
+    } else {
+        const double denom = 1.0 + q.sv2 * t;
+        const double e = (-0.5 * ((q.v2 * t + (q.a * (q.v + q.v)) * zr) - ((q.a2 * zr) * zr) * q.sv2)) / denom;
+        f = exp(e) * (q.inv_a2 * ddm_rsqrt(denom));
+    }
+    return isfinite(f) ? f : 0.0;
+}
+
+// integral_v (@hdr/ddm.h:457-485) and g_no_var (:433-454): the two share every step but the factor
+GG_DDM_FN double ddm_integral_v(const DdmCell &q, double t, double zr)
+{
+    if (0 >= t) return 0.0;
+    const double ta = t * q.inv_a2;
+    const double factor = ddm_factor(q, t, zr);
+    if (factor == 0) return 0.0;
+    const double eps = kDdmEpsilon / factor;
+    // get_N, :408-430: nl = max(ceil(1 / (pi sqrt t)), ceil(sqrt(-2 log(pi ta eps) / (pi^2 ta)))) terms of the large-time
+    // series, ns = ceil(max(sqrt ta + 1, sqrt(-2 ta log(2 eps sqrt(2 pi ta))) + 2)) of the small-time one (ceil and max
+    // commute, and ceil(x + integer) = ceil(x) + integer)
+    int nl = ddm_trunc(ceil(ddm_rsqrt(t) * kInvPi));
+    const double pe = (kPi * ta) * eps;
+    if (1.0 > pe) {
+        const int k = ddm_ceil_sqrt((log(pe) * -2.0) / (kPiSq * ta));
+        if (nl < k) nl = k;
+    }
+    int ns = 2;
+    const double rt2 = sqrt(ta * kTwoPi);
+    if (1.0 > (rt2 + rt2) * eps) {
+        const double x1 = (-2.0 * ta) * log(rt2 * (eps + eps));
+        if (ta > 1e-30 && ta < 1e12 && x1 > 1e-30 && x1 < 1e12) {
+            const int k1 = ddm_ceil_sqrt(x1) + 2, k2 = ddm_ceil_sqrt(ta) + 1;
+            ns = k2 < k1 ? k1 : k2;
+        } else { // roots that vanish next to the added integer, overflow, NaN: the reference's expression as it stands
+            const double t1 = sqrt(x1) + 2.0, t2 = sqrt(ta) + 1.0;
+            ns = ddm_trunc(ceil(t2 < t1 ? t1 : t2));
+        }
+    }
+    const bool use_small = ns < nl;
+    return ddm_series(ta, zr, use_small, use_small ? ns : nl) * factor;
+}
+
+// The start-point rule.  integrate_v_over_zr (@hdr/ddm.h:488-505) with integral_v (:457-485), compute_g_factor (:383-405)
+// and get_N (:408-430) folded into one function so that what depends on t alone is computed once per t and not once per
+// start-point abscissa:
 //  * t / a^2, ceil(1 / (pi sqrt t)), sqrt(2 pi ta), ceil(sqrt ta) + 1, the factor's zr-independent multiplier
 //    c = 1 / (a^2 sqrt(1 + sv^2 t));
 //  * the LOGARITHMS.  get_N needs log(pi ta eps) and log(2 eps sqrt(2 pi ta)) with eps = 1e-6 / factor and
@@ -176,22 +223,17 @@ GG_HD double ddm_series(double ta, double zr, bool use_small, int N)
 //    a sum that rounding pushes across 0 falls back to the reference's expression).  This moves the argument of a term
 //    count's ceil by ~1e-14 relative instead of ~1e-16.
 // The reference's midpoint rule is kept exactly: max(4, trunc(width / step)) abscissae, x accumulated by += step,
-// `upper > x` as the loop test.  Without start-point variability the "rule" is one abscissa of weight 1.
-GG_DDM_FN double ddm_integral_z(const DdmCell &q, double t)
+// `upper > x` as the loop test.  (Measured: 1.50e8 -> 2.11e8 trial-likelihoods/s with all variabilities on; the single
+// abscissa of a model without start-point variability keeps the plain ddm_integral_v, which needs fewer registers and
+// is 10-16 % faster there.)
+GG_DDM_FN double ddm_integrate_v_over_zr(const DdmCell &q, double t)
 {
-    double x = q.zr, upper = INFINITY, step = INFINITY, weight = 1.0, divisor = 1.0;
-    if (!(q.var_eps > q.szr)) { // :512
-        const double lower = q.zr - 0.5 * q.szr;
-        upper = 0.5 * q.szr + q.zr;
-        const double width = upper - lower;
-        int n = ddm_trunc(width / q.int_z);
-        if (n < 4) n = 4;
-        step = width / (double)n;
-        weight = step;
-        divisor = q.szr;
-        x = 0.5 * step + lower;
-    }
-    // every abscissa contributes 0 when 0 >= t (:459 / :434); a NaN t ends as 0 through the factor's isfinite test (:389, :403)
+    const double lower = q.zr - 0.5 * q.szr, upper = 0.5 * q.szr + q.zr, width = upper - lower;
+    int n = ddm_trunc(width / q.int_z);
+    if (n < 4) n = 4;
+    const double step = width / (double)n, weight = step, divisor = q.szr;
+    double x = 0.5 * step + lower;
+    // every abscissa contributes 0 when 0 >= t (:459); a NaN t ends as 0 through the factor's isfinite test (:389, :403)
     if (!(t > 0)) return 0.0 / divisor;
     const double ta = t * q.inv_a2;
     const double lt = log(ta);
@@ -242,6 +284,12 @@ GG_DDM_FN double ddm_integral_z(const DdmCell &q, double t)
         sum = val * weight + sum;
     }
     return sum / divisor;
+}
+
+// integral_z, @hdr/ddm.h:508-514
+GG_HD double ddm_integral_z(const DdmCell &q, double t)
+{
+    return q.var_eps > q.szr ? ddm_integral_v(q, t, q.zr) : ddm_integrate_v_over_zr(q, t);
 }
 
 // g (@hdr/ddm.h:545-549) -> integral_t0 (:537-542) with integrate_z_over_t (:517-534)
