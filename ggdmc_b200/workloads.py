@@ -105,6 +105,25 @@ def ddm_model(precision: float = 3.0, s: float = 1.0, fixed=()):
     return ct, np.array([full[k] for k in pnames]), prior
 
 
+def ddm_readme_model():
+    """The DDM of the reference's second README example (README.md:247-300): p_map all "1", factors S = (s1, s2),
+    match_map s1 -> r1, s2 -> r2, constants d = 0, s = 1, st0 = 0, sv = 0, precision = 3, free parameters
+    a, sz, t0, v, z; the matching response of a cell is the upper boundary (dmi@is_positive_drift per cell).
+    Returns (cell table, p_vector of README.md:297, population mean / scale of README.md:278-279)."""
+    from .model import DDM_CORE
+    pnames = ["a", "sz", "t0", "v", "z"]
+    cnames = ["d", "s", "st0", "sv", "precision"]
+    const = np.array([0.0, 1.0, 0.0, 0.0, 3.0])
+    src = np.zeros((4, len(DDM_CORE), 2), dtype=np.int32)
+    for r, core in enumerate(DDM_CORE):
+        src[:, r, :] = pnames.index(core) if core in pnames else -1 - cnames.index(core)
+    upper = np.array([1, 0, 0, 1], dtype=np.uint8)  # cells s1.r1, s1.r2, s2.r1, s2.r2: the match is the upper boundary
+    ct = CellTable(2, 4, 5, src, const, upper, pnames, ["s1.r1", "s1.r2", "s2.r1", "s2.r2"], "fastdm")
+    p_vector = np.array([1.0, 0.25, 0.15, 2.5, 0.38])
+    pop_mean, pop_scale = p_vector.copy(), np.array([0.05, 0.01, 0.02, 0.5, 0.01])
+    return ct, p_vector, pop_mean, pop_scale
+
+
 def ddm_simulate(theta: np.ndarray, n_per_stim: int, rng: np.random.Generator, dt: float = 1e-3, s: float = 1.0, pnames=None) -> Trials:
     """Euler-Maruyama simulation of ddm_model()'s design (synthetic inputs only): trials grouped by cell.
     `pnames` names the entries of theta (default DDM_PNAMES); parameters not named are 0."""

@@ -283,3 +283,26 @@ def test_ddm_integer_ceil_sqrt_equals_the_reference_expression(hostmath):
             assert got == want + 1 == k + 1 and x > k * k and np.sqrt(x) == k, (x, got, want)
             n_diff += 1
     assert n_diff <= 4000  # the nextafter(k^2, inf) probes
+
+
+@needs_ref
+def test_readme_ddm_example_model_bitwise_vs_reference_object_code():
+    """The DDM of the reference's second README example (README.md:247-300: free a, sz, t0, v, z; st0 = sv = 0,
+    precision = 3; the matching response is the upper boundary) with subjects drawn around its population mean: every
+    trial density of the restatement equals likelihood_class::ddm_likelihood of src/de.o bit for bit (start-point
+    variability on: the 4..10-abscissa midpoint rule is on the path)."""
+    from ggdmc_b200 import workloads as W
+    ct, p_vector, pop_mean, pop_scale = W.ddm_readme_model()
+    om = ob.OModel(ct.param_src, ct.const_val, ct.posdrift, ct.npar, type=ob.MODEL_DDM)
+    rng = np.random.default_rng(9032)
+    n = 256
+    cell = np.sort(rng.integers(0, 4, n)).astype(np.uint16)
+    d = ob.OData(0.15 + rng.gamma(2.0, 0.12, n), cell)
+    n_pos = 0
+    for _ in range(40):
+        th = pop_mean + pop_scale * rng.standard_normal(5)
+        ref = ob.ref2_ddm_density(om, d, th)
+        mine = _oracle_density(om, d, th)
+        assert np.all(_same(ref, mine)), th
+        n_pos += int(np.sum(ref > 1e-3))
+    assert n_pos > 20 * n
