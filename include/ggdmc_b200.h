@@ -1,4 +1,4 @@
-/* ggdmc_b200 -- C ABI of the B200-native DE-MCMC / LBA sampling engine.
+/* ggdmc_b200 -- C ABI of the B200-native DE-MCMC sampling engine (LBA and DDM likelihoods).
  *
  * Drop-in boundary: the three routines ggdmc registers for .Call
  *     _ggdmc_run_subject, _ggdmc_run_hyper, _ggdmc_run      (src/RcppExports.cpp:16-64)
@@ -179,7 +179,9 @@ int ggdmc_b200_sumloglike(const ggdmc_model_t *model, const ggdmc_trials_t *tria
 
 /* The same sum under the R-side initialisation rule (R/phi.R:3-13, `.sumlog`, used by initialise_theta
  * R/phi.R:166-201): a density <= 0 is replaced by .Machine$double.eps before the log, so a start value
- * whose likelihood the sampler would score -Inf still gets a finite (very low) score. */
+ * whose likelihood the sampler would score -Inf still gets a finite (very low) score.  The replacement is made trial by
+ * trial; R applies pmax(xi, eps) to a whole cell once one of its densities is <= 0, which differs only for DDM cells
+ * that also hold densities in (0, eps). */
 int ggdmc_b200_sumloglike_init(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta,
                                int32_t n_theta, double *out, char err[256]);
 
