@@ -63,7 +63,9 @@ def build(force: bool = False) -> None:
     if stale:
         subprocess.run(["make", "-C", HERE, "libggdmc_oracle.so"], check=True, capture_output=True)
     ref = os.path.join(HERE, "_ref", "libggdmc_ref.so")
-    if os.path.exists("/root/reference/src/de.o") and (force or not os.path.exists(ref)):
+    ref_srcs = [os.path.join(HERE, f) for f in ("ref_harness.cpp", "ref_harness2.cpp", "ref_shim.c", "rmath_port.c")]
+    ref_stale = force or not os.path.exists(ref) or any(os.path.getmtime(s) > os.path.getmtime(ref) for s in ref_srcs)
+    if os.path.exists("/root/reference/src/de.o") and ref_stale:
         subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
 
 
@@ -100,6 +102,8 @@ def ref_lib() -> Optional[C.CDLL]:
     global _ref
     if _ref is None:
         path = os.path.join(HERE, "_ref", "libggdmc_ref.so")
+        if os.path.exists("/root/reference/src/de.o"):
+            build()  # (re)link the harness where the reference is mounted; elsewhere the prebuilt file is used as it is
         if not os.path.exists(path):
             return None
         L = C.CDLL(path)
