@@ -306,3 +306,20 @@ def test_readme_ddm_example_model_bitwise_vs_reference_object_code():
         assert np.all(_same(ref, mine)), th
         n_pos += int(np.sum(ref > 1e-3))
     assert n_pos > 20 * n
+
+
+def test_ddm_golden_vectors():
+    """tests/golden/ddm_ref.npz -- trial densities written by the reference's own object code
+    (tests/golden/make_ddm_golden.py; three (precision, s) settings, all variability combinations, the edge cases) --
+    reproduced by the oracle bit for bit.  Needs neither /root/reference nor oracle/_ref."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ddm_ref.npz"))
+    n = 0
+    for k, (precision, s) in enumerate(g["settings"]):
+        ct, om = ddm_model(float(precision), float(s))
+        d = ob.OData(g[f"rt{k}"], g[f"cell{k}"])
+        assert np.array_equal(d.rt, g[f"rt{k}"])  # stored grouped by cell already
+        for th, want in zip(g[f"theta{k}"], g[f"dens{k}"]):
+            assert np.all(_same(_oracle_density(om, d, th), want)), (k, th)
+            n += int(np.sum(want > 1e-6))
+    assert n > 20000

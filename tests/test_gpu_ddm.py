@@ -309,3 +309,19 @@ def test_ddm_single_subject_posterior_recovers_generating_values():
     flat = x.reshape(-1, D)
     lo, hi = np.quantile(flat, 0.0005, axis=0), np.quantile(flat, 0.9995, axis=0)
     assert np.all((truth > lo) & (truth < hi)), (truth, lo, hi)
+
+
+def test_ddm_trial_logdens_vs_reference_golden_vectors():
+    """The kernel against known answers written by the reference's own object code (tests/golden/ddm_ref.npz, made by
+    tests/golden/make_ddm_golden.py from likelihood_class::ddm_likelihood of src/de.o): no oracle in between."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ddm_ref.npz"))
+    n_strict = 0
+    for k, (precision, s) in enumerate(g["settings"]):
+        ct, om = ddm_model(float(precision), float(s))
+        thetas, dens = g[f"theta{k}"][:48], g[f"dens{k}"][:48]
+        got = E.trial_logdens(ct, Trials(g[f"rt{k}"].copy(), g[f"cell{k}"].copy()), thetas)
+        for i in range(len(thetas)):
+            ref = np.log(np.where(dens[i] < 2.2250738585072014e-308, 2.2250738585072014e-308, dens[i]))  # @hdr/likelihood.h:303
+            n_strict += _check_logdens(got[i], ref, ("golden", k, i))
+    assert n_strict > 9000
