@@ -21,8 +21,20 @@ def build(S, rng):
     hp = PriorTable(2 * D, hlo, hhi, np.zeros(2 * D), np.zeros(2 * D), np.full(2 * D, 6, np.int32), np.ones(2 * D, np.uint8),
                     [f"loc_{n}" for n in ct.pnames] + [f"sca_{n}" for n in ct.pnames])
     truths = np.maximum(pop_mean + pop_scale * rng.standard_normal((S, D)), lower + 1e-3)
-    trials = [W.ddm_simulate(t, 128, rng, pnames=ct.pnames) for t in truths]
+    trials = [simulate_accuracy_coded(dict(zip(ct.pnames, t)), 128, rng) for t in truths]
     return ct, pp, hp, pop_mean, pop_scale, truths, trials
+
+
+def simulate_accuracy_coded(p, n_per_stim, rng):
+    """W.ddm_simulate draws with one drift per stimulus and r2 as the upper boundary; the README model has ONE drift
+    towards the matching response, which is the upper boundary of its cell: same paths, cells s1.r1 / s1.r2 swapped."""
+    from ggdmc_b200.model import Trials
+    full = dict(a=p["a"], st0=0.0, sv=0.0, sz=p["sz"], t0=p["t0"], z=p["z"])
+    full["v.s1"] = full["v.s2"] = p["v"]
+    tr = W.ddm_simulate(np.array([full[k] for k in W.DDM_PNAMES]), n_per_stim, rng)
+    cell = np.where(tr.cell < 2, 1 - tr.cell, tr.cell).astype(np.uint16)
+    order = np.argsort(cell, kind="stable")
+    return Trials(tr.rt[order], cell[order])
 
 
 def starts(ct, pp, hp, pop_mean, pop_scale, truths, trials, C, rng):
