@@ -411,3 +411,27 @@ def test_rprior_draws_follow_every_prior_family():
         assert np.all(np.abs(h - expect) <= 6 * np.sqrt(expect) + 0.01 * expect), (i, h, expect)
     v = np.array([[False, True, True], [False, False, False], [True, False, True]])
     assert list(_first_valid(v)) == [1, -1, 0]
+
+
+def test_ctypes_mirrors_match_the_c_header_layout(tmp_path):
+    """Every struct of include/ggdmc_b200.h has the size and field offsets its ctypes mirror in ggdmc_b200/_lib.py
+    assumes (a C probe compiled against the header prints offsetof / sizeof)."""
+    from ggdmc_b200 import _lib as B
+    pairs = {"ggdmc_model_t": B.ModelT, "ggdmc_trials_t": B.TrialsT, "ggdmc_prior_t": B.PriorT, "ggdmc_config_t": B.ConfigT,
+             "ggdmc_samples_t": B.SamplesT, "ggdmc_start_t": B.StartT}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "ggdmc_b200.h"', 'int main(void) {']
+    for cname, T in pairs.items():
+        lines.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for f, _ in T._fields_:
+            lines.append(f'  printf("{cname} {f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for cname, T in pairs.items():
+        assert got[(cname, "sizeof")] == C.sizeof(T), cname
+        for f, _ in T._fields_:
+            assert got[(cname, f)] == getattr(T, f).offset, (cname, f)
