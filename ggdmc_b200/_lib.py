@@ -67,7 +67,7 @@ class StartT(C.Structure):
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_int32, C.c_void_p)
 
 EXPORTS = [
-    "ggdmc_b200_run_subject", "ggdmc_b200_run_hyper", "ggdmc_b200_run", "ggdmc_b200_trial_logdens",
+    "ggdmc_b200_run_subject", "ggdmc_b200_run_hyper", "ggdmc_b200_run", "ggdmc_b200_trial_logdens", "ggdmc_b200_trial_logdens_hot",
     "ggdmc_b200_sumloglike", "ggdmc_b200_sumloglike_init", "ggdmc_b200_sumlogprior", "ggdmc_b200_select_chains", "ggdmc_b200_engine_create",
     "ggdmc_b200_engine_iterate", "ggdmc_b200_engine_iterate_flushed", "ggdmc_b200_engine_time_likelihood", "ggdmc_b200_engine_state",
     "ggdmc_b200_engine_launch_count", "ggdmc_b200_engine_destroy", "ggdmc_b200_engine_profile", "ggdmc_b200_engine_counters", "ggdmc_b200_comm_unique_id", "ggdmc_b200_comm_init",

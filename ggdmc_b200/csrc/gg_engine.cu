@@ -5,6 +5,7 @@
 // 272-383).  No PyTorch, no CPU fallback: every compute entry point needs a CUDA device.
 #include "../../include/ggdmc_b200.h"
 #include "gg_kernels.cuh"
+#include "gg_sampler.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -199,6 +200,7 @@ struct P2P {
             win.flags[r] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(peer_base[r]) + slots_bytes(n));
         }
         win.seq = seq; win.status = status; win.n_rank = n; win.rank = nc.rank;
+        win.spin_ns = peer_timeout_ns();
         ready = true;
     }
     void teardown(int rank, int n)
@@ -217,6 +219,13 @@ struct P2P {
         int v = 0;
         if (status) cudaMemcpy(&v, status, sizeof(int), cudaMemcpyDeviceToHost);
         return v;
+    }
+    // how long a rank waits for its peers inside an exchange before it gives up (seconds, GGDMC_B200_PEER_TIMEOUT_S)
+    static unsigned long long peer_timeout_ns()
+    {
+        double sec = 120.0;
+        if (const char *e = std::getenv("GGDMC_B200_PEER_TIMEOUT_S")) sec = std::max(0.001, std::atof(e));
+        return (unsigned long long)(sec * 1e9);
     }
 };
 P2P g_p2p;
@@ -570,6 +579,16 @@ void launch_like(const Level &L, const ModelDev &MD, const TrialData &T, const u
     }
 }
 
+template <int NACC>
+void launch_trial_logdens_hot(const DevModel &M, const TrialData &T, const double *theta, int n_theta, int ntr, uint64_t seed, uint32_t pop,
+                              uint32_t iter, double *out, double *sums)
+{
+    const size_t sm = like_smem(M, 64);
+    require(sm <= 220 * 1024, "cell table does not fit in shared memory");
+    allow_smem(k_trial_logdens_hot<NACC, 64>, sm);
+    k_trial_logdens_hot<NACC, 64><<<dim3(n_theta, T.nsplit), 64, sm>>>(M, T, theta, ntr, seed, pop, iter, out, sums);
+    CUDA_CHECK(cudaGetLastError());
+}
 } // namespace
 
 // GGDMC_B200_TRACE=1: every launch of an iteration is bracketed by CUDA events on its own stream and the
@@ -776,7 +795,10 @@ struct ggdmc_engine {
         trials.upload(t, m->n_cell, false, m->type == GGDMC_MODEL_DDM);
         pt.lap("  trials");
         S = t->n_subject;
-        trials.set_chunking((int64_t)R * S * C);
+        const bool want_persist = persist_planned = sampler_wanted() && m->type == GGDMC_MODEL_LBA && schedule == GGDMC_SCHEDULE_PARALLEL && !is_hblocked &&
+                                  !is_pblocked && (!(hp && g_nccl.comm && g_nccl.n_rank > 1) || (g_p2p.ready && R * C * 2 <= kP2PMaxN));
+        if (want_persist) sampler_chunking((int64_t)R * S * ((C + 1) / 2));
+        else trials.set_chunking((int64_t)R * S * C);
         subj.create(R * S, R, C, D, nmc, thin);
         pt.lap("  alloc");
         Level &L = subj.L;
@@ -807,6 +829,10 @@ struct ggdmc_engine {
         }
         make_groups();
         start_counter();
+        if (want_persist) setup_sampler();
+        if (kind == 2 && g_nccl.comm && g_nccl.n_rank > 1 && g_p2p.ready && g_p2p.timed_out())
+            throw Error(GGDMC_ERR_COMM, "the communicator is in an error state (an earlier exchange timed out): call ggdmc_b200_comm_finalize and initialise it again");
+        peer_barrier();
         pt.lap("  phi");
     }
 
@@ -881,6 +907,7 @@ struct ggdmc_engine {
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
         int want = std::max(1, (std::max(per_sm, 1) * n_sm) / (R * C));
         int spb = std::max(64, (S + want - 1) / want); // >= 3 terms per thread: the per-block setup (proposal, 4 Phi + 2 log per parameter) is not free
+        if (persist_planned) spb = 64; // 64-thread CTAs of the sampler kernel: D terms per thread, the phi half-sweep is on its critical path
         H.subj_per_block = spb;
         H.nsplit = (S + spb - 1) / spb;
         hpart.alloc((size_t)R * C * 2 * H.nsplit);
@@ -1047,19 +1074,21 @@ struct ggdmc_engine {
                 const int nw = half < 0 ? n : R * ((C + 1) / 2);
                 TR("k_propose", st, k_propose<kProposeWarps><<<(nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, st>>>(P, d_iter.p, sweep, -1, half));
                 hyper_eval(-1, st);
-                TR("k_phi_accept", st, k_phi_accept<<<(n + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur));
+                TR("k_phi_accept", st, k_phi_accept<<<(n + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, -1, hsum.p, need_cur, p2p_status()));
                 launches += 2;
             }
         } else {
             for (int step = 0; step < C; ++step) {
                 TR("k_propose", st, k_propose<kProposeWarps><<<(R + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, st>>>(P, d_iter.p, sweep, step, -1));
                 hyper_eval(step, st);
-                TR("k_phi_accept", st, k_phi_accept<<<(R + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, step, hsum.p, need_cur));
+                TR("k_phi_accept", st, k_phi_accept<<<(R + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, step, hsum.p, need_cur, p2p_status()));
                 launches += 2;
             }
         }
         CUDA_CHECK(cudaGetLastError());
     }
+
+    const int *p2p_status() const { return (kind == 2 && g_nccl.comm && g_nccl.n_rank > 1 && g_p2p.ready) ? g_p2p.status : nullptr; }
 
     void phi_constants(cudaStream_t st)
     {
@@ -1084,6 +1113,152 @@ struct ggdmc_engine {
         const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
         TR("k_store_advance", stream, k_store_advance<<<blocks, 256, 0, stream>>>(a.L, b ? b->L : a.L, b ? 1 : 0, d_iter.p, done_ctr.p));
         ++launches;
+    }
+
+    // ---- persistent sampler kernel (gg_sampler.cuh): the PARALLEL schedule of an LBA fit, whole iterations per launch -----
+    // GGDMC_B200_NO_PERSIST=1 keeps the multi-launch path (also used by the other schedules, per-parameter sweeps and the DDM).
+    bool persist = false, persist_planned = false;
+    SamplerArgs SA{};
+    int sampler_grid = 0, sampler_nacc = 0, sampler_max_batch = 64;
+    size_t sampler_smem = 0;
+    DBuf<unsigned long long> sy_queue, sy_all_done;
+    DBuf<unsigned int> sy_exit, sy_pop_arrive, sy_pop_done, sy_phi_arrive, sy_phi_done;
+    DBuf<int> sy_abort;
+
+    template <int NACC>
+    void sampler_prepare()
+    {
+        auto kern = k_sampler<NACC, 64, 12>;
+        allow_smem(kern, sampler_smem);
+        int per_sm = 0, n_sm = 148;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64, sampler_smem));
+        CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+        require(per_sm >= 1, "sampler kernel does not fit on an SM (cell table too large)");
+        sampler_grid = per_sm * n_sm;
+    }
+    template <int NACC>
+    void sampler_launch()
+    {
+        CUDA_CHECK(cudaLaunchKernelEx(&sampler_cfg, k_sampler<NACC, 64, 12>, SA));
+    }
+    cudaLaunchConfig_t sampler_cfg{};
+
+    static bool sampler_wanted() { return std::getenv("GGDMC_B200_NO_PERSIST") == nullptr; }
+
+    // trial chunks per proposal for the persistent kernel: one wave of items per half-sweep at most (a finer split only
+    // multiplies the per-item table build), as many as fit below that when the problem is small
+    void sampler_chunking(int64_t proposals_per_half)
+    {
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        const int64_t cap = (int64_t)n_sm * 12;
+        int nsplit = (int)std::max<int64_t>(1, cap / std::max<int64_t>(1, proposals_per_half));
+        nsplit = std::min(nsplit, std::max(1, trials.max_count / 128));
+        if (const char *e = std::getenv("GGDMC_B200_NSPLIT")) nsplit = std::max(1, std::min(std::atoi(e), std::max(1, trials.max_count / 8)));
+        if (trials.max_count > 8192) nsplit = std::max(nsplit, (trials.max_count + 4095) / 4096);
+        const int chunk = ((std::max(1, (trials.max_count + nsplit - 1) / nsplit)) + 7) & ~7;
+        trials.d.chunk = chunk;
+        trials.d.nsplit = std::max(1, (trials.max_count + chunk - 1) / chunk);
+    }
+
+    void setup_sampler()
+    {
+        const bool multi = kind == 2 && g_nccl.comm && g_nccl.n_rank > 1;
+        const bool p2p = multi && g_p2p.ready && R * C * 2 <= kP2PMaxN;
+        const int npop = R * S;
+        sy_queue.alloc(1); sy_queue.zero();
+        sy_all_done.alloc(1); sy_all_done.zero();
+        sy_exit.alloc(1); sy_exit.zero();
+        sy_pop_arrive.alloc(npop); sy_pop_arrive.zero();
+        sy_phi_arrive.alloc(1); sy_phi_arrive.zero();
+        sy_abort.alloc(1); sy_abort.zero();
+        std::vector<unsigned int> two((size_t)npop, 2u); // "half 1 of iteration 0 is accepted"
+        sy_pop_done.upload(two);
+        sy_phi_done.upload(two.data(), 1);
+        CUDA_CHECK(cudaStreamSynchronize(0));
+        SA.S = subj.L;
+        if (kind == 2) SA.P = phi.L;
+        SA.M = model.d;
+        SA.T = trials.d;
+        SA.H = H;
+        SA.w = g_p2p.win;
+        SA.y.queue = sy_queue.p; SA.y.exit_ctr = sy_exit.p; SA.y.pop_arrive = sy_pop_arrive.p; SA.y.pop_done = sy_pop_done.p;
+        SA.y.all_done = sy_all_done.p; SA.y.phi_arrive = sy_phi_arrive.p; SA.y.phi_done = sy_phi_done.p; SA.y.abort = sy_abort.p;
+        double sec = 20.0; // a local wait is bounded by the longest item chain of an iteration; peers are waited for inside the exchange
+        if (const char *e = std::getenv("GGDMC_B200_SPIN_TIMEOUT_S")) sec = std::max(0.001, std::atof(e));
+        SA.y.spin_ns = (unsigned long long)(sec * 1e9) + (multi ? g_p2p.win.spin_ns : 0ull);
+        SA.ll_part = ll_part.p; SA.hpart = hpart.p; SA.hsum = hsum.p; SA.phi_consts = phi_consts.p;
+        SA.d_iter = d_iter.p;
+        SA.hier = kind == 2; SA.use_p2p = p2p ? 1 : 0; SA.decide_once = kind == 0;
+        sampler_smem = sampler_smem_bytes(model.d.n_cell, model.d.n_acc, D, C, 64, SA.hier);
+        require(sampler_smem <= 220 * 1024, "cell table does not fit in shared memory");
+        sampler_nacc = model.d.n_acc;
+        switch (sampler_nacc) {
+        case 2: sampler_prepare<2>(); break;
+        case 3: sampler_prepare<3>(); break;
+        case 4: sampler_prepare<4>(); break;
+        default: sampler_prepare<0>();
+        }
+        const unsigned long long per_iter = 2ull * (SA.hier ? (unsigned long long)R * C * H.nsplit : 0ull) +
+                                            2ull * (unsigned long long)npop * ((C + 1) / 2) * trials.d.nsplit;
+        sampler_grid = (int)std::min<unsigned long long>((unsigned long long)sampler_grid, per_iter);
+        if (const char *e = std::getenv("GGDMC_B200_BATCH")) sampler_max_batch = std::max(1, std::atoi(e));
+        // the migration decisions of iteration 1 (later ones are drawn inside the kernel at the end of the previous iteration)
+        k_sweep_begin<<<npop, 128, (size_t)2 * C * sizeof(int), stream>>>(subj.L, d_iter.p, 0, SA.decide_once, -1);
+        if (kind == 2) k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), stream>>>(phi.L, d_iter.p, 0, 0, -1);
+        CUDA_CHECK(cudaGetLastError());
+        launches += kind == 2 ? 2 : 1;
+        persist = true;
+    }
+
+    // iterations [h_iter + 1, h_iter + n] in one launch
+    void run_persist(int n)
+    {
+        SA.t_begin = h_iter + 1;
+        SA.t_end = h_iter + 1 + (uint32_t)n;
+        sampler_cfg = cudaLaunchConfig_t{};
+        sampler_cfg.gridDim = dim3(sampler_grid); sampler_cfg.blockDim = dim3(64); sampler_cfg.dynamicSmemBytes = sampler_smem;
+        sampler_cfg.stream = stream;
+        cudaEvent_t ea = nullptr, eb = nullptr;
+        if (profile) {
+            if (prof_used + 2 > prof_ev.size()) {
+                for (int i = 0; i < 2; ++i) {
+                    cudaEvent_t e;
+                    CUDA_CHECK(cudaEventCreate(&e));
+                    prof_ev.push_back(e);
+                }
+            }
+            ea = prof_ev[prof_used]; eb = prof_ev[prof_used + 1];
+            prof_used += 2;
+            CUDA_CHECK(cudaEventRecord(ea, stream));
+        }
+        switch (sampler_nacc) {
+        case 2: sampler_launch<2>(); break;
+        case 3: sampler_launch<3>(); break;
+        case 4: sampler_launch<4>(); break;
+        default: sampler_launch<0>();
+        }
+        if (profile) CUDA_CHECK(cudaEventRecord(eb, stream));
+        h_iter += (uint32_t)n;
+        ++launches;
+    }
+
+    void check_sampler_status()
+    {
+        if (!persist) return;
+        int v = 0;
+        CUDA_CHECK(cudaMemcpy(&v, sy_abort.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (v == 1) throw Error(GGDMC_ERR_COMM, "peer exchange timed out: a rank did not arrive");
+        if (v != 0) throw Error(GGDMC_ERR_CUDA, "sampler kernel: a dependency wait timed out");
+    }
+
+    // all ranks of a sharded fit arrive before anybody iterates (the exchange assumes lock step within its timeout)
+    void peer_barrier()
+    {
+        if (kind == 2 && g_nccl.comm && g_nccl.n_rank > 1 && g_p2p.ready) {
+            k_peer_barrier<<<1, 32, 0, stream>>>(g_p2p.win);
+            ++launches;
+        }
     }
 
     // one DE-MCMC iteration: run_chains body (src/de.cpp:208-240) or run_hchains body (:281-381).
@@ -1194,14 +1369,25 @@ struct ggdmc_engine {
     void iterate(int n_iter, float *elapsed_ms, ggdmc_progress_fn progress, void *user, int report_length)
     {
         CUDA_CHECK(cudaSetDevice(device));
+        peer_barrier(); // ranks that enter seconds apart (uploads, host work) meet here, not inside the first exchange
         CUDA_CHECK(cudaEventRecord(ev0, stream));
         const bool streaming = !sinks.empty();
         if (streaming) {
             CUDA_CHECK(cudaStreamSynchronize(stream)); // slot 0 (the start state) is stored
             slot_ev.resize((size_t)nmc, nullptr);
         }
-        for (int i = 0; i < n_iter; ++i) {
-            step_once();
+        const bool per_slot = streaming || (progress && report_length > 0);
+        for (int i = 0; i < n_iter;) {
+            if (persist) {
+                // whole iterations per launch: up to the next stored sample when results are streamed, else up to the batch limit
+                int n = std::min(n_iter - i, sampler_max_batch);
+                if (per_slot) n = std::min(n, thin - (int)(h_iter % (uint32_t)thin));
+                run_persist(n);
+                i += n;
+            } else {
+                step_once();
+                ++i;
+            }
             if (streaming && h_iter % (uint32_t)thin == 0 && h_iter / (uint32_t)thin < (uint32_t)nmc) {
                 // slot k is complete once this iteration is; it is sent one slot late, so that the (host-blocking, for
                 // pageable arrays) copy runs while the device already works on the iterations of the next slot
@@ -1225,7 +1411,9 @@ struct ggdmc_engine {
         if (elapsed_ms) CUDA_CHECK(cudaEventElapsedTime(elapsed_ms, ev0, ev1));
         if (profile) collect_profile();
         trace.dump(g_nccl.comm ? g_nccl.rank : 0);
-        if (kind == 2 && g_p2p.ready && g_p2p.timed_out()) throw Error(GGDMC_ERR_COMM, "peer exchange timed out: a rank did not arrive");
+        check_sampler_status();
+        if (kind == 2 && g_nccl.comm && g_nccl.n_rank > 1 && g_p2p.ready && g_p2p.timed_out())
+            throw Error(GGDMC_ERR_COMM, "peer exchange timed out: a rank did not arrive");
     }
 
     // Timed iterations with an L2 flush (a memset larger than L2) before each one; only the iterations
@@ -1244,7 +1432,8 @@ struct ggdmc_engine {
             // up again before the bracket opens, so that the skew of the memsets is not booked as exchange wait
             if (kind == 2 && g_nccl.comm && g_nccl.n_rank > 1 && g_p2p.ready) k_peer_barrier<<<1, 32, 0, stream>>>(g_p2p.win);
             CUDA_CHECK(cudaEventRecord(ev[2 * i], stream));
-            step_once();
+            if (persist) run_persist(1);
+            else step_once();
             CUDA_CHECK(cudaEventRecord(ev[2 * i + 1], stream));
         }
         CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1258,6 +1447,7 @@ struct ggdmc_engine {
         for (auto &e : ev) cudaEventDestroy(e);
         if (elapsed_ms) *elapsed_ms = (float)total;
         if (profile) collect_profile();
+        check_sampler_status();
     }
 
 };
@@ -1504,6 +1694,49 @@ int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *t
         CUDA_CHECK(cudaMemcpy(h.data(), d_out.p, h.size() * 8, cudaMemcpyDeviceToHost));
         for (int k = 0; k < n_theta; ++k)
             for (int i = 0; i < ntr; ++i) out[(size_t)k * ntr + T.order[0][i]] = h[(size_t)k * ntr + i];
+    }
+    GG_CATCH
+}
+
+int ggdmc_b200_trial_logdens_hot(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta, int32_t n_theta,
+                                 uint64_t seed, uint32_t pop, uint32_t iter, double *out, double *sums, char err[256])
+{
+    GG_TRY
+    require(model && trials && theta && out && n_theta >= 1, "bad arguments");
+    require(trials->n_subject == 1, "trial_logdens takes exactly one subject");
+    require(model->type == GGDMC_MODEL_LBA, "trial_logdens_hot is an LBA probe");
+    pick_device(-1);
+    ModelDev M;
+    M.upload(model);
+    TrialsDev T;
+    T.upload(trials, model->n_cell, true);
+    T.set_chunking(n_theta);
+    T.d.counter = nullptr;
+    const int ntr = T.h_count[0];
+    DBuf<double> d_theta, d_out, d_sums;
+    d_theta.upload(theta, (size_t)n_theta * model->npar);
+    d_out.alloc((size_t)n_theta * std::max(ntr, 1));
+    d_sums.alloc((size_t)n_theta * T.d.nsplit);
+    if (ntr > 0) {
+        switch (M.d.n_acc) {
+        case 2: launch_trial_logdens_hot<2>(M.d, T.d, d_theta.p, n_theta, ntr, seed, pop, iter, d_out.p, d_sums.p); break;
+        case 3: launch_trial_logdens_hot<3>(M.d, T.d, d_theta.p, n_theta, ntr, seed, pop, iter, d_out.p, d_sums.p); break;
+        case 4: launch_trial_logdens_hot<4>(M.d, T.d, d_theta.p, n_theta, ntr, seed, pop, iter, d_out.p, d_sums.p); break;
+        default: launch_trial_logdens_hot<0>(M.d, T.d, d_theta.p, n_theta, ntr, seed, pop, iter, d_out.p, d_sums.p);
+        }
+        std::vector<double> h((size_t)n_theta * ntr), hs((size_t)n_theta * T.d.nsplit);
+        CUDA_CHECK(cudaMemcpy(h.data(), d_out.p, h.size() * 8, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(hs.data(), d_sums.p, hs.size() * 8, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < n_theta; ++k) {
+            for (int i = 0; i < ntr; ++i) out[(size_t)k * ntr + T.order[0][i]] = h[(size_t)k * ntr + i];
+            if (sums) {
+                double v = 0.0;
+                for (int q = 0; q < T.d.nsplit; ++q) v += hs[(size_t)k * T.d.nsplit + q];
+                sums[k] = v;
+            }
+        }
+    } else if (sums) {
+        for (int k = 0; k < n_theta; ++k) sums[k] = 0.0;
     }
     GG_CATCH
 }

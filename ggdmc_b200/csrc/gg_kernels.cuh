@@ -98,6 +98,15 @@ __device__ __forceinline__ double runif_from(double lo, double hi, double u)
     return __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));
 }
 
+// Load of MUTABLE sampler state (theta, lp, ll, proposals, targets, migration sets, phi constants, partial sums):
+// L2 only.  Inside the persistent sampler kernel (gg_sampler.cuh) other CTAs rewrite this state while the kernel runs,
+// and an L1 line filled in an earlier iteration would be stale; the multi-launch kernels lose nothing by it.
+template <class T>
+__device__ __forceinline__ T ldm(const T *p)
+{
+    return __ldcg(p);
+}
+
 // ------------------------------------------------------------------------------------------------
 // block-wide sum of one double per thread (warp shuffles, then one shared-memory pass)
 // ------------------------------------------------------------------------------------------------
@@ -125,23 +134,22 @@ __device__ __forceinline__ double block_sum(double v, double *scratch /* [BLOCK/
 // decide_once = 1: run_chains (src/de.cpp:201-242): ONE draw per iteration (made in sweep 0); a
 //                  migration is a single unblocked sweep, so migrating populations idle (mode 2)
 //                  in the remaining blocked sweeps.
-__global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int decide_once, int para_idx)
+// block-wide; sm_keys: 2 * nchain ints of shared memory.  The caller provides a barrier before sm_keys is reused.
+__device__ __forceinline__ void sweep_begin_pop(const Level &L, int p, uint32_t iter, int sweep, int decide_once, int para_idx, int *sm_keys,
+                                                int *s_mode_n /* 2 ints of shared memory */)
 {
-    extern __shared__ int sm_keys[]; // keys [C], ranks [C]
-    const int p = blockIdx.x, C = L.nchain, tid = threadIdx.x;
-    const uint32_t iter = *d_iter;
-    __shared__ int s_mode, s_n;
+    const int C = L.nchain, tid = threadIdx.x, nthr = blockDim.x;
     DrawAddr a = make_addr(L, p, iter, decide_once ? 0 : sweep, 0);
     if (tid == 0) {
         int mode;
         if (decide_once && sweep > 0) {
-            mode = L.mode0[p] ? 2 : 0;
+            mode = ldm(L.mode0 + p) ? 2 : 0;
         } else {
             double u = draw_uniform(a, U_DECIDE, 0);
             mode = (u < L.mig_prob) ? 1 : 0;
             L.mode0[p] = mode;
         }
-        s_mode = mode;
+        s_mode_n[0] = mode;
         L.mode[p] = mode;
         L.para[p] = (decide_once && mode == 1) ? -1 : para_idx;
         if (mode == 1) { // get_subchains, src/de.cpp:64-70
@@ -149,17 +157,17 @@ __global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int de
             unsigned n = (unsigned)ceil((double)C * prop);
             n = n < 2u ? 2u : n;
             n = n > (unsigned)C ? (unsigned)C : n;
-            s_n = (int)n;
+            s_mode_n[1] = (int)n;
             L.mig_n[p] = (int)n;
         } else if (mode == 2) {
             L.mig_n[p] = 0;
         }
     }
-    for (int c = tid; c < C; c += blockDim.x) L.target[p * C + c] = -1;
+    for (int c = tid; c < C; c += nthr) L.target[p * C + c] = -1;
     __syncthreads();
-    if (s_mode != 1) return;
+    if (s_mode_n[0] != 1) return;
     // arma::shuffle keys for all chains, then the n smallest keys (ties by position), sorted by index
-    for (int blk = tid; blk * 4 < C; blk += blockDim.x) {
+    for (int blk = tid; blk * 4 < C; blk += nthr) {
         U4 w = draw_block(a, U_MIG_KEYS, (uint32_t)blk);
         int j = blk * 4;
         sm_keys[j] = shuffle_key(word_to_uniform(w.x));
@@ -168,9 +176,9 @@ __global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int de
         if (j + 3 < C) sm_keys[j + 3] = shuffle_key(word_to_uniform(w.w));
     }
     __syncthreads();
-    const int n = s_n;
+    const int n = s_mode_n[1];
     int *sm_rank = sm_keys + C;
-    for (int j = tid; j < C; j += blockDim.x) {
+    for (int j = tid; j < C; j += nthr) {
         const int kj = sm_keys[j];
         int rank = 0;
         for (int k = 0; k < C; ++k) {
@@ -180,13 +188,20 @@ __global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int de
         sm_rank[j] = rank;
     }
     __syncthreads();
-    for (int j = tid; j < C; j += blockDim.x) {
+    for (int j = tid; j < C; j += nthr) {
         if (sm_rank[j] < n) { // selected: position among the selected chains in ascending index order
             int pos = 0;
             for (int k = 0; k < j; ++k) pos += sm_rank[k] < n;
             L.mig_list[p * C + pos] = j;
         }
     }
+}
+
+__global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int decide_once, int para_idx)
+{
+    extern __shared__ int sm_keys[]; // keys [C], ranks [C]
+    __shared__ int s_mode_n[2];
+    sweep_begin_pop(L, blockIdx.x, *d_iter, sweep, decide_once, para_idx, sm_keys, s_mode_n);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -276,12 +291,12 @@ __device__ __forceinline__ double prior_term(const Level &L, int d, double x, co
 {
     const int D = L.npar;
     const double lo = L.prior.lower[d], up = L.prior.upper[d];
-    const double K = oc ? oc[2 * d + 1] : NAN;
+    const double K = oc ? ldm(oc + 2 * d + 1) : NAN;
     if (K == K) { // phi-driven truncated normal, log scale: -(ln sqrt(2 pi) + z^2/2 + ln sd) - ln denom
-        const double z = (x - ovr[d]) * oc[2 * d];
+        const double z = (x - ldm(ovr + d)) * ldm(oc + 2 * d);
         return (x < lo || x > up) ? -INFINITY : -(0.5 * z * z + K);
     }
-    const double q0 = ovr ? ovr[d] : L.prior.p0[d], q1 = ovr ? ovr[D + d] : L.prior.p1[d];
+    const double q0 = ovr ? ldm(ovr + d) : L.prior.p0[d], q1 = ovr ? ldm(ovr + D + d) : L.prior.p1[d];
     return dprior1(L.prior.dist[d], x, q0, q1, lo, up, L.prior.log_p[d] != 0);
 }
 
@@ -296,10 +311,10 @@ __device__ __forceinline__ double deferred_prop_lp(const Level &L, int p, int sr
     double a1 = 0.0, a2 = 0.0; // arma::accu order, as sum_arma_order
     int d = 0;
     for (; d + 1 < D; d += 2) {
-        a1 += prior_term(L, d, pr[d], ovr, oc);
-        a2 += prior_term(L, d + 1, pr[d + 1], ovr, oc);
+        a1 += prior_term(L, d, ldm(pr + d), ovr, oc);
+        a2 += prior_term(L, d + 1, ldm(pr + d + 1), ovr, oc);
     }
-    if (d < D) a1 += prior_term(L, d, pr[d], ovr, oc);
+    if (d < D) a1 += prior_term(L, d, ldm(pr + d), ovr, oc);
     return a1 + a2;
 }
 
@@ -314,8 +329,8 @@ __device__ __forceinline__ void propose_position(const Level &L, int p, int k, i
     const int C = L.nchain, D = L.npar;
     int c0 = 0, c1 = 0;
     if (mode) {
-        src = L.mig_list[p * C + k];
-        tgt = L.mig_list[p * C + ((k + 1 == nsteps) ? 0 : k + 1)];
+        src = ldm(L.mig_list + p * C + k);
+        tgt = ldm(L.mig_list + p * C + ((k + 1 == nsteps) ? 0 : k + 1));
     } else {
         src = k;
         tgt = k;
@@ -346,12 +361,12 @@ __device__ __forceinline__ void propose_position(const Level &L, int p, int k, i
         my_word = q == 0 ? x : (q == 1 ? y : (q == 2 ? z : w4));
     }
     for (int d = lane; d < D; d += 32) {
-        double x = th[d];
+        double x = ldm(th + d);
         const bool moved = para_idx >= 0 ? (d == para_idx) : (d < L.nmove);
         if (moved) {
             double u = one_pass ? word_to_uniform(my_word) : draw_uniform(a, U_NOISE, (uint32_t)d);
             double noise = runif_from(-L.rp, L.rp, u);
-            double inc = mode ? noise : __dadd_rn(noise, __dmul_rn(L.gamma, __dsub_rn(t0[d], t1[d])));
+            double inc = mode ? noise : __dadd_rn(noise, __dmul_rn(L.gamma, __dsub_rn(ldm(t0 + d), ldm(t1 + d))));
             x = __dadd_rn(x, inc);
         }
         pr[d] = x;
@@ -519,29 +534,26 @@ __device__ __forceinline__ void build_cell_table(const DevModel &M, const double
     __syncthreads();
 }
 
-// sum-log-likelihood of ONE proposal (population p, chain) over one trial chunk, by the whole block
-template <int NACC, int BLOCK>
-__device__ __forceinline__ void like_one(const Level &L, const DevModel &M, const TrialData &T, uint32_t iter, int sweep, int p,
-                                         int chain, int split, double *ll_part, unsigned char *sm_raw)
+// sum-log-likelihood of ONE parameter vector `th` (global or shared memory) for local subject s over trial chunk `split`, by
+// the whole block; addr addresses the draws of `t0 + st0 U`.  The sum is returned in thread 0 (0 for an empty chunk).
+// sm_raw: like_smem() bytes of shared memory; the caller provides a barrier before it is reused.
+// TRACE (parity entry point ggdmc_b200_trial_logdens_hot only): every density the loops fold into the running product is
+// also written, as its log, to trace_out[trial] -- the production loops, the production trial functions.
+template <int NACC, int BLOCK, bool TRACE = false>
+__device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &T, const double *th, const DrawAddr &addr, int s, int split,
+                                            unsigned char *sm_raw, double *trace_out = nullptr)
 {
-    const int C = L.nchain, D = L.npar, na = M.n_acc;
-    const int s = p / L.n_rep;
+    const int na = M.n_acc;
     const int ntr = T.count[s]; // these two loads are only needed after the table is built: they travel meanwhile
     const int64_t t_off = T.offset[s];
     const int t_begin = split * T.chunk;
-    double *part = ll_part + ((size_t)p * C + chain) * T.nsplit + split;
     CellAcc *ent = reinterpret_cast<CellAcc *>(sm_raw);
     double *red = reinterpret_cast<double *>(ent + M.n_cell * na);
     uint8_t *bad = reinterpret_cast<uint8_t *>(red + BLOCK / 32);
-    const double *th = L.prop + ((size_t)p * C + chain) * D;
-    DrawAddr addr = make_addr(L, p, iter, sweep, chain);
     build_cell_table<BLOCK>(M, th, ent, bad, addr);
     unsigned long long *bslot = (T.btrace && threadIdx.x == 0) ? T.btrace + 5 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
     if (bslot) bslot[3] = BlockTrace::now();
-    if (t_begin >= ntr) { // empty chunk (a subject with fewer trials than the longest one)
-        if (threadIdx.x == 0) *part = 0.0;
-        return;
-    }
+    if (t_begin >= ntr) return 0.0; // empty chunk (a subject with fewer trials than the longest one)
 
     const int t_end = min(ntr, t_begin + T.chunk);
     const double *rt = T.rt + t_off;
@@ -574,6 +586,10 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
                 }
                 acc.mul_fast(p0);
                 acc.mul_fast(p1);
+                if constexpr (TRACE) {
+                    trace_out[t] = log(p0);
+                    trace_out[t + 1] = log(p1);
+                }
             } else
                 leftovers = true;
         }
@@ -591,6 +607,7 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
                     double pdf = n1pdf_any<NACC>(bad[c], rt[t + h], ent + c * na, na);
                     if (zf > 0.0 && pdf <= 0.0) pdf = zf;
                     acc.mul(pdf);
+                    if constexpr (TRACE) trace_out[t + h] = log(pdf);
                 }
             }
         }
@@ -608,6 +625,7 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
                     double pdf = n1pdf_fast<NACC>(r, e, na);
                     if (zf > 0.0 && pdf <= 0.0) pdf = zf;
                     acc.mul_fast(pdf);
+                    if constexpr (TRACE) trace_out[t + h] = log(pdf);
                 } else
                     leftovers = true;
             }
@@ -624,16 +642,26 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
                     double pdf = cls == kCellInvalid ? kFloor : n1pdf_generic_body<NACC>(r, e, na);
                     if (zf > 0.0 && pdf <= 0.0) pdf = zf;
                     acc.mul(pdf);
+                    if constexpr (TRACE) trace_out[t + h] = log(pdf);
                 }
             }
         }
     }
     if (bslot) bslot[4] = BlockTrace::now();
     double v = block_sum<BLOCK>(acc.value(), red);
-    if (threadIdx.x == 0) {
-        *part = v;
-        if (T.counter) atomicAdd(T.counter, (unsigned long long)(t_end - t_begin));
-    }
+    if (threadIdx.x == 0 && T.counter) atomicAdd(T.counter, (unsigned long long)(t_end - t_begin));
+    return v;
+}
+
+// sum-log-likelihood of ONE proposal (population p, chain) over one trial chunk, by the whole block
+template <int NACC, int BLOCK>
+__device__ __forceinline__ void like_one(const Level &L, const DevModel &M, const TrialData &T, uint32_t iter, int sweep, int p,
+                                         int chain, int split, double *ll_part, unsigned char *sm_raw)
+{
+    const int C = L.nchain, D = L.npar;
+    const double v = like_eval<NACC, BLOCK>(M, T, L.prop + ((size_t)p * C + chain) * D, make_addr(L, p, iter, sweep, chain), p / L.n_rep, split,
+                                            sm_raw);
+    if (threadIdx.x == 0) ll_part[((size_t)p * C + chain) * T.nsplit + split] = v;
 }
 
 // DDM twin of like_one (model type "fastdm"): sum over one trial chunk of log(max(g(rt), DBL_MIN))
@@ -784,6 +812,19 @@ __global__ void __launch_bounds__(BLOCK) k_trial_logdens(DevModel M, const doubl
     }
 }
 
+// Per-trial log densities through the PRODUCTION trial loops (like_eval with TRACE): block (theta k, subject 0, chunk y).
+// sums[k * nsplit + y] also receives the chunk's sum as the sampler would see it.
+template <int NACC, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_trial_logdens_hot(DevModel M, TrialData T, const double *theta, int ntr, uint64_t seed, uint32_t pop,
+                                                             uint32_t iter, double *out, double *sums)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int k = blockIdx.x;
+    DrawAddr addr = {seed, pop, iter, 0u, (uint32_t)k};
+    const double v = like_eval<NACC, BLOCK, true>(M, T, theta + (size_t)k * M.npar, addr, 0, blockIdx.y, sm_raw, out + (size_t)k * ntr);
+    if (threadIdx.x == 0) sums[(size_t)k * T.nsplit + blockIdx.y] = v;
+}
+
 // the same for the DDM: log(max(density, DBL_MIN)) of every trial (@hdr/likelihood.h:303)
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_trial_logdens_ddm(DevModel M, const double *rt, const uint16_t *cl, int ntr,
@@ -811,9 +852,33 @@ __global__ void __launch_bounds__(BLOCK) k_trial_logdens_ddm(DevModel M, const d
 // ------------------------------------------------------------------------------------------------
 // K3: Metropolis accept / commit at the subject level (update_theta, src/de.cpp:81-108)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *ll_part, int nsplit)
+// MH test of the proposal made from chain src of population p, if one is pending (update_theta, src/de.cpp:81-108)
+__device__ __forceinline__ void accept_one(const Level &L, int p, int src, uint32_t iter, int sweep, const double *ll_part, int nsplit)
 {
     const int C = L.nchain, D = L.npar;
+    const int tgt = ldm(L.target + p * C + src);
+    if (tgt < 0) return;
+    double tmp_ll = 0.0;
+    const double *part = ll_part + ((size_t)p * C + src) * nsplit;
+    for (int k = 0; k < nsplit; ++k) tmp_ll += ldm(part + k);
+    const double tmp_lp = L.prior_ovr ? deferred_prop_lp(L, p, src) : ldm(L.prop_lp + p * C + src);
+    const double cur = ldm(L.lp + p * C + tgt) + ldm(L.ll + p * C + tgt); // src/de.cpp:121 / :189-190 / :577 / :656-657
+    const double mh = exp((tmp_lp + tmp_ll) - cur);                       // :147
+    L.target[p * C + src] = -1;                                            // proposal consumed
+    if (isnan(mh)) return;                                                 // :83-87, no draw
+    DrawAddr a = make_addr(L, p, iter, sweep, src);
+    if (draw_uniform(a, U_ACCEPT, 0) < mh) {                               // :88
+        const double *pr = L.prop + ((size_t)p * C + src) * D;
+        double *th = L.theta + ((size_t)p * C + tgt) * D;
+        for (int d = 0; d < D; ++d) th[d] = ldm(pr + d);
+        L.lp[p * C + tgt] = tmp_lp;
+        L.ll[p * C + tgt] = tmp_ll;
+    }
+}
+
+__global__ void k_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *ll_part, int nsplit)
+{
+    const int C = L.nchain;
     int p, src;
     if (step < 0) {
         int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -830,24 +895,7 @@ __global__ void k_accept(Level L, const uint32_t *d_iter, int sweep, int step, c
         } else
             src = step;
     }
-    const int tgt = L.target[p * C + src];
-    if (tgt < 0) return;
-    double tmp_ll = 0.0;
-    const double *part = ll_part + ((size_t)p * C + src) * nsplit;
-    for (int k = 0; k < nsplit; ++k) tmp_ll += part[k];
-    const double tmp_lp = L.prior_ovr ? deferred_prop_lp(L, p, src) : L.prop_lp[p * C + src];
-    const double cur = L.lp[p * C + tgt] + L.ll[p * C + tgt];     // src/de.cpp:121 / :189-190 / :577 / :656-657
-    const double mh = exp((tmp_lp + tmp_ll) - cur);               // :147
-    L.target[p * C + src] = -1;                                    // proposal consumed
-    if (isnan(mh)) return;                                         // :83-87, no draw
-    DrawAddr a = make_addr(L, p, *d_iter, sweep, src);
-    if (draw_uniform(a, U_ACCEPT, 0) < mh) {                       // :88
-        const double *pr = L.prop + ((size_t)p * C + src) * D;
-        double *th = L.theta + ((size_t)p * C + tgt) * D;
-        for (int d = 0; d < D; ++d) th[d] = pr[d];
-        L.lp[p * C + tgt] = tmp_lp;
-        L.ll[p * C + tgt] = tmp_ll;
-    }
+    accept_one(L, p, src, *d_iter, sweep, ll_part, nsplit);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -869,20 +917,25 @@ struct HyperArgs {
 
 // hyper-likelihood terms of one block: the subjects [s_begin, s_end) of (replicate r, chain c) under the
 // current phi (cm, cs, cl) and the proposed phi (pm, ps, pl); sm_h layout as in k_hyper
+// phi_c: global memory (mutable state); phi_p: the proposal, in shared memory (prop_in_smem) or global memory, read only
+// when has_prop
 template <int BLOCK>
 __device__ __forceinline__ void hyper_block(const HyperArgs &H, int r, int c, int split, const double *phi_c, const double *phi_p,
-                                            bool has_prop, double *sm_h, double &vc, double &vp)
+                                            bool has_prop, bool prop_in_smem, double *sm_h, double &vc, double &vp)
 {
     const int D = H.D;
     double *cm = sm_h, *cs = cm + D, *cl = cs + D, *pm = cl + D, *ps = pm + D, *pl = ps + D, *red = pl + D;
     for (int d = threadIdx.x; d < D; d += BLOCK) {
         const double lo = H.like.lower[d], up = H.like.upper[d];
-        double m = phi_c[d], s = phi_c[D + d];
+        double m = ldm(phi_c + d), s = ldm(phi_c + D + d);
         cm[d] = m; cs[d] = s;
-        cl[d] = log(pnorm5(up, m, s, true) - pnorm5(lo, m, s, true)); // tnorm_class::set_parameters, @hdr/tnorm.h:59-67
-        m = phi_p[d]; s = phi_p[D + d];
-        pm[d] = m; ps[d] = s;
-        pl[d] = log(pnorm5(up, m, s, true) - pnorm5(lo, m, s, true));
+        if (H.need_cur) cl[d] = log(pnorm5(up, m, s, true) - pnorm5(lo, m, s, true)); // tnorm_class::set_parameters, @hdr/tnorm.h:59-67
+        if (has_prop) {
+            m = prop_in_smem ? phi_p[d] : ldm(phi_p + d);
+            s = prop_in_smem ? phi_p[D + d] : ldm(phi_p + D + d);
+            pm[d] = m; ps[d] = s;
+            pl[d] = log(pnorm5(up, m, s, true) - pnorm5(lo, m, s, true));
+        }
     }
     __syncthreads();
     const int s_begin = split * H.subj_per_block, s_end = min(H.S, s_begin + H.subj_per_block);
@@ -891,7 +944,7 @@ __device__ __forceinline__ void hyper_block(const HyperArgs &H, int r, int c, in
     double sum_c = 0.0, sum_p = 0.0;
     for (int e = threadIdx.x; e < n_el; e += BLOCK) {
         const int si = e / D, d = e - si * D;
-        const double x = xbase[(size_t)(s_begin + si) * H.x_subj_stride + d];
+        const double x = ldm(xbase + (size_t)(s_begin + si) * H.x_subj_stride + d);
         const int dist = H.like.dist[d];
         const bool lg = H.like.log_p[d] != 0;
         const double lo = H.like.lower[d], up = H.like.upper[d];
@@ -932,7 +985,7 @@ __global__ void __launch_bounds__(BLOCK) k_hyper(Level L, HyperArgs H, int step,
     const int split = blockIdx.y;
     double vc, vp;
     hyper_block<BLOCK>(H, r, c, split, L.theta + ((size_t)r * C + c) * 2 * D, L.prop + ((size_t)r * C + c) * 2 * D,
-                       L.target[r * C + c] >= 0, sm_h, vc, vp);
+                       L.target[r * C + c] >= 0, false, sm_h, vc, vp);
     if (threadIdx.x == 0) {
         double *o = hpart + (((size_t)r * C + c) * 2) * H.nsplit + split;
         o[0] = vc;
@@ -963,7 +1016,10 @@ __global__ void k_hyper_reduce(const double *hpart, int n, int nsplit, double *h
 //   4. thread i sums slots[b][0..n_rank)[i] in rank order -> identical bits on every rank
 // Parity double-buffering is enough: a rank can only start exchange seq + 2 after every peer has
 // raised its seq + 1 flag, i.e. after every peer finished reading exchange seq.
-// A bounded spin (about 2 s) sets *status instead of hanging the GPU if a peer never arrives.
+// A bounded spin (spin_ns) sets *status instead of hanging the GPU if a peer never arrives; the function then returns
+// false in every thread and the callers do no further work on the exchanged sums (no MH test on partial sums): the
+// host finds the status word set at its next synchronisation and reports GGDMC_ERR_COMM.  Once set, the status word
+// makes every later exchange of the process return false immediately until ggdmc_b200_comm_finalize().
 // ------------------------------------------------------------------------------------------------
 constexpr int kP2PMaxN = 4096;   // doubles per exchange (2 * nchain * n_replicate)
 constexpr int kP2PMaxRanks = 16;
@@ -974,12 +1030,20 @@ struct P2PWindow {
     unsigned long long *seq;                   // local exchange counter (device memory)
     int *status;                               // local: set to 1 on timeout
     int n_rank, rank;
+    unsigned long long spin_ns;                // how long a rank waits for its peers (GGDMC_B200_PEER_TIMEOUT_S, default 120 s)
 };
 
-// block-wide: reduce the nsplit partials of every value, exchange with the peers, leave the all-rank sums in hsum
-__device__ __forceinline__ void reduce_exchange_block(const double *hpart, int n, int nsplit, double *hsum, const P2PWindow &w)
+__device__ __forceinline__ unsigned long long globaltimer_ns()
 {
-    const unsigned long long seq = *w.seq + 1;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// block-wide: reduce the nsplit partials of every value, exchange with the peers, leave the all-rank sums in hsum
+__device__ __forceinline__ bool reduce_exchange_block(const double *hpart, int n, int nsplit, double *hsum, const P2PWindow &w)
+{
+    const unsigned long long seq = ldm(w.seq) + 1;
     const int b = (int)(seq & 1ull);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double v = 0.0;
@@ -994,18 +1058,19 @@ __device__ __forceinline__ void reduce_exchange_block(const double *hpart, int n
     }
     if (threadIdx.x < w.n_rank) {
         volatile unsigned long long *mine = w.flags[w.rank] + (size_t)b * kP2PMaxRanks + threadIdx.x;
-        const long long t0 = clock64();
+        const unsigned long long t0 = globaltimer_ns();
         while (*mine < seq) {
             if (*(volatile int *)w.status) break; // an earlier exchange already timed out: do not wait again
             __nanosleep(64);
-            if (clock64() - t0 > 4000000000ll) { // ~2 s at 2 GHz: a peer is gone
-                *w.status = 1;
+            if (globaltimer_ns() - t0 > w.spin_ns) { // a peer is gone
+                *(volatile int *)w.status = 1;
                 break;
             }
         }
     }
     __threadfence_system();
     __syncthreads();
+    if (*(volatile int *)w.status) return false; // block-uniform: read after the barrier, never cleared while kernels run
     const double *loc = w.slots[w.rank] + (size_t)b * w.n_rank * kP2PMaxN;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double v = 0.0;
@@ -1014,6 +1079,7 @@ __device__ __forceinline__ void reduce_exchange_block(const double *hpart, int n
     }
     __syncthreads();
     if (threadIdx.x == 0) *w.seq = seq;
+    return true;
 }
 
 __global__ void __launch_bounds__(256) k_hyper_reduce_exchange(const double *hpart, int n, int nsplit, double *hsum, P2PWindow w)
@@ -1021,7 +1087,8 @@ __global__ void __launch_bounds__(256) k_hyper_reduce_exchange(const double *hpa
     reduce_exchange_block(hpart, n, nsplit, hsum, w);
 }
 
-// all ranks arrive (an exchange of zero values): used to line the ranks up outside timed regions
+// all ranks arrive (an exchange of zero values): lines the ranks up at the end of engine construction and at the start
+// of every iterate call (the exchange inside the sampler assumes lock step within spin_ns), and outside timed regions
 __global__ void k_peer_barrier(P2PWindow w) { reduce_exchange_block(nullptr, 0, 0, nullptr, w); }
 
 // phi-level accept of the proposal made from chain src (src/de.cpp:397-400, 427-463 and :494-500, 519-549)
@@ -1029,17 +1096,17 @@ __device__ __forceinline__ void phi_accept_one(const Level &L, int r, int src, u
                                                const double *hsum, int need_cur)
 {
     const int C = L.nchain, D = L.npar;
-    const int tgt = L.target[r * C + src];
+    const int tgt = ldm(L.target + r * C + src);
     if (tgt < 0) return;
-    const double tmp_ll = hsum[((size_t)r * C + src) * 2 + 1];
-    const double tmp_lp = L.prop_lp[r * C + src];
-    double cur_ll = L.ll[r * C + tgt];
+    const double tmp_ll = ldm(hsum + ((size_t)r * C + src) * 2 + 1);
+    const double tmp_lp = ldm(L.prop_lp + r * C + src);
+    double cur_ll = ldm(L.ll + r * C + tgt);
     if (need_cur) {
-        cur_ll = hsum[((size_t)r * C + tgt) * 2 + 0];
-        if (in_place_migration) L.ll[r * C + src] = hsum[((size_t)r * C + src) * 2 + 0]; // :494-496 (in place order only)
+        cur_ll = ldm(hsum + ((size_t)r * C + tgt) * 2 + 0);
+        if (in_place_migration) L.ll[r * C + src] = ldm(hsum + ((size_t)r * C + src) * 2 + 0); // :494-496 (in place order only)
         L.ll[r * C + tgt] = cur_ll; // :397-398 / :498-500
     }
-    const double cur = L.lp[r * C + tgt] + cur_ll;
+    const double cur = ldm(L.lp + r * C + tgt) + cur_ll;
     const double mh = exp((tmp_lp + tmp_ll) - cur);
     L.target[r * C + src] = -1; // proposal consumed
     if (isnan(mh)) return;
@@ -1047,16 +1114,18 @@ __device__ __forceinline__ void phi_accept_one(const Level &L, int r, int src, u
     if (draw_uniform(a, U_ACCEPT, 0) < mh) {
         const double *pr = L.prop + ((size_t)r * C + src) * D;
         double *th = L.theta + ((size_t)r * C + tgt) * D;
-        for (int d = 0; d < D; ++d) th[d] = pr[d];
+        for (int d = 0; d < D; ++d) th[d] = ldm(pr + d);
         L.lp[r * C + tgt] = tmp_lp;
         L.ll[r * C + tgt] = tmp_ll;
     }
 }
 
-__global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *hsum, int need_cur)
+// status: the peer window's status word (or null); set = the exchange before this launch timed out, hsum is not valid
+__global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *hsum, int need_cur, const int *status)
 {
     const int C = L.nchain;
     int r, src;
+    if (status && *status) return;
     if (step < 0) {
         int g = blockIdx.x * blockDim.x + threadIdx.x;
         if (g >= L.npop * C) return;
@@ -1083,17 +1152,16 @@ __global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int ste
 //   peer-memory window (multi-GPU), MH test of every proposal.
 // Replaces k_propose + k_hyper + k_hyper_reduce(_exchange) + k_phi_accept on the phi critical path.
 // ------------------------------------------------------------------------------------------------
+// Part 1, every block (replicate r, chain c, subject split): proposal + the block's share of the two sums -> hpart.
+// sm_h: 6 D + 2 BLOCK/32 doubles (hyper_block), then proposal [2 D], prior scratch [2 D]; s_k: one int of shared memory.
+// Returns (block-uniform) the sweep position at which chain c proposes in this half, -1 if it does not.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_phi_half(Level L, HyperArgs H, const uint32_t *d_iter, int sweep, int half, double *hpart,
-                                                    double *hsum, unsigned int *ticket, P2PWindow w, int use_p2p)
+__device__ __forceinline__ int phi_half_part(const Level &L, const HyperArgs &H, uint32_t iter, int sweep, int half, int r, int c, int split,
+                                             double *hpart, double *sm_h, int *s_k)
 {
-    extern __shared__ double sm_h[]; // hyper_block's 6 D + 2 BLOCK/32, then proposal [2 D], prior scratch [2 D]
-    __shared__ int s_k, s_last;
     const int C = L.nchain, D = H.D, D2 = 2 * D;
-    const int r = blockIdx.x / C, c = blockIdx.x - r * C, split = blockIdx.y;
-    const uint32_t iter = *d_iter;
-    const int mode = L.mode[r], para_idx = L.para[r];
-    const int nsteps = mode ? L.mig_n[r] : C;
+    const int mode = ldm(L.mode + r), para_idx = ldm(L.para + r);
+    const int nsteps = mode ? ldm(L.mig_n + r) : C;
     double *sprop = sm_h + 6 * D + 2 * (BLOCK / 32), *scratch = sprop + D2;
     if (threadIdx.x == 0) { // sweep position at which chain c proposes in this launch, -1: it does not
         int k = -1;
@@ -1101,12 +1169,12 @@ __global__ void __launch_bounds__(BLOCK) k_phi_half(Level L, HyperArgs H, const 
             if (half < 0 || (c & 1) == half) k = c;
         } else if (mode == 1 && half <= 0) {
             for (int j = 0; j < nsteps; ++j)
-                if (L.mig_list[r * C + j] == c) { k = j; break; }
+                if (ldm(L.mig_list + r * C + j) == c) { k = j; break; }
         }
-        s_k = k;
+        *s_k = k;
     }
     __syncthreads();
-    const int k = s_k;
+    const int k = *s_k;
     if (k >= 0 && threadIdx.x < 32) {
         int src, tgt;
         double lp;
@@ -1122,30 +1190,55 @@ __global__ void __launch_bounds__(BLOCK) k_phi_half(Level L, HyperArgs H, const 
     }
     __syncthreads();
     double vc, vp;
-    hyper_block<BLOCK>(H, r, c, split, L.theta + ((size_t)r * C + c) * D2, k >= 0 ? sprop : L.theta + ((size_t)r * C + c) * D2, k >= 0,
-                       sm_h, vc, vp);
+    hyper_block<BLOCK>(H, r, c, split, L.theta + ((size_t)r * C + c) * D2, sprop, k >= 0, true, sm_h, vc, vp);
     if (threadIdx.x == 0) {
         double *o = hpart + (((size_t)r * C + c) * 2) * H.nsplit + split;
         o[0] = vc;
         o[H.nsplit] = vp;
+    }
+    return k;
+}
+
+// Part 2, the block that finishes last: sum over the splits, exchange with the peer GPUs, MH test of every proposal.
+// Returns false (block-uniform) when the exchange timed out: nothing was accepted.
+template <int BLOCK>
+__device__ __forceinline__ bool phi_half_finish(const Level &L, const HyperArgs &H, uint32_t iter, int sweep, const double *hpart, double *hsum,
+                                                const P2PWindow &w, int use_p2p)
+{
+    const int C = L.nchain;
+    const int n = L.npop * C * 2;
+    if (use_p2p) {
+        if (!reduce_exchange_block(hpart, n, H.nsplit, hsum, w)) return false;
+    } else {
+        for (int i = threadIdx.x; i < n; i += BLOCK) {
+            double v = 0.0;
+            for (int q = 0; q < H.nsplit; ++q) v += ldm(hpart + (size_t)i * H.nsplit + q);
+            hsum[i] = v;
+        }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < L.npop * C; g += BLOCK) phi_accept_one(L, g / C, g - (g / C) * C, iter, sweep, false, hsum, H.need_cur);
+    return true;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_phi_half(Level L, HyperArgs H, const uint32_t *d_iter, int sweep, int half, double *hpart,
+                                                    double *hsum, unsigned int *ticket, P2PWindow w, int use_p2p)
+{
+    extern __shared__ double sm_h[]; // hyper_block's 6 D + 2 BLOCK/32, then proposal [2 D], prior scratch [2 D]
+    __shared__ int s_k, s_last;
+    const int C = L.nchain;
+    const int r = blockIdx.x / C, c = blockIdx.x - r * C, split = blockIdx.y;
+    const uint32_t iter = *d_iter;
+    phi_half_part<BLOCK>(L, H, iter, sweep, half, r, c, split, hpart, sm_h, &s_k);
+    if (threadIdx.x == 0) {
         __threadfence();
         s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int n = L.npop * C * 2;
-    if (use_p2p) {
-        reduce_exchange_block(hpart, n, H.nsplit, hsum, w);
-    } else {
-        for (int i = threadIdx.x; i < n; i += BLOCK) {
-            double v = 0.0;
-            for (int q = 0; q < H.nsplit; ++q) v += *(volatile const double *)(hpart + (size_t)i * H.nsplit + q);
-            hsum[i] = v;
-        }
-    }
-    __syncthreads();
-    for (int g = threadIdx.x; g < L.npop * C; g += BLOCK) phi_accept_one(L, g / C, g - (g / C) * C, iter, sweep, false, hsum, H.need_cur);
+    phi_half_finish<BLOCK>(L, H, iter, sweep, hpart, hsum, w, use_p2p);
     if (threadIdx.x == 0) *ticket = 0;
 }
 

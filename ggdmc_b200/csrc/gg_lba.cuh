@@ -38,7 +38,13 @@ GG_HD void cellacc_build(CellAcc &e, double A, double B, double mean_v, double s
     e.A = A;
     e.mean_v = mean_v;
     e.sd_v = sd_v;
-    e.t0a = (st0 != 0.0) ? t0 + st0 * u_st0 : t0 + st0 * 0.0; // lba.h:117 (t0 + 0*U == t0 + 0)
+    // lba.h:117: t0 + st0 * U as a separately rounded product and sum like the reference's scalar code (no FMA contraction:
+    // the value is a threshold -- rt > t0 -- and feeds every z of the cell); t0 + 0 * U == t0 + 0
+#ifdef __CUDA_ARCH__
+    e.t0a = __dadd_rn(t0, __dmul_rn(st0, (st0 != 0.0) ? u_st0 : 0.0));
+#else
+    e.t0a = t0 + st0 * ((st0 != 0.0) ? u_st0 : 0.0);
+#endif
     e.inv_sdv = inv_sdv;
     e.inv_A = rcp_table(A);
     e.inv_denom = posdrift ? rcp_table(denom) : 1.0;
@@ -79,7 +85,7 @@ GG_HD double n1pdf_generic_body(double rt, const CellAcc *e, int n_acc_rt)
         if (0.0 > dt) { // lba.h:217-219
             pdf = kFloor;
         } else if (A < kFloor) { // lba.h:221-227
-            pdf = fmax(b / (dt * dt) * dnorm4(b / dt, mv, sv, false) * e[0].inv_denom, kFloor);
+            pdf = fmax(b / (dt * dt) * (dnorm4(b / dt, mv, sv, false) * e[0].inv_denom), kFloor); // the reference divides the density by denom first
         } else { // lba.h:231-244
             double rts = e[0].inv_sdv * rdt, tv = mv * dt;
             PhiPair n1 = norm_both((b - tv) * rts);

@@ -280,6 +280,19 @@ def trial_logdens(ct: CellTable, trials: Trials, theta: np.ndarray) -> np.ndarra
     return out
 
 
+def trial_logdens_hot(ct: CellTable, trials: Trials, theta: np.ndarray, seed: int = 0, pop: int = 0, iteration: int = 0):
+    """Per-trial log n1PDF through the SAMPLER's trial loops (parity probe of the production path) -> ([n_theta, n_trial],
+    [n_theta] sums).  The `t0 + st0 U` draws are those of (seed, pop, iteration, sweep 0, chain = row of theta)."""
+    m, t = _model(ct), _trials([trials])
+    th = B.f64(np.atleast_2d(theta))
+    out = np.empty((th.shape[0], len(trials.rt)))
+    sums = np.empty(th.shape[0])
+    err = B.errbuf()
+    B.check(B.lib().ggdmc_b200_trial_logdens_hot(C.byref(m.c), C.byref(t.c), B.ptr(th), th.shape[0], C.c_uint64(seed), C.c_uint32(pop),
+                                                 C.c_uint32(iteration), B.ptr(out), B.ptr(sums), err), err)
+    return out, sums
+
+
 def sumloglike(ct: CellTable, trials: Sequence[Trials], theta: np.ndarray, init_rule: bool = False) -> np.ndarray:
     """theta [S, n_theta, npar] -> summed log-likelihoods [S, n_theta].  init_rule: densities <= 0 are floored at
     .Machine$double.eps like the R-side initialisation path does (R/phi.R:3-13)."""

@@ -172,6 +172,15 @@ int ggdmc_b200_run(const ggdmc_model_t *model, const ggdmc_trials_t *trials, con
 int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta,
                              int32_t n_theta, double *out, char err[256]);
 
+/* The same per-trial log densities (LBA only), but computed by the trial loops of the SAMPLER's likelihood code
+ * (two trials of a thread advanced in lock step for 2-accumulator models, the hot / cold split, the running product) --
+ * a parity probe of the production path, not something the reference exposes.  The draws of `t0 + st0 U`
+ * (@hdr/lba.h:117) are the addressed draws of (seed, population pop, iteration iter, sweep 0, chain k) for row k of
+ * theta, as in a fit.  sums (may be NULL) receives the n_theta summed log-likelihoods as the sampler would see them. */
+int ggdmc_b200_trial_logdens_hot(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta,
+                                 int32_t n_theta, uint64_t seed, uint32_t pop, uint32_t iter, double *out, double *sums,
+                                 char err[256]);
+
 /* likelihood_class::sumloglike (@hdr/likelihood.h:272-317) for every subject x n_theta vectors:
  * theta [n_subject][n_theta][npar] -> out [n_subject][n_theta]. */
 int ggdmc_b200_sumloglike(const ggdmc_model_t *model, const ggdmc_trials_t *trials, const double *theta,

@@ -119,7 +119,10 @@ int orc_lba_cell(const double *P, int na, const unsigned char *posdrift, const d
         if (0 > dt) { /* :217-219 */
             pdf = FLOOR_;
         } else if (A[0] < FLOOR_) { /* :221-227 */
-            pdf = fmax(b[0] / (dt * dt) * orc_dnorm4(b[0] / dt, mv[0], sv[0], 0) / denom[0], FLOOR_);
+            /* object code (de.o, lba_class::d +0xf6..+0x198): the normal density is divided by the drift denominator
+             * first (:224-225), THEN multiplied by b / (dt * dt) (:226) -- one rounding apart from the left-to-right product */
+            double term = orc_dnorm4(b[0] / dt, mv[0], sv[0], 0) / denom[0];
+            pdf = fmax(b[0] / (dt * dt) * term, FLOOR_);
         } else { /* :231-244 */
             double ts = sv[0] * dt, tv = mv[0] * dt;
             double t1 = mv[0] * (orc_pnorm5((b[0] - tv) / ts, 0.0, 1.0, 1, 0) - orc_pnorm5((b[0] - A[0] - tv) / ts, 0.0, 1.0, 1, 0));

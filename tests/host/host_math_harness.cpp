@@ -20,6 +20,60 @@ int hm_lba_cell(const double *P, int n_acc, const unsigned char *posdrift, const
     for (int i = 0; i < n; ++i) out[i] = gg::n1pdf_any<0>(cls, rt[i], e, n_acc);
     return cls;
 }
+// the same with the uniforms of `t0 + st0 U` (one per accumulator)
+int hm_lba_cell_u(const double *P, int n_acc, const unsigned char *posdrift, const double *u_st0, const double *rt, int n, double *out)
+{
+    gg::CellAcc e[16];
+    uint8_t cls = gg::kCellRegular;
+    for (int j = 0; j < n_acc; ++j) {
+        gg::cellacc_build(e[j], P[0 * n_acc + j], P[1 * n_acc + j], P[2 * n_acc + j], P[3 * n_acc + j], P[4 * n_acc + j],
+                          P[5 * n_acc + j], posdrift[j] != 0, u_st0[j]);
+        cls = gg::cell_class_update(cls, P[0 * n_acc + j], P[1 * n_acc + j], P[2 * n_acc + j], P[3 * n_acc + j], P[4 * n_acc + j],
+                                    P[5 * n_acc + j]);
+    }
+    for (int i = 0; i < n; ++i) out[i] = gg::n1pdf_any<0>(cls, rt[i], e, n_acc);
+    return cls;
+}
+// The trial functions of the sampler's hot loop on a regular 2-accumulator cell: consecutive trials in pairs through
+// n1pdf_fast2<2> (a last odd trial and trials with rt <= t0 through n1pdf_any, like the cold loop); how[i] = 2 for fast2.
+int hm_lba_cell_hot2(const double *P, const unsigned char *posdrift, const double *rt, int n, double *out, int *how)
+{
+    gg::CellAcc e[2];
+    uint8_t cls = gg::kCellRegular;
+    for (int j = 0; j < 2; ++j) {
+        gg::cellacc_build(e[j], P[0 * 2 + j], P[1 * 2 + j], P[2 * 2 + j], P[3 * 2 + j], P[4 * 2 + j], P[5 * 2 + j], posdrift[j] != 0, 0.0);
+        cls = gg::cell_class_update(cls, P[0 * 2 + j], P[1 * 2 + j], P[2 * 2 + j], P[3 * 2 + j], P[4 * 2 + j], P[5 * 2 + j]);
+    }
+    for (int i = 0; i < n; i += 2) {
+        const bool pair = i + 1 < n && cls == gg::kCellRegular && gg::n1pdf_fast_ok<2>(rt[i], e, 2) && gg::n1pdf_fast_ok<2>(rt[i + 1], e, 2);
+        if (pair) {
+            gg::n1pdf_fast2<2>(rt[i], e, rt[i + 1], e, 2, out[i], out[i + 1]);
+            how[i] = how[i + 1] = 2;
+        } else {
+            for (int h = 0; h < 2 && i + h < n; ++h) {
+                out[i + h] = gg::n1pdf_any<2>(cls, rt[i + h], e, 2);
+                how[i + h] = 1;
+            }
+        }
+    }
+    return cls;
+}
+// one-trial fast path of the 3- and 4-accumulator hot loops
+int hm_lba_cell_hot1(const double *P, int n_acc, const unsigned char *posdrift, const double *rt, int n, double *out)
+{
+    gg::CellAcc e[16];
+    uint8_t cls = gg::kCellRegular;
+    for (int j = 0; j < n_acc; ++j) {
+        gg::cellacc_build(e[j], P[0 * n_acc + j], P[1 * n_acc + j], P[2 * n_acc + j], P[3 * n_acc + j], P[4 * n_acc + j],
+                          P[5 * n_acc + j], posdrift[j] != 0, 0.0);
+        cls = gg::cell_class_update(cls, P[0 * n_acc + j], P[1 * n_acc + j], P[2 * n_acc + j], P[3 * n_acc + j], P[4 * n_acc + j],
+                                    P[5 * n_acc + j]);
+    }
+    for (int i = 0; i < n; ++i)
+        out[i] = (cls == gg::kCellRegular && gg::n1pdf_fast_ok<0>(rt[i], e, n_acc)) ? gg::n1pdf_fast<0>(rt[i], e, n_acc)
+                                                                                     : gg::n1pdf_any<0>(cls, rt[i], e, n_acc);
+    return cls;
+}
 double hm_pnorm_std(double z) { return gg::pnorm_std(z); }
 double hm_dnorm_std(double z) { return gg::dnorm_std(z); }
 double hm_pnorm5(double x, double mu, double s, int lower) { return gg::pnorm5(x, mu, s, lower != 0); }
