@@ -234,9 +234,10 @@ P2P g_p2p;
 // uploads
 // ---------------------------------------------------------------------------------------------
 struct ModelDev {
-    DBuf<int> param_src;
+    DBuf<int> param_src, row_src;
     DBuf<double> const_val;
     DBuf<uint8_t> posdrift;
+    DBuf<uint16_t> row_of;
     DevModel d{};
     int type = GGDMC_MODEL_LBA; // enum ggdmc_model_type: which likelihood kernels the host launches
     void upload(const ggdmc_model_t *m)
@@ -258,6 +259,49 @@ struct ModelDev {
         d.n_acc = m->n_acc; d.n_cell = m->n_cell; d.npar = m->npar; d.n_const = m->n_const;
         d.param_src = param_src.p; d.const_val = const_val.p; d.posdrift = posdrift.p;
         type = m->type;
+        if (!ddm) build_rows_table(m);
+    }
+    // The distinct (cell, accumulator) rows of an LBA model: entries with the same six parameter sources and the same
+    // drift rule share one row of the likelihood kernels' table.  If st0 can be non-zero every entry draws its own
+    // uniform (`t0 + st0 U`, @hdr/lba.h:117) and keeps its own row.
+    void build_rows_table(const ggdmc_model_t *m)
+    {
+        const int na = m->n_acc, n_ent = m->n_cell * na;
+        bool st0_zero = true;
+        for (int c = 0; c < m->n_cell && st0_zero; ++c)
+            for (int j = 0; j < na; ++j) {
+                const int s = m->param_src[((size_t)c * GGDMC_LBA_ROWS + 4) * na + j];
+                if (s >= 0 || m->const_val[-1 - s] != 0.0) { st0_zero = false; break; }
+            }
+        std::vector<uint16_t> h_row_of((size_t)n_ent);
+        std::vector<int> h_row_src;
+        for (int c = 0; c < m->n_cell; ++c)
+            for (int j = 0; j < na; ++j) {
+                int key[8];
+                for (int r = 0; r < 6; ++r) key[r] = m->param_src[((size_t)c * GGDMC_LBA_ROWS + r) * na + j];
+                key[6] = c * na + j;
+                key[7] = m->posdrift[j] != 0;
+                int found = -1;
+                const int n_row = (int)h_row_src.size() / 8;
+                if (st0_zero)
+                    for (int q = 0; q < n_row && found < 0; ++q) {
+                        const int *o = &h_row_src[(size_t)q * 8];
+                        bool same = o[7] == key[7];
+                        for (int r = 0; r < 6 && same; ++r) same = o[r] == key[r];
+                        if (same) found = q;
+                    }
+                if (found < 0) {
+                    found = n_row;
+                    h_row_src.insert(h_row_src.end(), key, key + 8);
+                }
+                h_row_of[(size_t)c * na + j] = (uint16_t)found;
+            }
+        require(h_row_src.size() / 8 <= 65535, "too many table rows");
+        row_of.upload(h_row_of);
+        row_src.upload(h_row_src);
+        d.n_row = (int)h_row_src.size() / 8;
+        d.row_of = row_of.p;
+        d.row_src = row_src.p;
     }
 };
 
@@ -478,11 +522,7 @@ int like_variant()
     return v;
 }
 
-size_t like_smem(const DevModel &M, int block)
-{
-    size_t b = (size_t)M.n_cell * M.n_acc * sizeof(CellAcc) + (size_t)(block / 32) * 8 + (size_t)M.n_cell * (1 + M.n_acc);
-    return (b + 15) & ~(size_t)15;
-}
+size_t like_smem(const DevModel &M, int block) { return like_smem_bytes(M.n_row, M.n_cell, block); }
 
 template <int NACC, int BLOCK, int MINB>
 void launch_like_t(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
@@ -688,7 +728,7 @@ struct ggdmc_engine {
     DBuf<uint64_t> seeds;
     DBuf<uint32_t> d_iter;
     DBuf<unsigned int> done_ctr, phi_ticket;
-    DBuf<double> ll_part, hpart, hsum, hyper_data, phi_consts;
+    DBuf<double> ll_part, hpart, hsum, hyper_data, phi_consts, prop_consts;
     HyperArgs H{};
 
     ~ggdmc_engine()
@@ -796,7 +836,8 @@ struct ggdmc_engine {
         pt.lap("  trials");
         S = t->n_subject;
         const bool want_persist = persist_planned = sampler_wanted() && m->type == GGDMC_MODEL_LBA && schedule == GGDMC_SCHEDULE_PARALLEL && !is_hblocked &&
-                                  !is_pblocked && (!(hp && g_nccl.comm && g_nccl.n_rank > 1) || (g_p2p.ready && R * C * 2 <= kP2PMaxN));
+                                  !is_pblocked && (!(hp && g_nccl.comm && g_nccl.n_rank > 1) || (g_p2p.ready && R * C * 2 <= kP2PMaxN)) &&
+                                  sampler_fits(m->npar, hp != nullptr);
         if (want_persist) sampler_chunking((int64_t)R * S * ((C + 1) / 2));
         else trials.set_chunking((int64_t)R * S * C);
         subj.create(R * S, R, C, D, nmc, thin);
@@ -826,6 +867,12 @@ struct ggdmc_engine {
             phi_consts.alloc((size_t)R * C * D * 2);
             L.ovr_consts = phi_consts.p;
             setup_hyper(subj.theta.p, C * D, R * C * D, D, 1);
+            if (want_persist) { // the persistent kernel keeps the prior constants up to date by itself (phi_accept_one)
+                prop_consts.alloc((size_t)R * C * D * 2);
+                prop_consts.zero();
+                H.prop_consts = prop_consts.p;
+                H.consts = phi_consts.p;
+            }
         }
         make_groups();
         start_counter();
@@ -902,12 +949,16 @@ struct ggdmc_engine {
         H.S = S; H.D = D; H.need_cur = need_cur;
         // split subjects over blocks so that the phi kernels fill the GPU (R*C blocks alone would not) in ONE wave
         int per_sm = 4, n_sm = 148;
-        const size_t sm_bytes = (size_t)(6 * D + 2 * (kHyperBlock / 32) + 4 * D) * 8;
+        const size_t sm_bytes = (size_t)(8 * D + 2 * (kHyperBlock / 32) + 4 * D) * 8;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_phi_half<kHyperBlock>, kHyperBlock, sm_bytes);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
         int want = std::max(1, (std::max(per_sm, 1) * n_sm) / (R * C));
         int spb = std::max(64, (S + want - 1) / want); // >= 3 terms per thread: the per-block setup (proposal, 4 Phi + 2 log per parameter) is not free
-        if (persist_planned) spb = 64; // 64-thread CTAs of the sampler kernel: D terms per thread, the phi half-sweep is on its critical path
+        if (persist_planned) { // one WARP per item in the sampler kernel and the phi half-sweep on the critical path of a small fit:
+            // short items (8 subjects = 3 terms per lane) while they are few, at most about half a wave of them otherwise
+            const int per_wave = n_sm * 12;
+            spb = std::max(8, (S * R * C + per_wave - 1) / per_wave);
+        }
         H.subj_per_block = spb;
         H.nsplit = (S + spb - 1) / spb;
         hpart.alloc((size_t)R * C * 2 * H.nsplit);
@@ -1029,7 +1080,7 @@ struct ggdmc_engine {
     void hyper_eval(int step, cudaStream_t st)
     {
         Level &P = phi.L;
-        const size_t sm = (size_t)(6 * D + 2 * (kHyperBlock / 32)) * 8;
+        const size_t sm = (size_t)(8 * D + 2 * (kHyperBlock / 32)) * 8;
         dim3 grid(step < 0 ? R * C : R, H.nsplit, step < 0 ? 1 : 2);
         TR("k_hyper", st, k_hyper<kHyperBlock><<<grid, kHyperBlock, sm, st>>>(P, H, step, hpart.p));
         const int n = R * C * 2;
@@ -1059,7 +1110,7 @@ struct ggdmc_engine {
         if (schedule != GGDMC_SCHEDULE_REFERENCE && fuse_phi && (!multi || p2p)) {
             // one launch per half-sweep: proposal + hyper-likelihood + reduction (+ peer exchange) + MH test
             const int nhalf = schedule == GGDMC_SCHEDULE_PARALLEL ? 2 : 1;
-            const size_t sm = (size_t)(6 * D + 2 * (kHyperBlock / 32) + 2 * D2) * 8;
+            const size_t sm = (size_t)(8 * D + 2 * (kHyperBlock / 32) + 2 * D2) * 8;
             for (int h = 0; h < nhalf; ++h) {
                 dim3 grid(R * C, H.nsplit);
                 TR("k_phi_half", st, k_phi_half<kHyperBlock><<<grid, kHyperBlock, sm, st>>>(P, H, d_iter.p, sweep, nhalf == 2 ? h : -1, hpart.p,
@@ -1119,41 +1170,51 @@ struct ggdmc_engine {
     // GGDMC_B200_NO_PERSIST=1 keeps the multi-launch path (also used by the other schedules, per-parameter sweeps and the DDM).
     bool persist = false, persist_planned = false;
     SamplerArgs SA{};
-    int sampler_grid = 0, sampler_nacc = 0, sampler_max_batch = 64;
+    int sampler_grid = 0, sampler_threads = 0, sampler_nacc = 0, sampler_max_batch = 64;
     size_t sampler_smem = 0;
-    DBuf<unsigned long long> sy_queue, sy_all_done;
-    DBuf<unsigned int> sy_exit, sy_pop_arrive, sy_pop_done, sy_phi_arrive, sy_phi_done;
+    DBuf<unsigned long long> sy_queue, sy_all_done, sy_trace;
+    DBuf<unsigned int> sy_exit, sy_pop_flags, sy_chain_arrive, sy_phi_arrive, sy_phi_done;
     DBuf<int> sy_abort;
 
     template <int NACC>
-    void sampler_prepare()
+    int sampler_blocks_per_sm()
     {
-        auto kern = k_sampler<NACC, 64, 12>;
+        auto kern = k_sampler<NACC>;
         allow_smem(kern, sampler_smem);
-        int per_sm = 0, n_sm = 148;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64, sampler_smem));
-        CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
-        require(per_sm >= 1, "sampler kernel does not fit on an SM (cell table too large)");
-        sampler_grid = per_sm * n_sm;
+        int per_sm = 0;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sampler_threads, sampler_smem));
+        return per_sm;
     }
     template <int NACC>
     void sampler_launch()
     {
-        CUDA_CHECK(cudaLaunchKernelEx(&sampler_cfg, k_sampler<NACC, 64, 12>, SA));
+        CUDA_CHECK(cudaLaunchKernelEx(&sampler_cfg, k_sampler<NACC>, SA));
     }
     cudaLaunchConfig_t sampler_cfg{};
 
     static bool sampler_wanted() { return std::getenv("GGDMC_B200_NO_PERSIST") == nullptr; }
-
-    // trial chunks per proposal for the persistent kernel: one wave of items per half-sweep at most (a finer split only
-    // multiplies the per-item table build), as many as fit below that when the problem is small
-    void sampler_chunking(int64_t proposals_per_half)
+    int sm_count() const
     {
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-        const int64_t cap = (int64_t)n_sm * 12;
+        return n_sm;
+    }
+    size_t sampler_cta_bytes(int D_, bool hier, int warps) const
+    {
+        return sampler_stage_bytes(model.d.n_cell, model.d.n_acc, model.d.n_row, model.d.n_const) +
+               (size_t)warps * sampler_warp_bytes(model.d.n_cell, model.d.n_row, D_, C, hier ? 1 : 0);
+    }
+    // The kernel wants its 24 warps per SM; a model whose row table leaves room for fewer than 16 stays on the multi-launch path.
+    bool sampler_fits(int D_, bool hier) const { return 2 * sampler_cta_bytes(D_, hier, 8) <= 220 * 1024; }
+
+    // Trial chunks per proposal: a warp per (proposal, chunk).  Large fits: one chunk (the table build is paid once per
+    // proposal).  Small fits: as many chunks as it takes to give every resident warp of the GPU an item in each half-sweep,
+    // down to 64 trials (one pass of a warp) per chunk.
+    void sampler_chunking(int64_t proposals_per_half)
+    {
+        const int64_t cap = (int64_t)sm_count() * 24;
         int nsplit = (int)std::max<int64_t>(1, cap / std::max<int64_t>(1, proposals_per_half));
-        nsplit = std::min(nsplit, std::max(1, trials.max_count / 128));
+        nsplit = std::min(nsplit, std::max(1, trials.max_count / 64));
         if (const char *e = std::getenv("GGDMC_B200_NSPLIT")) nsplit = std::max(1, std::min(std::atoi(e), std::max(1, trials.max_count / 8)));
         if (trials.max_count > 8192) nsplit = std::max(nsplit, (trials.max_count + 4095) / 4096);
         const int chunk = ((std::max(1, (trials.max_count + nsplit - 1) / nsplit)) + 7) & ~7;
@@ -1169,12 +1230,13 @@ struct ggdmc_engine {
         sy_queue.alloc(1); sy_queue.zero();
         sy_all_done.alloc(1); sy_all_done.zero();
         sy_exit.alloc(1); sy_exit.zero();
-        sy_pop_arrive.alloc(npop); sy_pop_arrive.zero();
+        sy_chain_arrive.alloc((size_t)npop * C); sy_chain_arrive.zero();
         sy_phi_arrive.alloc(1); sy_phi_arrive.zero();
         sy_abort.alloc(1); sy_abort.zero();
-        std::vector<unsigned int> two((size_t)npop, 2u); // "half 1 of iteration 0 is accepted"
-        sy_pop_done.upload(two);
-        sy_phi_done.upload(two.data(), 1);
+        std::vector<unsigned int> flags((size_t)npop * kPopFlagStride, 0u);
+        for (int p = 0; p < npop; ++p) flags[(size_t)p * kPopFlagStride] = 2u; // "half 1 of iteration 0 is closed"
+        sy_pop_flags.upload(flags);
+        sy_phi_done.upload(flags.data(), 1);
         CUDA_CHECK(cudaStreamSynchronize(0));
         SA.S = subj.L;
         if (kind == 2) SA.P = phi.L;
@@ -1182,33 +1244,92 @@ struct ggdmc_engine {
         SA.T = trials.d;
         SA.H = H;
         SA.w = g_p2p.win;
-        SA.y.queue = sy_queue.p; SA.y.exit_ctr = sy_exit.p; SA.y.pop_arrive = sy_pop_arrive.p; SA.y.pop_done = sy_pop_done.p;
+        SA.y.queue = sy_queue.p; SA.y.exit_ctr = sy_exit.p; SA.y.pop_flags = sy_pop_flags.p; SA.y.chain_arrive = sy_chain_arrive.p;
         SA.y.all_done = sy_all_done.p; SA.y.phi_arrive = sy_phi_arrive.p; SA.y.phi_done = sy_phi_done.p; SA.y.abort = sy_abort.p;
         double sec = 20.0; // a local wait is bounded by the longest item chain of an iteration; peers are waited for inside the exchange
         if (const char *e = std::getenv("GGDMC_B200_SPIN_TIMEOUT_S")) sec = std::max(0.001, std::atof(e));
         SA.y.spin_ns = (unsigned long long)(sec * 1e9) + (multi ? g_p2p.win.spin_ns : 0ull);
-        SA.ll_part = ll_part.p; SA.hpart = hpart.p; SA.hsum = hsum.p; SA.phi_consts = phi_consts.p;
+        SA.ll_part = ll_part.p; SA.hpart = hpart.p; SA.hsum = hsum.p;
         SA.d_iter = d_iter.p;
         SA.hier = kind == 2; SA.use_p2p = p2p ? 1 : 0; SA.decide_once = kind == 0;
-        sampler_smem = sampler_smem_bytes(model.d.n_cell, model.d.n_acc, D, C, 64, SA.hier);
-        require(sampler_smem <= 220 * 1024, "cell table does not fit in shared memory");
+        // items of one iteration, and the launch shape: every warp is a worker; CTAs of 8 warps share one copy of the model's
+        // tables, small fits use smaller CTAs so that their few workers spread over all SMs
+        const unsigned long long n_sub = (unsigned long long)npop * ((C + 1) / 2) * trials.d.nsplit;
+        const unsigned long long n_phi = SA.hier ? (unsigned long long)R * C * H.nsplit : 0ull;
+        const unsigned long long n_accept = SA.hier ? (unsigned long long)npop * ((C + 31) / 32) : 0ull;
+        const unsigned long long per_iter = 2 * n_sub + 2 * n_phi + n_accept;
+        const int n_sm = sm_count();
+        int warps = 8;
+        while (warps > 1 && per_iter < (unsigned long long)n_sm * 24 && per_iter < (unsigned long long)n_sm * warps * 3) warps >>= 1;
+        if (const char *e = std::getenv("GGDMC_B200_SAMPLER_WARPS")) warps = std::max(1, std::min(8, std::atoi(e)));
+        sampler_threads = warps * 32;
+        SA.stage_bytes = (int)sampler_stage_bytes(model.d.n_cell, model.d.n_acc, model.d.n_row, model.d.n_const);
+        SA.warp_bytes = (int)sampler_warp_bytes(model.d.n_cell, model.d.n_row, D, C, SA.hier);
+        sampler_smem = (size_t)SA.stage_bytes + (size_t)warps * SA.warp_bytes;
+        require(sampler_smem <= 220 * 1024, "row table does not fit in shared memory");
         sampler_nacc = model.d.n_acc;
+        int per_sm = 0;
         switch (sampler_nacc) {
-        case 2: sampler_prepare<2>(); break;
-        case 3: sampler_prepare<3>(); break;
-        case 4: sampler_prepare<4>(); break;
-        default: sampler_prepare<0>();
+        case 2: per_sm = sampler_blocks_per_sm<2>(); break;
+        case 3: per_sm = sampler_blocks_per_sm<3>(); break;
+        case 4: per_sm = sampler_blocks_per_sm<4>(); break;
+        default: per_sm = sampler_blocks_per_sm<0>();
         }
-        const unsigned long long per_iter = 2ull * (SA.hier ? (unsigned long long)R * C * H.nsplit : 0ull) +
-                                            2ull * (unsigned long long)npop * ((C + 1) / 2) * trials.d.nsplit;
-        sampler_grid = (int)std::min<unsigned long long>((unsigned long long)sampler_grid, per_iter);
+        require(per_sm >= 1, "sampler kernel does not fit on an SM (row table too large)");
+        per_sm = std::min(per_sm, 24 / warps);
+        sampler_grid = (int)std::min<unsigned long long>((unsigned long long)per_sm * n_sm, (per_iter + warps - 1) / warps);
+        sampler_segments(n_sub, n_phi, n_accept, (unsigned long long)sampler_grid * warps);
         if (const char *e = std::getenv("GGDMC_B200_BATCH")) sampler_max_batch = std::max(1, std::atoi(e));
-        // the migration decisions of iteration 1 (later ones are drawn inside the kernel at the end of the previous iteration)
+        if (const char *e = std::getenv("GGDMC_B200_ITEMTRACE")) { // diagnostics: stamps of the first items of every launch
+            (void)e;
+            unsigned long long cap = 400000;
+            if (const char *c = std::getenv("GGDMC_B200_ITEMTRACE_CAP")) cap = std::strtoull(c, nullptr, 10);
+            sy_trace.alloc((size_t)cap * 8);
+            sy_trace.zero();
+            CUDA_CHECK(cudaStreamSynchronize(0));
+            SA.trace = sy_trace.p;
+            SA.trace_cap = cap;
+        }
+        // the migration decisions of iteration 1 (later ones are drawn inside the kernel at the end of the previous iteration),
+        // and the constants of the subject prior under the start state of phi (later ones travel with accepted proposals)
         k_sweep_begin<<<npop, 128, (size_t)2 * C * sizeof(int), stream>>>(subj.L, d_iter.p, 0, SA.decide_once, -1);
-        if (kind == 2) k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), stream>>>(phi.L, d_iter.p, 0, 0, -1);
+        if (kind == 2) {
+            k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), stream>>>(phi.L, d_iter.p, 0, 0, -1);
+            phi_constants(stream);
+        }
         CUDA_CHECK(cudaGetLastError());
         launches += kind == 2 ? 2 : 1;
         persist = true;
+    }
+
+    // Queue order of one iteration (gg_sampler.cuh).  A fit with many waves of subject items per half-sweep gets its phi
+    // items early: after two waves of half 0 the previous iteration is certainly finished, one wave later so is phi's half
+    // 0, and so on -- nobody ever waits, and the rest of half 0 finds phi ready and takes its MH decisions on the spot.
+    void sampler_segments(unsigned long long n_sub, unsigned long long n_phi, unsigned long long n_accept, unsigned long long workers)
+    {
+        int n = 0;
+        auto seg = [&](int kind, int half, unsigned long long first, unsigned long long count) {
+            if (count == 0) return;
+            SA.seg_kind[n] = kind; SA.seg_half[n] = half; SA.seg_first[n] = first; SA.seg_count[n] = count;
+            ++n;
+        };
+        const bool early_phi = n_phi > 0 && n_sub >= 5 * workers && std::getenv("GGDMC_B200_NO_EARLY_PHI") == nullptr;
+        if (early_phi) {
+            const unsigned long long a = 2 * workers, b = workers;
+            seg(kItemSubject, 0, 0, a);
+            seg(kItemPhi, 0, 0, n_phi);
+            seg(kItemSubject, 0, a, b);
+            seg(kItemPhi, 1, 0, n_phi);
+            seg(kItemSubject, 0, a + b, n_sub - a - b);
+        } else {
+            seg(kItemSubject, 0, 0, n_sub);
+            seg(kItemPhi, 0, 0, n_phi);
+            seg(kItemPhi, 1, 0, n_phi);
+        }
+        seg(kItemAccept, 0, 0, n_accept);
+        seg(kItemSubject, 1, 0, n_sub);
+        SA.n_seg = n;
+        SA.per_iter = 2 * n_sub + 2 * n_phi + n_accept;
     }
 
     // iterations [h_iter + 1, h_iter + n] in one launch
@@ -1217,7 +1338,7 @@ struct ggdmc_engine {
         SA.t_begin = h_iter + 1;
         SA.t_end = h_iter + 1 + (uint32_t)n;
         sampler_cfg = cudaLaunchConfig_t{};
-        sampler_cfg.gridDim = dim3(sampler_grid); sampler_cfg.blockDim = dim3(64); sampler_cfg.dynamicSmemBytes = sampler_smem;
+        sampler_cfg.gridDim = dim3(sampler_grid); sampler_cfg.blockDim = dim3(sampler_threads); sampler_cfg.dynamicSmemBytes = sampler_smem;
         sampler_cfg.stream = stream;
         cudaEvent_t ea = nullptr, eb = nullptr;
         if (profile) {
@@ -1250,6 +1371,22 @@ struct ggdmc_engine {
         CUDA_CHECK(cudaMemcpy(&v, sy_abort.p, sizeof(int), cudaMemcpyDeviceToHost));
         if (v == 1) throw Error(GGDMC_ERR_COMM, "peer exchange timed out: a rank did not arrive");
         if (v != 0) throw Error(GGDMC_ERR_CUDA, "sampler kernel: a dependency wait timed out");
+        if (SA.trace) dump_item_trace();
+    }
+    // GGDMC_B200_ITEMTRACE=<file>: the stamps of the LAST launch (tools/exp_itemtrace.py reads them)
+    void dump_item_trace()
+    {
+        const char *path = std::getenv("GGDMC_B200_ITEMTRACE");
+        if (!path || !*path) return;
+        std::vector<unsigned long long> h((size_t)SA.trace_cap * 8);
+        CUDA_CHECK(cudaMemcpy(h.data(), sy_trace.p, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE *f = std::fopen(path, "wb")) {
+            const unsigned long long hdr[8] = {SA.trace_cap, (unsigned long long)R * S, (unsigned long long)((C + 1) / 2), (unsigned long long)trials.d.nsplit,
+                                               SA.hier ? (unsigned long long)R * C * H.nsplit : 0ull, (unsigned long long)sampler_grid, (unsigned long long)sampler_threads, SA.per_iter};
+            std::fwrite(hdr, 8, 8, f);
+            std::fwrite(h.data(), 8, h.size(), f);
+            std::fclose(f);
+        }
     }
 
     // all ranks of a sharded fit arrive before anybody iterates (the exchange assumes lock step within its timeout)
@@ -1680,8 +1817,7 @@ int ggdmc_b200_trial_logdens(const ggdmc_model_t *model, const ggdmc_trials_t *t
     d_theta.upload(theta, (size_t)n_theta * model->npar);
     d_out.alloc((size_t)n_theta * std::max(ntr, 1));
     const bool ddm = M.type == GGDMC_MODEL_DDM;
-    const size_t sm = ddm ? (size_t)M.d.n_cell * sizeof(DdmCell)
-                          : ((size_t)M.d.n_cell * M.d.n_acc * sizeof(CellAcc) + (size_t)M.d.n_cell * (1 + M.d.n_acc) + 15) & ~(size_t)15;
+    const size_t sm = ddm ? (size_t)M.d.n_cell * sizeof(DdmCell) : like_smem(M.d, 128);
     require(sm <= 220 * 1024, "cell table does not fit in shared memory");
     if (ddm) allow_smem(k_trial_logdens_ddm<128>, sm);
     else allow_smem(k_trial_logdens<128>, sm);

@@ -36,6 +36,26 @@ struct DevModel {
     const int *param_src;
     const double *const_val;
     const uint8_t *posdrift; // LBA: [n_acc].  DDM: [n_cell], non-zero = upper-boundary response (the host picks the kernels by model type)
+    // LBA: the DISTINCT (cell, accumulator) rows of the model.  Entries that draw the same six parameters with the same
+    // drift rule get one table row (B x v README model: 24 rows for 48 entries; 4-accumulator factorial model: 48 for 384).
+    // A model whose st0 can be non-zero keeps one row per entry, because every entry then has its own `t0 + st0 U` draw.
+    int n_row;
+    const uint16_t *row_of;  // [n_cell][n_acc] row of entry (cell, accumulator)
+    const int *row_src;      // [n_row][8]: sources of A, B, mean_v, sd_v, st0, t0 (>= 0 parameter, < 0 constant -1 - s), entry index
+                             // of the row's first entry (addresses its st0 draw), positive-drift flag
+};
+
+// A "group" is the set of threads that works on one item together: a whole thread block (G = block size, or 0 = whatever
+// the launch says) or ONE WARP of a larger block (G = 32: the persistent sampler kernel, whose warps are independent workers).
+template <int G>
+struct Grp {
+    __device__ __forceinline__ static int tid() { return G == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+    __device__ __forceinline__ static int size() { return G > 0 ? G : (int)blockDim.x; }
+    __device__ __forceinline__ static void sync()
+    {
+        if constexpr (G == 32) __syncwarp();
+        else __syncthreads();
+    }
 };
 
 struct DevPrior {
@@ -115,6 +135,7 @@ __device__ __forceinline__ double block_sum(double v, double *scratch /* [BLOCK/
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if constexpr (BLOCK == 32) return v; // one warp: valid in lane 0, no shared memory, no barrier
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) scratch[w] = v;
     __syncthreads();
@@ -135,10 +156,11 @@ __device__ __forceinline__ double block_sum(double v, double *scratch /* [BLOCK/
 //                  migration is a single unblocked sweep, so migrating populations idle (mode 2)
 //                  in the remaining blocked sweeps.
 // block-wide; sm_keys: 2 * nchain ints of shared memory.  The caller provides a barrier before sm_keys is reused.
+template <int G = 0>
 __device__ __forceinline__ void sweep_begin_pop(const Level &L, int p, uint32_t iter, int sweep, int decide_once, int para_idx, int *sm_keys,
                                                 int *s_mode_n /* 2 ints of shared memory */)
 {
-    const int C = L.nchain, tid = threadIdx.x, nthr = blockDim.x;
+    const int C = L.nchain, tid = Grp<G>::tid(), nthr = Grp<G>::size();
     DrawAddr a = make_addr(L, p, iter, decide_once ? 0 : sweep, 0);
     if (tid == 0) {
         int mode;
@@ -164,7 +186,7 @@ __device__ __forceinline__ void sweep_begin_pop(const Level &L, int p, uint32_t 
         }
     }
     for (int c = tid; c < C; c += nthr) L.target[p * C + c] = -1;
-    __syncthreads();
+    Grp<G>::sync();
     if (s_mode_n[0] != 1) return;
     // arma::shuffle keys for all chains, then the n smallest keys (ties by position), sorted by index
     for (int blk = tid; blk * 4 < C; blk += nthr) {
@@ -175,7 +197,7 @@ __device__ __forceinline__ void sweep_begin_pop(const Level &L, int p, uint32_t 
         if (j + 2 < C) sm_keys[j + 2] = shuffle_key(word_to_uniform(w.z));
         if (j + 3 < C) sm_keys[j + 3] = shuffle_key(word_to_uniform(w.w));
     }
-    __syncthreads();
+    Grp<G>::sync();
     const int n = s_mode_n[1];
     int *sm_rank = sm_keys + C;
     for (int j = tid; j < C; j += nthr) {
@@ -187,7 +209,7 @@ __device__ __forceinline__ void sweep_begin_pop(const Level &L, int p, uint32_t 
         }
         sm_rank[j] = rank;
     }
-    __syncthreads();
+    Grp<G>::sync();
     for (int j = tid; j < C; j += nthr) {
         if (sm_rank[j] < n) { // selected: position among the selected chains in ascending index order
             int pos = 0;
@@ -310,6 +332,19 @@ __device__ __forceinline__ double deferred_prop_lp(const Level &L, int p, int sr
     const double *pr = L.prop + ((size_t)p * C + src) * D;
     double a1 = 0.0, a2 = 0.0; // arma::accu order, as sum_arma_order
     int d = 0;
+    if (oc) { // the usual case -- every term a phi-driven truncated normal: a pass without calls, whose loads can travel together
+        bool all_fast = true;
+#pragma unroll 4
+        for (int e = 0; e < D; ++e) {
+            const double x = ldm(pr + e), K = ldm(oc + 2 * e + 1), m = ldm(ovr + e), iv = ldm(oc + 2 * e);
+            const double z = (x - m) * iv;
+            const double term = (x < L.prior.lower[e] || x > L.prior.upper[e]) ? -INFINITY : -(0.5 * z * z + K);
+            all_fast = all_fast && (K == K);
+            if (e & 1) a2 += term; else a1 += term;
+        }
+        if (all_fast) return a1 + a2;
+        a1 = a2 = 0.0;
+    }
     for (; d + 1 < D; d += 2) {
         a1 += prior_term(L, d, ldm(pr + d), ovr, oc);
         a2 += prior_term(L, d + 1, ldm(pr + d + 1), ovr, oc);
@@ -498,66 +533,103 @@ struct LogProd {
     __device__ __forceinline__ double value() const { return fma((double)e, kLn2Hi, fma((double)e, kLn2Lo, log(m))) + extra; }
 };
 
-// Builds the (cell, accumulator) table of one parameter vector in shared memory: thread k fills
-// entry (cell, column) = (k / n_acc, k % n_acc); the thread of column 0 also decides the cell's
-// validity (@hdr/lba.h:121-146: invalid when ANY accumulator has A, b, sd_v, st0 or t0 < 0 or
-// b < A).  One barrier at the end.
-template <int BLOCK>
-__device__ __forceinline__ void build_cell_table(const DevModel &M, const double *__restrict__ theta, CellAcc *ent,
-                                                 uint8_t *cell_bad, const DrawAddr &addr)
+// Shared memory of one likelihood evaluation by a group of `group` threads (bytes): the row table, the reduction scratch
+// of block_sum, the class of every cell and of every row.
+__host__ __device__ inline size_t like_smem_bytes(int n_row, int n_cell, int group)
 {
-    const int n = M.n_cell * M.n_acc, na = M.n_acc;
-    uint8_t *row_cls = cell_bad + M.n_cell; // [n_cell * n_acc] class of every row on its own
-    for (int k = threadIdx.x; k < n; k += BLOCK) {
-        const int c = k / na, j = k - c * na;
-        const int *src = M.param_src + (size_t)c * 6 * na;
+    size_t b = (size_t)n_row * sizeof(CellAcc) + (size_t)(group / 32) * 8 + (size_t)n_cell + (size_t)n_row;
+    return (b + 15) & ~(size_t)15;
+}
+
+// Builds the row table of one parameter vector in shared memory: thread k fills row k -- b = A + B, t0 + st0 U,
+// max(Phi(mean_v / sd_v), 1e-10) and the reciprocals the trial loop multiplies by -- and classifies it
+// (@hdr/lba.h:121-146: a cell is invalid when ANY accumulator has A, b, sd_v, st0 or t0 < 0 or b < A); then one thread per
+// cell combines the classes of the cell's rows.  Two group barriers.
+template <int G>
+__device__ __forceinline__ void build_rows(const DevModel &M, const double *theta, CellAcc *rows, uint8_t *cell_bad, uint8_t *row_cls,
+                                           const DrawAddr &addr)
+{
+    const int na = M.n_acc, tid = Grp<G>::tid();
+    for (int r = tid; r < M.n_row; r += Grp<G>::size()) {
+        const int *src = M.row_src + 8 * r;
         double v[6];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const int s = src[r * na + j];
-            v[r] = s >= 0 ? theta[s] : M.const_val[-1 - s];
+        for (int i = 0; i < 6; ++i) {
+            const int s = src[i];
+            v[i] = s >= 0 ? theta[s] : M.const_val[-1 - s];
         }
         double u = 0.0;
-        if (v[4] != 0.0) u = draw_uniform(addr, U_ST0, (uint32_t)k);
-        cellacc_build(ent[k], v[0], v[1], v[2], v[3], v[4], v[5], M.posdrift[j] != 0, u);
-        row_cls[k] = cell_class_update(kCellRegular, v[0], v[1], v[2], v[3], v[4], v[5]);
+        if (v[4] != 0.0) u = draw_uniform(addr, U_ST0, (uint32_t)src[6]);
+        cellacc_build(rows[r], v[0], v[1], v[2], v[3], v[4], v[5], src[7] != 0, u);
+        row_cls[r] = cell_class_update(kCellRegular, v[0], v[1], v[2], v[3], v[4], v[5]);
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < M.n_cell; c += BLOCK) { // a cell is invalid if any row is, else generic if any row is
+    Grp<G>::sync();
+    for (int c = tid; c < M.n_cell; c += Grp<G>::size()) { // a cell is invalid if any row is, else generic if any row is
         uint8_t cls = kCellRegular;
         for (int j = 0; j < na; ++j) {
-            const uint8_t r = row_cls[c * na + j];
+            const uint8_t r = row_cls[M.row_of[c * na + j]];
             cls = (r == kCellInvalid || cls == kCellInvalid) ? (uint8_t)kCellInvalid : (r != kCellRegular ? r : cls);
         }
         cell_bad[c] = cls;
     }
-    __syncthreads();
+    Grp<G>::sync();
+}
+
+// The trials the hot loops of like_eval leave behind -- invalid / generic cells, rt <= t0, a last odd trial -- with the
+// reference's full branch structure.  Not inlined: rare, and long enough to matter for the instruction cache of the
+// persistent kernel.  PAIRS: the hot loop worked on pairs of trials (a pair is left behind as a whole).
+template <int NACC, int G, bool PAIRS, bool TRACE>
+__device__ __noinline__ void like_cold(const CellAcc *rows, const uint16_t *row_of, const uint8_t *bad, int na, const double *rt,
+                                       const uint16_t *cl, int t_begin, int t_end, double zf, LogProd &acc, double *trace_out)
+{
+    const int tid = Grp<G>::tid();
+    for (int t = t_begin + 2 * tid; t < t_end; t += 2 * G) {
+        const int nh = (t + 1 < t_end) ? 2 : 1;
+        if (PAIRS && nh == 2) {
+            const int c0 = cl[t], c1 = cl[t + 1];
+            if (bad[c0] == kCellRegular && bad[c1] == kCellRegular && n1pdf_fast_ok<NACC>(rt[t], RowRef{rows, row_of + c0 * na}, na) &&
+                n1pdf_fast_ok<NACC>(rt[t + 1], RowRef{rows, row_of + c1 * na}, na))
+                continue; // done in the hot loop
+        }
+        for (int h = 0; h < nh; ++h) {
+            const int c = cl[t + h];
+            const double r = rt[t + h];
+            const RowRef e{rows, row_of + c * na};
+            const uint8_t cls = bad[c];
+            if (!PAIRS && cls == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) continue; // done in the hot loop
+            double pdf = cls == kCellInvalid ? kFloor : ((cls == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) ? n1pdf_fast<NACC>(r, e, na) : n1pdf_generic_body<NACC>(r, e, na));
+            if (zf > 0.0 && pdf <= 0.0) pdf = zf;
+            acc.mul(pdf);
+            if constexpr (TRACE) trace_out[t + h] = log(pdf);
+        }
+    }
 }
 
 // sum-log-likelihood of ONE parameter vector `th` (global or shared memory) for local subject s over trial chunk `split`, by
-// the whole block; addr addresses the draws of `t0 + st0 U`.  The sum is returned in thread 0 (0 for an empty chunk).
-// sm_raw: like_smem() bytes of shared memory; the caller provides a barrier before it is reused.
+// one group (a block, or with G = 32 one warp); addr addresses the draws of `t0 + st0 U`.  The sum is returned in thread 0
+// of the group (0 for an empty chunk).  sm_raw: like_smem_bytes() of shared memory; the caller provides a barrier before
+// it is reused.  stamp (diagnostics, may be null): thread 0 writes the time the table was finished to stamp[0].
 // TRACE (parity entry point ggdmc_b200_trial_logdens_hot only): every density the loops fold into the running product is
 // also written, as its log, to trace_out[trial] -- the production loops, the production trial functions.
-template <int NACC, int BLOCK, bool TRACE = false>
+template <int NACC, int G, bool TRACE = false>
 __device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &T, const double *th, const DrawAddr &addr, int s, int split,
-                                            unsigned char *sm_raw, double *trace_out = nullptr)
+                                            unsigned char *sm_raw, double *trace_out = nullptr, unsigned long long *stamp = nullptr)
 {
-    const int na = M.n_acc;
+    const int na = M.n_acc, tid = Grp<G>::tid();
     const int ntr = T.count[s]; // these two loads are only needed after the table is built: they travel meanwhile
     const int64_t t_off = T.offset[s];
     const int t_begin = split * T.chunk;
-    CellAcc *ent = reinterpret_cast<CellAcc *>(sm_raw);
-    double *red = reinterpret_cast<double *>(ent + M.n_cell * na);
-    uint8_t *bad = reinterpret_cast<uint8_t *>(red + BLOCK / 32);
-    build_cell_table<BLOCK>(M, th, ent, bad, addr);
-    unsigned long long *bslot = (T.btrace && threadIdx.x == 0) ? T.btrace + 5 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
-    if (bslot) bslot[3] = BlockTrace::now();
+    CellAcc *rows = reinterpret_cast<CellAcc *>(sm_raw);
+    double *red = reinterpret_cast<double *>(rows + M.n_row);
+    uint8_t *bad = reinterpret_cast<uint8_t *>(red + G / 32);
+    build_rows<G>(M, th, rows, bad, bad + M.n_cell, addr);
+    if (stamp && tid == 0) stamp[0] = BlockTrace::now();
     if (t_begin >= ntr) return 0.0; // empty chunk (a subject with fewer trials than the longest one)
 
     const int t_end = min(ntr, t_begin + T.chunk);
     const double *rt = T.rt + t_off;
     const uint16_t *cl = T.cell + t_off;
+    const uint16_t *row_of = M.row_of;
     LogProd acc;
     acc.init();
     const double zf = T.zero_floor;
@@ -569,12 +641,12 @@ __device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &
     bool leftovers = false;
     if constexpr (NACC == 2) {
         // two trials of a thread advance together (n1pdf_fast2); with more accumulators the second trial's
-        // state no longer fits the register budget of 12 blocks per SM and the one-trial loop below is faster
-        for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
+        // state no longer fits the register budget of 24 warps per SM and the one-trial loop below is faster
+        for (int t = t_begin + 2 * tid; t < t_end; t += 2 * G) {
             const double2 r2 = __ldg(reinterpret_cast<const double2 *>(rt + t));
             const ushort2 c2 = __ldg(reinterpret_cast<const ushort2 *>(cl + t));
             const int c0 = c2.x, c1 = (t + 1 < t_end) ? c2.y : c2.x; // the partner of a last odd trial is padding
-            const CellAcc *e0 = ent + c0 * na, *e1 = ent + c1 * na;
+            const RowRef e0{rows, row_of + c0 * na}, e1{rows, row_of + c1 * na};
             const bool pair_ok = (t + 1 < t_end) && bad[c0] == kCellRegular && bad[c1] == kCellRegular && n1pdf_fast_ok<NACC>(r2.x, e0, na) &&
                                  n1pdf_fast_ok<NACC>(r2.y, e1, na);
             if (pair_ok) {
@@ -593,26 +665,9 @@ __device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &
             } else
                 leftovers = true;
         }
-        if (leftovers) { // cold loop: pairs with an invalid / generic cell or rt <= t0 in them, and a last odd trial
-            for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
-                const int nh = (t + 1 < t_end) ? 2 : 1;
-                if (nh == 2) {
-                    const int c0 = cl[t], c1 = cl[t + 1];
-                    if (bad[c0] == kCellRegular && bad[c1] == kCellRegular && n1pdf_fast_ok<NACC>(rt[t], ent + c0 * na, na) &&
-                        n1pdf_fast_ok<NACC>(rt[t + 1], ent + c1 * na, na))
-                        continue; // done in the hot loop
-                }
-                for (int h = 0; h < nh; ++h) {
-                    const int c = cl[t + h];
-                    double pdf = n1pdf_any<NACC>(bad[c], rt[t + h], ent + c * na, na);
-                    if (zf > 0.0 && pdf <= 0.0) pdf = zf;
-                    acc.mul(pdf);
-                    if constexpr (TRACE) trace_out[t + h] = log(pdf);
-                }
-            }
-        }
+        if (leftovers) like_cold<NACC, G, true, TRACE>(rows, row_of, bad, na, rt, cl, t_begin, t_end, zf, acc, trace_out);
     } else {
-        for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
+        for (int t = t_begin + 2 * tid; t < t_end; t += 2 * G) {
             const double2 r2 = __ldg(reinterpret_cast<const double2 *>(rt + t));
             const ushort2 c2 = __ldg(reinterpret_cast<const ushort2 *>(cl + t));
             const int nh = (t + 1 < t_end) ? 2 : 1;
@@ -620,7 +675,7 @@ __device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &
             for (int h = 0; h < nh; ++h) {
                 const int c = h ? c2.y : c2.x;
                 const double r = h ? r2.y : r2.x;
-                const CellAcc *e = ent + c * na;
+                const RowRef e{rows, row_of + c * na};
                 if (bad[c] == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) {
                     double pdf = n1pdf_fast<NACC>(r, e, na);
                     if (zf > 0.0 && pdf <= 0.0) pdf = zf;
@@ -630,26 +685,11 @@ __device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &
                     leftovers = true;
             }
         }
-        if (leftovers) { // cold loop: invalid / generic cells and trials with rt <= t0
-            for (int t = t_begin + 2 * threadIdx.x; t < t_end; t += 2 * BLOCK) {
-                const int nh = (t + 1 < t_end) ? 2 : 1;
-                for (int h = 0; h < nh; ++h) {
-                    const int c = cl[t + h];
-                    const double r = rt[t + h];
-                    const CellAcc *e = ent + c * na;
-                    const uint8_t cls = bad[c];
-                    if (cls == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) continue; // done in the hot loop
-                    double pdf = cls == kCellInvalid ? kFloor : n1pdf_generic_body<NACC>(r, e, na);
-                    if (zf > 0.0 && pdf <= 0.0) pdf = zf;
-                    acc.mul(pdf);
-                    if constexpr (TRACE) trace_out[t + h] = log(pdf);
-                }
-            }
-        }
+        if (leftovers) like_cold<NACC, G, false, TRACE>(rows, row_of, bad, na, rt, cl, t_begin, t_end, zf, acc, trace_out);
     }
-    if (bslot) bslot[4] = BlockTrace::now();
-    double v = block_sum<BLOCK>(acc.value(), red);
-    if (threadIdx.x == 0 && T.counter) atomicAdd(T.counter, (unsigned long long)(t_end - t_begin));
+    if (stamp && tid == 0) stamp[1] = BlockTrace::now();
+    double v = block_sum<G>(acc.value(), red);
+    if (tid == 0 && T.counter) atomicAdd(T.counter, (unsigned long long)(t_end - t_begin));
     return v;
 }
 
@@ -659,8 +699,9 @@ __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, cons
                                          int chain, int split, double *ll_part, unsigned char *sm_raw)
 {
     const int C = L.nchain, D = L.npar;
+    unsigned long long *bslot = (T.btrace && threadIdx.x == 0) ? T.btrace + 5 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
     const double v = like_eval<NACC, BLOCK>(M, T, L.prop + ((size_t)p * C + chain) * D, make_addr(L, p, iter, sweep, chain), p / L.n_rep, split,
-                                            sm_raw);
+                                            sm_raw, nullptr, bslot ? bslot + 3 : nullptr);
     if (threadIdx.x == 0) ll_part[((size_t)p * C + chain) * T.nsplit + split] = v;
 }
 
@@ -802,13 +843,13 @@ __global__ void __launch_bounds__(BLOCK) k_trial_logdens(DevModel M, const doubl
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int na = M.n_acc, D = M.npar, k = blockIdx.x;
-    CellAcc *ent = reinterpret_cast<CellAcc *>(sm_raw);
-    uint8_t *bad = reinterpret_cast<uint8_t *>(ent + M.n_cell * na);
+    CellAcc *rows = reinterpret_cast<CellAcc *>(sm_raw);
+    uint8_t *bad = reinterpret_cast<uint8_t *>(rows + M.n_row);
     DrawAddr addr = {0, 0, 0, 0, 0};
-    build_cell_table<BLOCK>(M, theta + (size_t)k * D, ent, bad, addr);
+    build_rows<BLOCK>(M, theta + (size_t)k * D, rows, bad, bad + M.n_cell, addr);
     for (int t = blockIdx.y * BLOCK + threadIdx.x; t < ntr; t += gridDim.y * BLOCK) {
         const int c = cl[t];
-        out[(size_t)k * ntr + t] = log(n1pdf_any<0>(bad[c], rt[t], ent + c * na, na));
+        out[(size_t)k * ntr + t] = log(n1pdf_any<0>(bad[c], rt[t], RowRef{rows, M.row_of + c * na}, na));
     }
 }
 
@@ -876,6 +917,105 @@ __device__ __forceinline__ void accept_one(const Level &L, int p, int src, uint3
     }
 }
 
+// MH tests of the pending proposals made from chains [c_begin, c_end) of population p by ONE WARP: lane = chain for the
+// decision (update_theta, src/de.cpp:81-108), then the whole warp copies every accepted vector (a lane copying its own
+// vector alone pays one memory round trip per element: the loads may alias the stores).
+__device__ __forceinline__ void accept_warp(const Level &L, int p, int c_begin, int c_end, uint32_t iter, int sweep, const double *ll_part, int nsplit,
+                                            int lane)
+{
+    const int C = L.nchain, D = L.npar;
+    for (int base = c_begin; base < c_end; base += 32) {
+        const int src = base + lane;
+        int tgt = -1, acc = 0;
+        double tmp_lp = 0.0, tmp_ll = 0.0;
+        if (src < c_end) tgt = ldm(L.target + p * C + src);
+        if (tgt >= 0) {
+            const double *part = ll_part + ((size_t)p * C + src) * nsplit;
+            for (int k = 0; k < nsplit; ++k) tmp_ll += ldm(part + k);
+            tmp_lp = L.prior_ovr ? deferred_prop_lp(L, p, src) : ldm(L.prop_lp + p * C + src);
+            const double cur = ldm(L.lp + p * C + tgt) + ldm(L.ll + p * C + tgt); // src/de.cpp:121 / :189-190 / :577 / :656-657
+            const double mh = exp((tmp_lp + tmp_ll) - cur);                       // :147
+            L.target[p * C + src] = -1;                                            // proposal consumed
+            if (!isnan(mh)) {                                                      // :83-87, no draw
+                DrawAddr a = make_addr(L, p, iter, sweep, src);
+                acc = draw_uniform(a, U_ACCEPT, 0) < mh;                           // :88
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, acc);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int s2 = base + l, t2 = __shfl_sync(0xffffffffu, tgt, l);
+            const double *pr = L.prop + ((size_t)p * C + s2) * D;
+            double *th = L.theta + ((size_t)p * C + t2) * D;
+            for (int d = lane; d < D; d += 32) th[d] = ldm(pr + d);
+        }
+        if (acc) {
+            L.lp[p * C + tgt] = tmp_lp;
+            L.ll[p * C + tgt] = tmp_ll;
+        }
+    }
+}
+
+// The same MH test by ONE WARP for a crossover proposal that is still in shared memory (prop_sm; made from chain src, which
+// is also the chain it challenges): lane d evaluates prior term d, so the dependent loads of the thirteen terms travel
+// together instead of one after the other.  No other item of the half-sweep reads chain src (difference partners come
+// from the other parity), so the chain can be overwritten at once.  lp_lane0: log prior of the proposal (lane 0) when the
+// prior is fixed; ll_lane0: its log-likelihood (lane 0) when there is one trial chunk.  scratch: D doubles of shared memory.
+__device__ __forceinline__ void accept_self(const Level &L, int p, int src, uint32_t iter, int sweep, const double *prop_sm, double lp_lane0,
+                                            const double *ll_part, int nsplit, double ll_lane0, double *scratch, int lane)
+{
+    const int C = L.nchain, D = L.npar;
+    // every global load of the decision is issued up front: they travel together
+    double cur = 0.0, tmp_ll = ll_lane0;
+    if (lane == 0) {
+        cur = ldm(L.lp + p * C + src) + ldm(L.ll + p * C + src); // src/de.cpp:121 / :577
+        if (nsplit > 1) {
+            const double *part = ll_part + ((size_t)p * C + src) * nsplit;
+            tmp_ll = 0.0;
+            for (int k = 0; k < nsplit; ++k) tmp_ll += ldm(part + k);
+        }
+    }
+    if (L.prior_ovr) {
+        const size_t rc = (size_t)(p % L.n_rep) * C + src;
+        const double *ovr = L.prior_ovr + rc * 2 * D;
+        const double *oc = L.ovr_consts ? L.ovr_consts + rc * 2 * D : nullptr;
+        bool generic = oc == nullptr;
+        if (oc && D <= 32) { // phi-driven truncated normals (the hierarchical fits of the reference): no dependent loads
+            double K = 0.0, m = 0.0, iv = 0.0, x = 0.0, lo = 0.0, up = 0.0;
+            if (lane < D) {
+                K = ldm(oc + 2 * lane + 1); m = ldm(ovr + lane); iv = ldm(oc + 2 * lane);
+                lo = L.prior.lower[lane]; up = L.prior.upper[lane];
+                x = prop_sm[lane];
+                const double z = (x - m) * iv;
+                scratch[lane] = (x < lo || x > up) ? -INFINITY : -(0.5 * z * z + K);
+            }
+            generic = __any_sync(0xffffffffu, lane < D && !(K == K));
+        }
+        if (generic)
+            for (int d = lane; d < D; d += 32) scratch[d] = prior_term(L, d, prop_sm[d], ovr, oc);
+        __syncwarp();
+    }
+    int acc = 0;
+    double tmp_lp = 0.0;
+    if (lane == 0) {
+        tmp_lp = L.prior_ovr ? sum_arma_order(scratch, D) : lp_lane0;
+        const double mh = exp((tmp_lp + tmp_ll) - cur); // :147
+        if (!isnan(mh)) {                               // :83-87, no draw
+            DrawAddr a = make_addr(L, p, iter, sweep, src);
+            acc = draw_uniform(a, U_ACCEPT, 0) < mh;    // :88
+        }
+    }
+    if (__shfl_sync(0xffffffffu, acc, 0)) {
+        double *th = L.theta + ((size_t)p * C + src) * D;
+        for (int d = lane; d < D; d += 32) th[d] = prop_sm[d];
+        if (lane == 0) {
+            L.lp[p * C + src] = tmp_lp;
+            L.ll[p * C + src] = tmp_ll;
+        }
+    }
+}
+
 __global__ void k_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *ll_part, int nsplit)
 {
     const int C = L.nchain;
@@ -913,6 +1053,11 @@ struct HyperArgs {
     int D;                    // subject-level npar (phi vector is 2 D)
     int subj_per_block, nsplit;
     int need_cur;             // refresh current hyper-likelihood (hierarchy) or not (run_hyper)
+    // Constants of the phi-driven subject prior (what k_phi_consts computes) of every PROPOSED phi vector, written by the
+    // proposing item and copied over the target chain's constants when the proposal is accepted -- the two Phi and the
+    // logarithm are needed for the hyper-likelihood anyway.  Null: the constants are refreshed by k_phi_consts instead.
+    double *prop_consts;      // [n_rep][C][D][2], indexed by the chain proposed FROM
+    double *consts;           // [n_rep][C][D][2] = Level::ovr_consts of the subject level
 };
 
 // hyper-likelihood terms of one block: the subjects [s_begin, s_end) of (replicate r, chain c) under the
@@ -921,40 +1066,78 @@ struct HyperArgs {
 // when has_prop
 template <int BLOCK>
 __device__ __forceinline__ void hyper_block(const HyperArgs &H, int r, int c, int split, const double *phi_c, const double *phi_p,
-                                            bool has_prop, bool prop_in_smem, double *sm_h, double &vc, double &vp)
+                                            bool has_prop, bool prop_in_smem, double *sm_h, double &vc, double &vp, double *prop_consts = nullptr)
 {
-    const int D = H.D;
-    double *cm = sm_h, *cs = cm + D, *cl = cs + D, *pm = cl + D, *ps = pm + D, *pl = ps + D, *red = pl + D;
-    for (int d = threadIdx.x; d < D; d += BLOCK) {
-        const double lo = H.like.lower[d], up = H.like.upper[d];
-        double m = ldm(phi_c + d), s = ldm(phi_c + D + d);
+    const int D = H.D, tid = Grp<BLOCK>::tid();
+    double *cm = sm_h, *cs = cm + D, *cl = cs + D, *pm = cl + D, *ps = pm + D, *pl = ps + D, *cls = pl + D, *pls = cls + D, *red = pls + D;
+    auto prep_cur = [&](int d) {
+        const double m = ldm(phi_c + d), s = ldm(phi_c + D + d);
         cm[d] = m; cs[d] = s;
-        if (H.need_cur) cl[d] = log(pnorm5(up, m, s, true) - pnorm5(lo, m, s, true)); // tnorm_class::set_parameters, @hdr/tnorm.h:59-67
-        if (has_prop) {
-            m = prop_in_smem ? phi_p[d] : ldm(phi_p + d);
-            s = prop_in_smem ? phi_p[D + d] : ldm(phi_p + D + d);
-            pm[d] = m; ps[d] = s;
-            pl[d] = log(pnorm5(up, m, s, true) - pnorm5(lo, m, s, true));
+        if (H.need_cur) {
+            cl[d] = tnorm_logmass(H.like.lower[d], H.like.upper[d], m, s); // tnorm_class::set_parameters, @hdr/tnorm.h:59-67
+            cls[d] = log(s); // dnorm4's log(sigma): once per parameter instead of once per subject
+        }
+    };
+    auto prep_prop = [&](int d) {
+        const double m = prop_in_smem ? phi_p[d] : ldm(phi_p + d);
+        const double s = prop_in_smem ? phi_p[D + d] : ldm(phi_p + D + d);
+        pm[d] = m; ps[d] = s;
+        pl[d] = tnorm_logmass(H.like.lower[d], H.like.upper[d], m, s);
+        const double ls = log(s);
+        pls[d] = ls;
+        if (prop_consts) { // the same expressions as k_phi_consts
+            double inv = 0.0, K = NAN;
+            if (H.like.dist[d] == 1 && H.like.log_p[d] != 0 && s > 0.0 && isfinite(s) && isfinite(m)) {
+                inv = 1.0 / s;
+                K = kLnSqrt2Pi + ls + pl[d];
+            }
+            prop_consts[2 * d] = inv;
+            prop_consts[2 * d + 1] = K;
+        }
+    };
+    if (BLOCK == 32 && D <= 16) { // one warp: the current phi on lanes 0-15, the proposed one on lanes 16-31, side by side
+        const int d = tid & 15;
+        if (d < D) {
+            if (tid < 16) prep_cur(d);
+            else if (has_prop) prep_prop(d);
+        }
+    } else {
+        for (int d = tid; d < D; d += BLOCK) {
+            prep_cur(d);
+            if (has_prop) prep_prop(d);
         }
     }
-    __syncthreads();
+    Grp<BLOCK>::sync();
     const int s_begin = split * H.subj_per_block, s_end = min(H.S, s_begin + H.subj_per_block);
     const int n_el = (s_end - s_begin) * D;
     const double *xbase = H.x + (size_t)r * H.x_rep_stride + (size_t)c * H.x_chain_stride;
     double sum_c = 0.0, sum_p = 0.0;
-    for (int e = threadIdx.x; e < n_el; e += BLOCK) {
-        const int si = e / D, d = e - si * D;
-        const double x = ldm(xbase + (size_t)(s_begin + si) * H.x_subj_stride + d);
-        const int dist = H.like.dist[d];
-        const bool lg = H.like.log_p[d] != 0;
-        const double lo = H.like.lower[d], up = H.like.upper[d];
-        if (dist == 1 && lg) { // TNORM, log scale: the hierarchical fits of the reference
-            const bool outside = (x < lo) || (x > up);
-            if (H.need_cur) sum_c += outside ? -INFINITY : dnorm4(x, cm[d], cs[d], true) - cl[d];
-            if (has_prop) sum_p += outside ? -INFINITY : dnorm4(x, pm[d], ps[d], true) - pl[d];
-        } else {
-            if (H.need_cur) sum_c += dprior1(dist, x, cm[d], cs[d], lo, up, lg);
-            if (has_prop) sum_p += dprior1(dist, x, pm[d], ps[d], lo, up, lg);
+    for (int e0 = tid; e0 < n_el; e0 += 4 * BLOCK) { // four loads in flight per thread; the order of the additions is unchanged
+        double xs[4];
+        int ds[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = e0 + k * BLOCK;
+            const int si = e / D;
+            ds[k] = e - si * D;
+            xs[k] = e < n_el ? ldm(xbase + (size_t)(s_begin + si) * H.x_subj_stride + ds[k]) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (e0 + k * BLOCK >= n_el) break;
+            const int d = ds[k];
+            const double x = xs[k];
+            const int dist = H.like.dist[d];
+            const bool lg = H.like.log_p[d] != 0;
+            const double lo = H.like.lower[d], up = H.like.upper[d];
+            if (dist == 1 && lg) { // TNORM, log scale: the hierarchical fits of the reference
+                const bool outside = (x < lo) || (x > up);
+                if (H.need_cur) sum_c += outside ? -INFINITY : dnorm4_log_pre(x, cm[d], cs[d], cls[d]) - cl[d];
+                if (has_prop) sum_p += outside ? -INFINITY : dnorm4_log_pre(x, pm[d], ps[d], pls[d]) - pl[d];
+            } else {
+                if (H.need_cur) sum_c += dprior1(dist, x, cm[d], cs[d], lo, up, lg);
+                if (has_prop) sum_p += dprior1(dist, x, pm[d], ps[d], lo, up, lg);
+            }
         }
     }
     vc = block_sum<BLOCK>(sum_c, red);
@@ -964,7 +1147,7 @@ __device__ __forceinline__ void hyper_block(const HyperArgs &H, int r, int c, in
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_hyper(Level L, HyperArgs H, int step, double *hpart /* [npop][C][2][nsplit] */)
 {
-    extern __shared__ double sm_h[]; // cur: mean[D] sd[D] logden[D]; prop: same; then reduction scratch
+    extern __shared__ double sm_h[]; // cur: mean[D] sd[D] logden[D]; prop: same; log sd of both [2 D]; then reduction scratch
     const int C = L.nchain, D = H.D;
     int r, c;
     if (step < 0) {
@@ -1040,24 +1223,26 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-// block-wide: reduce the nsplit partials of every value, exchange with the peers, leave the all-rank sums in hsum
+// group-wide: reduce the nsplit partials of every value, exchange with the peers, leave the all-rank sums in hsum
+template <int G = 0>
 __device__ __forceinline__ bool reduce_exchange_block(const double *hpart, int n, int nsplit, double *hsum, const P2PWindow &w)
 {
+    const int tid = Grp<G>::tid(), nthr = Grp<G>::size();
     const unsigned long long seq = ldm(w.seq) + 1;
     const int b = (int)(seq & 1ull);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = tid; i < n; i += nthr) {
         double v = 0.0;
         for (int k = 0; k < nsplit; ++k) v += *(volatile const double *)(hpart + (size_t)i * nsplit + k);
         for (int q = 0; q < w.n_rank; ++q) w.slots[q][((size_t)b * w.n_rank + w.rank) * kP2PMaxN + i] = v;
     }
     __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < w.n_rank) {
-        volatile unsigned long long *f = w.flags[threadIdx.x] + (size_t)b * kP2PMaxRanks + w.rank;
+    Grp<G>::sync();
+    if (tid < w.n_rank) {
+        volatile unsigned long long *f = w.flags[tid] + (size_t)b * kP2PMaxRanks + w.rank;
         *f = seq;
     }
-    if (threadIdx.x < w.n_rank) {
-        volatile unsigned long long *mine = w.flags[w.rank] + (size_t)b * kP2PMaxRanks + threadIdx.x;
+    if (tid < w.n_rank) {
+        volatile unsigned long long *mine = w.flags[w.rank] + (size_t)b * kP2PMaxRanks + tid;
         const unsigned long long t0 = globaltimer_ns();
         while (*mine < seq) {
             if (*(volatile int *)w.status) break; // an earlier exchange already timed out: do not wait again
@@ -1069,16 +1254,16 @@ __device__ __forceinline__ bool reduce_exchange_block(const double *hpart, int n
         }
     }
     __threadfence_system();
-    __syncthreads();
-    if (*(volatile int *)w.status) return false; // block-uniform: read after the barrier, never cleared while kernels run
+    Grp<G>::sync();
+    if (*(volatile int *)w.status) return false; // group-uniform: read after the barrier, never cleared while kernels run
     const double *loc = w.slots[w.rank] + (size_t)b * w.n_rank * kP2PMaxN;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = tid; i < n; i += nthr) {
         double v = 0.0;
         for (int q = 0; q < w.n_rank; ++q) v += *(volatile const double *)(loc + (size_t)q * kP2PMaxN + i);
         hsum[i] = v;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) *w.seq = seq;
+    Grp<G>::sync();
+    if (tid == 0) *w.seq = seq;
     return true;
 }
 
@@ -1092,8 +1277,9 @@ __global__ void __launch_bounds__(256) k_hyper_reduce_exchange(const double *hpa
 __global__ void k_peer_barrier(P2PWindow w) { reduce_exchange_block(nullptr, 0, 0, nullptr, w); }
 
 // phi-level accept of the proposal made from chain src (src/de.cpp:397-400, 427-463 and :494-500, 519-549)
+// prop_consts / consts (HyperArgs, may be null): on accept the constants of the proposal replace those of the target chain
 __device__ __forceinline__ void phi_accept_one(const Level &L, int r, int src, uint32_t iter, int sweep, bool in_place_migration,
-                                               const double *hsum, int need_cur)
+                                               const double *hsum, int need_cur, const double *prop_consts = nullptr, double *consts = nullptr)
 {
     const int C = L.nchain, D = L.npar;
     const int tgt = ldm(L.target + r * C + src);
@@ -1117,6 +1303,57 @@ __device__ __forceinline__ void phi_accept_one(const Level &L, int r, int src, u
         for (int d = 0; d < D; ++d) th[d] = ldm(pr + d);
         L.lp[r * C + tgt] = tmp_lp;
         L.ll[r * C + tgt] = tmp_ll;
+        if (prop_consts) { // D = 2 x (subject npar): [npar][2] doubles per chain
+            const double *pc = prop_consts + ((size_t)r * C + src) * D;
+            double *cc = consts + ((size_t)r * C + tgt) * D;
+            for (int d = 0; d < D; ++d) cc[d] = ldm(pc + d);
+        }
+    }
+}
+
+// Every MH decision of a phi half-sweep by ONE WARP: lane = chain for the decision (phi_accept_one's rules), then the whole
+// warp copies every accepted phi vector and the prior constants that belong to it.
+__device__ __forceinline__ void phi_accept_warp(const Level &L, int n_rc, uint32_t iter, int sweep, const double *hsum, int need_cur,
+                                                const double *prop_consts, double *consts, int lane)
+{
+    const int C = L.nchain, D = L.npar;
+    for (int base = 0; base < n_rc; base += 32) {
+        const int g = base + lane; // = r * C + src
+        int tgt = -1, acc = 0;
+        double tmp_lp = 0.0, tmp_ll = 0.0;
+        if (g < n_rc) tgt = ldm(L.target + g);
+        const int r = g / C;
+        if (tgt >= 0) {
+            tmp_ll = ldm(hsum + (size_t)g * 2 + 1);
+            tmp_lp = ldm(L.prop_lp + g);
+            double cur_ll = ldm(L.ll + r * C + tgt);
+            if (need_cur) {
+                cur_ll = ldm(hsum + ((size_t)r * C + tgt) * 2 + 0);
+                L.ll[r * C + tgt] = cur_ll; // :397-398 / :498-500
+            }
+            const double cur = ldm(L.lp + r * C + tgt) + cur_ll;
+            const double mh = exp((tmp_lp + tmp_ll) - cur);
+            L.target[g] = -1; // proposal consumed
+            if (!isnan(mh)) {
+                DrawAddr a = make_addr(L, r, iter, sweep, g - r * C);
+                acc = draw_uniform(a, U_ACCEPT, 0) < mh;
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, acc);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int g2 = base + l, t2 = __shfl_sync(0xffffffffu, tgt, l);
+            const size_t to = ((size_t)(g2 / C) * C + t2) * D;
+            const double *pr = L.prop + (size_t)g2 * D;
+            for (int d = lane; d < D; d += 32) L.theta[to + d] = ldm(pr + d);
+            if (prop_consts)
+                for (int d = lane; d < D; d += 32) consts[to + d] = ldm(prop_consts + (size_t)g2 * D + d);
+        }
+        if (acc) {
+            L.lp[r * C + tgt] = tmp_lp;
+            L.ll[r * C + tgt] = tmp_ll;
+        }
     }
 }
 
@@ -1153,17 +1390,17 @@ __global__ void k_phi_accept(Level L, const uint32_t *d_iter, int sweep, int ste
 // Replaces k_propose + k_hyper + k_hyper_reduce(_exchange) + k_phi_accept on the phi critical path.
 // ------------------------------------------------------------------------------------------------
 // Part 1, every block (replicate r, chain c, subject split): proposal + the block's share of the two sums -> hpart.
-// sm_h: 6 D + 2 BLOCK/32 doubles (hyper_block), then proposal [2 D], prior scratch [2 D]; s_k: one int of shared memory.
+// sm_h: 8 D + 2 BLOCK/32 doubles (hyper_block), then proposal [2 D], prior scratch [2 D]; s_k: one int of shared memory.
 // Returns (block-uniform) the sweep position at which chain c proposes in this half, -1 if it does not.
 template <int BLOCK>
 __device__ __forceinline__ int phi_half_part(const Level &L, const HyperArgs &H, uint32_t iter, int sweep, int half, int r, int c, int split,
                                              double *hpart, double *sm_h, int *s_k)
 {
-    const int C = L.nchain, D = H.D, D2 = 2 * D;
+    const int C = L.nchain, D = H.D, D2 = 2 * D, tid = Grp<BLOCK>::tid();
     const int mode = ldm(L.mode + r), para_idx = ldm(L.para + r);
     const int nsteps = mode ? ldm(L.mig_n + r) : C;
-    double *sprop = sm_h + 6 * D + 2 * (BLOCK / 32), *scratch = sprop + D2;
-    if (threadIdx.x == 0) { // sweep position at which chain c proposes in this launch, -1: it does not
+    double *sprop = sm_h + 8 * D + 2 * (BLOCK / 32), *scratch = sprop + D2;
+    if (tid == 0) { // sweep position at which chain c proposes in this launch, -1: it does not
         int k = -1;
         if (mode == 0) {
             if (half < 0 || (c & 1) == half) k = c;
@@ -1173,25 +1410,26 @@ __device__ __forceinline__ int phi_half_part(const Level &L, const HyperArgs &H,
         }
         *s_k = k;
     }
-    __syncthreads();
+    Grp<BLOCK>::sync();
     const int k = *s_k;
-    if (k >= 0 && threadIdx.x < 32) {
+    if (k >= 0 && tid < 32) {
         int src, tgt;
         double lp;
-        propose_position(L, r, k, mode, nsteps, para_idx, iter, sweep, half, (int)threadIdx.x, scratch, sprop, src, tgt, lp);
+        propose_position(L, r, k, mode, nsteps, para_idx, iter, sweep, half, tid, scratch, sprop, src, tgt, lp);
         if (split == 0) {
             double *pr = L.prop + ((size_t)r * C + c) * D2;
-            for (int d = threadIdx.x; d < D2; d += 32) pr[d] = sprop[d];
-            if (threadIdx.x == 0) {
+            for (int d = tid; d < D2; d += 32) pr[d] = sprop[d];
+            if (tid == 0) {
                 L.prop_lp[r * C + c] = lp;
                 L.target[r * C + c] = tgt;
             }
         }
     }
-    __syncthreads();
+    Grp<BLOCK>::sync();
     double vc, vp;
-    hyper_block<BLOCK>(H, r, c, split, L.theta + ((size_t)r * C + c) * D2, sprop, k >= 0, true, sm_h, vc, vp);
-    if (threadIdx.x == 0) {
+    hyper_block<BLOCK>(H, r, c, split, L.theta + ((size_t)r * C + c) * D2, sprop, k >= 0, true, sm_h, vc, vp,
+                       (H.prop_consts && split == 0) ? H.prop_consts + ((size_t)r * C + c) * D2 : nullptr);
+    if (tid == 0) {
         double *o = hpart + (((size_t)r * C + c) * 2) * H.nsplit + split;
         o[0] = vc;
         o[H.nsplit] = vp;
@@ -1199,25 +1437,37 @@ __device__ __forceinline__ int phi_half_part(const Level &L, const HyperArgs &H,
     return k;
 }
 
-// Part 2, the block that finishes last: sum over the splits, exchange with the peer GPUs, MH test of every proposal.
-// Returns false (block-uniform) when the exchange timed out: nothing was accepted.
+// Part 2, the group that finishes last: sum over the splits, exchange with the peer GPUs, MH test of every proposal.
+// Returns false (group-uniform) when the exchange timed out: nothing was accepted.
 template <int BLOCK>
 __device__ __forceinline__ bool phi_half_finish(const Level &L, const HyperArgs &H, uint32_t iter, int sweep, const double *hpart, double *hsum,
                                                 const P2PWindow &w, int use_p2p)
 {
-    const int C = L.nchain;
+    const int C = L.nchain, tid = Grp<BLOCK>::tid();
     const int n = L.npop * C * 2;
     if (use_p2p) {
-        if (!reduce_exchange_block(hpart, n, H.nsplit, hsum, w)) return false;
+        if (!reduce_exchange_block<BLOCK>(hpart, n, H.nsplit, hsum, w)) return false;
     } else {
-        for (int i = threadIdx.x; i < n; i += BLOCK) {
+        for (int i = tid; i < n; i += BLOCK) {
+            const double *hp = hpart + (size_t)i * H.nsplit;
             double v = 0.0;
-            for (int q = 0; q < H.nsplit; ++q) v += ldm(hpart + (size_t)i * H.nsplit + q);
+            int q = 0;
+            for (; q + 4 <= H.nsplit; q += 4) { // same order of additions, four loads in flight
+                const double a = ldm(hp + q), b = ldm(hp + q + 1), c = ldm(hp + q + 2), e = ldm(hp + q + 3);
+                v += a; v += b; v += c; v += e;
+            }
+            for (; q < H.nsplit; ++q) v += ldm(hp + q);
             hsum[i] = v;
         }
     }
-    __syncthreads();
-    for (int g = threadIdx.x; g < L.npop * C; g += BLOCK) phi_accept_one(L, g / C, g - (g / C) * C, iter, sweep, false, hsum, H.need_cur);
+    __threadfence();
+    Grp<BLOCK>::sync();
+    if constexpr (BLOCK == 32) {
+        phi_accept_warp(L, L.npop * C, iter, sweep, hsum, H.need_cur, H.prop_consts, H.consts, tid);
+    } else {
+        for (int g = tid; g < L.npop * C; g += BLOCK)
+            phi_accept_one(L, g / C, g - (g / C) * C, iter, sweep, false, hsum, H.need_cur, H.prop_consts, H.consts);
+    }
     return true;
 }
 
@@ -1225,7 +1475,7 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_phi_half(Level L, HyperArgs H, const uint32_t *d_iter, int sweep, int half, double *hpart,
                                                     double *hsum, unsigned int *ticket, P2PWindow w, int use_p2p)
 {
-    extern __shared__ double sm_h[]; // hyper_block's 6 D + 2 BLOCK/32, then proposal [2 D], prior scratch [2 D]
+    extern __shared__ double sm_h[]; // hyper_block's 8 D + 2 BLOCK/32, then proposal [2 D], prior scratch [2 D]
     __shared__ int s_k, s_last;
     const int C = L.nchain;
     const int r = blockIdx.x / C, c = blockIdx.x - r * C, split = blockIdx.y;

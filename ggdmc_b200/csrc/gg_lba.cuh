@@ -19,6 +19,14 @@ struct CellAcc {
     double b, A, mean_v, sd_v, t0a, inv_sdv, inv_A, inv_denom;
 };
 
+// The table holds every DISTINCT (cell, accumulator) row once (the model says which entries draw the same six
+// parameters, gg_engine.cu ModelDev); a trial reaches its cell's rows through the cell's row indices.
+struct RowRef {
+    const CellAcc *rows;
+    const uint16_t *idx; // [n_acc] row of accumulator j
+    GG_HD const CellAcc &operator[](int j) const { return rows[idx[j]]; }
+};
+
 // 1 / x for the cell table: hardware seed + two Newton steps (<= 1 ulp) when x is a comfortable positive normal
 // number -- true of A, sd_v and the drift denominator of every regular cell --, IEEE division otherwise, so the
 // generic path keeps the reference's behaviour for zeros, negatives, infinities and NaN
@@ -72,8 +80,10 @@ enum : uint8_t {
 
 // density of one trial whose cell's table row is e[0 .. n_acc): the reference's arithmetic with all of
 // its branches and NaN rules (lba_class::d / p, @hdr/lba.h:213-248, 286-345)
-template <int NACC>
-GG_HD double n1pdf_generic_body(double rt, const CellAcc *e, int n_acc_rt)
+// `e` is anything indexable by accumulator: a `const CellAcc *` (rows of one cell side by side) or a RowRef (rows of a
+// de-duplicated table picked through the cell's row indices)
+template <int NACC, class E>
+GG_HD double n1pdf_generic_body(double rt, const E &e, int n_acc_rt)
 {
     const int n_acc = NACC > 0 ? NACC : n_acc_rt;
     double t0a = e[0].t0a;
@@ -125,8 +135,8 @@ GG_HD double n1pdf_generic_body(double rt, const CellAcc *e, int n_acc_rt)
 }
 
 // Can the fast path take this trial?  Needs rt > t0 for every accumulator (then every z is finite).
-template <int NACC>
-GG_HD bool n1pdf_fast_ok(double rt, const CellAcc *e, int n_acc_rt)
+template <int NACC, class E>
+GG_HD bool n1pdf_fast_ok(double rt, const E &e, int n_acc_rt)
 {
     const int n_acc = NACC > 0 ? NACC : n_acc_rt;
     bool ok = (rt - e[0].t0a) > 0.0;
@@ -138,8 +148,8 @@ GG_HD bool n1pdf_fast_ok(double rt, const CellAcc *e, int n_acc_rt)
 // Fast path for a trial of a REGULAR cell with n1pdf_fast_ok(): same formulas as the generic body,
 // but with finite parameters, A >= 1e-10, sd_v > 0 and rt > t0 the point-mass branches and every NaN
 // rule are dead code and every z is finite.
-template <int NACC>
-GG_HD double n1pdf_fast(double rt, const CellAcc *e, int n_acc_rt)
+template <int NACC, class E>
+GG_HD double n1pdf_fast(double rt, const E &e, int n_acc_rt)
 {
     const int n_acc = NACC > 0 ? NACC : n_acc_rt;
     double t0a = e[0].t0a;
@@ -182,8 +192,8 @@ GG_HD double n1pdf_fast(double rt, const CellAcc *e, int n_acc_rt)
 // consecutive FP64 instructions depend on each other cannot fill the FP64 pipe even with every scheduler slot
 // taken (measured on B200, tools/cuda_probe/dfma_lat.cu: 3.0 / 2.5 / 2.2 cycles per DFMA per scheduler with
 // 1 / 2 / 4 independent chains per warp at 6 warps per scheduler).  Per trial the arithmetic is n1pdf_fast's.
-template <int NACC>
-GG_HD void n1pdf_fast2(double rtA, const CellAcc *eA, double rtB, const CellAcc *eB, int n_acc_rt, double &outA, double &outB)
+template <int NACC, class E>
+GG_HD void n1pdf_fast2(double rtA, const E &eA, double rtB, const E &eB, int n_acc_rt, double &outA, double &outB)
 {
     const int n_acc = NACC > 0 ? NACC : n_acc_rt;
     double t0A = eA[0].t0a, t0B = eB[0].t0a;
@@ -235,8 +245,8 @@ GG_HD void n1pdf_fast2(double rtA, const CellAcc *eA, double rtB, const CellAcc 
 }
 
 // density of any trial of any cell class (used outside the hot loop)
-template <int NACC>
-GG_HD double n1pdf_any(uint8_t cls, double rt, const CellAcc *e, int n_acc)
+template <int NACC, class E>
+GG_HD double n1pdf_any(uint8_t cls, double rt, const E &e, int n_acc)
 {
     if (cls == kCellInvalid) return kFloor;
     if (cls == kCellRegular && n1pdf_fast_ok<NACC>(rt, e, n_acc)) return n1pdf_fast<NACC>(rt, e, n_acc);

@@ -13,8 +13,10 @@
 
 #ifdef __CUDACC__
 #define GG_HD __device__ __forceinline__
+#define GG_COLD __device__ __noinline__ // rare or long code that must not be copied into every caller (instruction cache)
 #else
 #define GG_HD inline
+#define GG_COLD inline
 #endif
 
 namespace gg {
@@ -77,6 +79,21 @@ GG_HD double dnorm4(double x, double mu, double sigma, bool give_log)
     if (z >= 2.0 * 1.3407807929942596e154) return give_log ? -INFINITY : 0.0;
     if (give_log) return -(kLnSqrt2Pi + 0.5 * z * z + log(sigma));
     return kInvSqrt2Pi * exp_mhalf_sq(z) / sigma;
+}
+
+// dnorm4(x, mu, sigma, true) with log(sigma) supplied by the caller (the hyper-likelihood evaluates thousands of x per sigma)
+GG_HD double dnorm4_log_pre(double x, double mu, double sigma, double log_sigma)
+{
+    if (isnan(x) || isnan(mu) || isnan(sigma)) return x + mu + sigma;
+    if (sigma < 0.0) return NAN;
+    if (isinf(sigma)) return -INFINITY;
+    if (isinf(x) && mu == x) return NAN;
+    if (sigma == 0.0) return (x == mu) ? INFINITY : -INFINITY;
+    double z = (x - mu) / sigma;
+    if (isinf(z)) return -INFINITY;
+    z = fabs(z);
+    if (z >= 2.0 * 1.3407807929942596e154) return -INFINITY;
+    return -(kLnSqrt2Pi + 0.5 * z * z + log_sigma);
 }
 
 // Rf_dunif
@@ -172,8 +189,14 @@ GG_HD double dcauchy_trunc(double x, double loc, double scale, double lower, dou
     return out;
 }
 
+// log of the probability mass a normal(mean, sd) puts on [lower, upper]: tnorm_class::set_parameters (@hdr/tnorm.h:59-67)
+GG_COLD double tnorm_logmass(double lower, double upper, double mean, double sd)
+{
+    return log(pnorm5(upper, mean, sd, true) - pnorm5(lower, mean, sd, true));
+}
+
 // one element of prior_class::dprior (@hdr/prior.h:342-407)
-GG_HD double dprior1(int dist, double x, double p0, double p1, double lower, double upper, bool log_p)
+GG_COLD double dprior1(int dist, double x, double p0, double p1, double lower, double upper, bool log_p)
 {
     switch (dist) {
     case 1: return tnorm_d(x, p0, p1, lower, upper, log_p);
