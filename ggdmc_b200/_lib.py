@@ -70,7 +70,7 @@ EXPORTS = [
     "ggdmc_b200_run_subject", "ggdmc_b200_run_hyper", "ggdmc_b200_run", "ggdmc_b200_trial_logdens", "ggdmc_b200_trial_logdens_hot",
     "ggdmc_b200_sumloglike", "ggdmc_b200_sumloglike_init", "ggdmc_b200_sumlogprior", "ggdmc_b200_select_chains", "ggdmc_b200_engine_create",
     "ggdmc_b200_engine_iterate", "ggdmc_b200_engine_iterate_flushed", "ggdmc_b200_engine_time_likelihood", "ggdmc_b200_engine_state",
-    "ggdmc_b200_engine_launch_count", "ggdmc_b200_engine_destroy", "ggdmc_b200_engine_profile", "ggdmc_b200_engine_counters", "ggdmc_b200_comm_unique_id", "ggdmc_b200_comm_init",
+    "ggdmc_b200_engine_launch_count", "ggdmc_b200_engine_is_persistent", "ggdmc_b200_engine_destroy", "ggdmc_b200_engine_profile", "ggdmc_b200_engine_counters", "ggdmc_b200_comm_unique_id", "ggdmc_b200_comm_init",
     "ggdmc_b200_comm_finalize", "ggdmc_b200_abi_version", "ggdmc_b200_device_count", "ggdmc_b200_measure_fp64_tflops",
     "ggdmc_b200_philox",
 ]
@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
         L.ggdmc_b200_measure_fp64_tflops.restype = C.c_double
         L.ggdmc_b200_engine_launch_count.restype = C.c_int64
         L.ggdmc_b200_engine_launch_count.argtypes = [C.c_void_p]
+        L.ggdmc_b200_engine_is_persistent.argtypes = [C.c_void_p]
         L.ggdmc_b200_engine_destroy.argtypes = [C.c_void_p]
         L.ggdmc_b200_engine_destroy.restype = None
         L.ggdmc_b200_comm_finalize.restype = None

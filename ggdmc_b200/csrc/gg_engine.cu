@@ -507,6 +507,7 @@ void allow_smem(K kernel, size_t bytes)
 
 constexpr int kHyperBlock = 256;
 constexpr int kProposeWarps = 4;
+constexpr int kAcceptWarps = 4;
 
 // Launch shape of the likelihood kernel: (threads per block, minimum resident blocks per SM).
 // The default was picked by measurement on B200 (profiles/); GGDMC_B200_LIKE_VARIANT overrides it
@@ -835,7 +836,7 @@ struct ggdmc_engine {
         trials.upload(t, m->n_cell, false, m->type == GGDMC_MODEL_DDM);
         pt.lap("  trials");
         S = t->n_subject;
-        const bool want_persist = persist_planned = sampler_wanted() && m->type == GGDMC_MODEL_LBA && schedule == GGDMC_SCHEDULE_PARALLEL && !is_hblocked &&
+        const bool want_persist = persist_planned = sampler_wanted(hp != nullptr) && m->type == GGDMC_MODEL_LBA && schedule == GGDMC_SCHEDULE_PARALLEL && !is_hblocked &&
                                   !is_pblocked && (!(hp && g_nccl.comm && g_nccl.n_rank > 1) || (g_p2p.ready && R * C * 2 <= kP2PMaxN)) &&
                                   sampler_fits(m->npar, hp != nullptr);
         if (want_persist) sampler_chunking((int64_t)R * S * ((C + 1) / 2));
@@ -867,7 +868,11 @@ struct ggdmc_engine {
             phi_consts.alloc((size_t)R * C * D * 2);
             L.ovr_consts = phi_consts.p;
             setup_hyper(subj.theta.p, C * D, R * C * D, D, 1);
-            if (want_persist) { // the persistent kernel keeps the prior constants up to date by itself (phi_accept_one)
+            // The fused phi half-sweep (k_phi_half, and the persistent kernel) computes the prior constants of every proposed phi
+            // vector on the way and copies them over the target chain's on accept: no k_phi_consts launch per iteration.
+            const bool multi_rank = g_nccl.comm && g_nccl.n_rank > 1;
+            consts_travel = want_persist || (schedule != GGDMC_SCHEDULE_REFERENCE && fuse_phi && !is_hblocked && (!multi_rank || (g_p2p.ready && R * C * 2 <= kP2PMaxN)));
+            if (consts_travel) {
                 prop_consts.alloc((size_t)R * C * D * 2);
                 prop_consts.zero();
                 H.prop_consts = prop_consts.p;
@@ -877,6 +882,7 @@ struct ggdmc_engine {
         make_groups();
         start_counter();
         if (want_persist) setup_sampler();
+        else if (consts_travel) phi_constants(stream); // the constants of the start state; later ones travel with accepted proposals
         if (kind == 2 && g_nccl.comm && g_nccl.n_rank > 1 && g_p2p.ready && g_p2p.timed_out())
             throw Error(GGDMC_ERR_COMM, "the communicator is in an error state (an earlier exchange timed out): call ggdmc_b200_comm_finalize and initialise it again");
         peer_barrier();
@@ -954,11 +960,8 @@ struct ggdmc_engine {
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
         int want = std::max(1, (std::max(per_sm, 1) * n_sm) / (R * C));
         int spb = std::max(64, (S + want - 1) / want); // >= 3 terms per thread: the per-block setup (proposal, 4 Phi + 2 log per parameter) is not free
-        if (persist_planned) { // one WARP per item in the sampler kernel and the phi half-sweep on the critical path of a small fit:
-            // short items (8 subjects = 3 terms per lane) while they are few, at most about half a wave of them otherwise
-            const int per_wave = n_sm * 12;
-            spb = std::max(8, (S * R * C + per_wave - 1) / per_wave);
-        }
+        if (persist_planned) // one WARP per item in the sampler kernel, the phi half-sweep on the critical path of a small fit and its fixed
+            spb = std::max(8, (S + 15) / 16); // cost (proposal, 4 Phi + 4 log per parameter) paid per item: at most 16 items per chain
         H.subj_per_block = spb;
         H.nsplit = (S + spb - 1) / spb;
         hpart.alloc((size_t)R * C * 2 * H.nsplit);
@@ -1043,7 +1046,7 @@ struct ggdmc_engine {
                 if (h == 0 && rec_first) CUDA_CHECK(cudaEventRecord(rec_first, stream));
                 timed_like(G, stream, sweep, -1, half);
                 if (join && h == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0)); // the MH test needs this iteration's phi
-                TR("k_accept", stream, launch_hi(k_accept, (n + 127) / 128, 128, 0, stream, L, d_iter.p, sweep, -1, (const double *)G.ll_part, G.T.nsplit));
+                TR("k_accept", stream, launch_hi(k_accept<kAcceptWarps>, (n + kAcceptWarps - 1) / kAcceptWarps, kAcceptWarps * 32, (size_t)kAcceptWarps * D * 8, stream, L, d_iter.p, sweep, -1, (const double *)G.ll_part, G.T.nsplit));
                 launches += 3;
             }
         } else {
@@ -1051,7 +1054,7 @@ struct ggdmc_engine {
                 TR("k_propose", stream, launch_hi(k_propose<kProposeWarps>, (L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream, L, d_iter.p, sweep, step, -1));
                 timed_like(G, stream, sweep, step, -1);
                 if (join && step == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0));
-                TR("k_accept", stream, launch_hi(k_accept, (L.npop + 127) / 128, 128, 0, stream, L, d_iter.p, sweep, step, (const double *)G.ll_part, G.T.nsplit));
+                TR("k_accept", stream, launch_hi(k_accept<kAcceptWarps>, (L.npop + kAcceptWarps - 1) / kAcceptWarps, kAcceptWarps * 32, (size_t)kAcceptWarps * D * 8, stream, L, d_iter.p, sweep, step, (const double *)G.ll_part, G.T.nsplit));
                 launches += 3;
             }
         }
@@ -1168,12 +1171,12 @@ struct ggdmc_engine {
 
     // ---- persistent sampler kernel (gg_sampler.cuh): the PARALLEL schedule of an LBA fit, whole iterations per launch -----
     // GGDMC_B200_NO_PERSIST=1 keeps the multi-launch path (also used by the other schedules, per-parameter sweeps and the DDM).
-    bool persist = false, persist_planned = false;
+    bool persist = false, persist_planned = false, consts_travel = false;
     SamplerArgs SA{};
     int sampler_grid = 0, sampler_threads = 0, sampler_nacc = 0, sampler_max_batch = 64;
     size_t sampler_smem = 0;
-    DBuf<unsigned long long> sy_queue, sy_all_done, sy_trace;
-    DBuf<unsigned int> sy_exit, sy_pop_flags, sy_chain_arrive, sy_phi_arrive, sy_phi_done;
+    DBuf<unsigned long long> sy_all_done, sy_trace, sy_urgent;
+    DBuf<unsigned int> sy_close_list, sy_queue, sy_exit, sy_pop_flags, sy_chain_arrive, sy_phi_arrive, sy_phi_done;
     DBuf<int> sy_abort;
 
     template <int NACC>
@@ -1192,7 +1195,17 @@ struct ggdmc_engine {
     }
     cudaLaunchConfig_t sampler_cfg{};
 
-    static bool sampler_wanted() { return std::getenv("GGDMC_B200_NO_PERSIST") == nullptr; }
+    // The persistent kernel is the default where it is the faster path on B200 (profiles/r02_sampler.md): fits without a phi
+    // level (run_subject: a 3-replicate README fit takes 133 ms instead of 205 ms).  For a hierarchy the launch sequence
+    // still wins at every measured size -- its proposal / MH kernels hide their memory latency behind tens of thousands of
+    // warps, a persistent worker pays it item by item -- so there it is opt-in: GGDMC_B200_PERSIST=1.
+    // GGDMC_B200_NO_PERSIST=1 forces the launch sequence everywhere.
+    static bool sampler_wanted(bool hier)
+    {
+        if (std::getenv("GGDMC_B200_NO_PERSIST")) return false;
+        if (const char *e = std::getenv("GGDMC_B200_PERSIST")) return std::atoi(e) != 0;
+        return !hier;
+    }
     int sm_count() const
     {
         int n_sm = 148;
@@ -1256,8 +1269,17 @@ struct ggdmc_engine {
         // tables, small fits use smaller CTAs so that their few workers spread over all SMs
         const unsigned long long n_sub = (unsigned long long)npop * ((C + 1) / 2) * trials.d.nsplit;
         const unsigned long long n_phi = SA.hier ? (unsigned long long)R * C * H.nsplit : 0ull;
-        const unsigned long long n_accept = SA.hier ? (unsigned long long)npop * ((C + 31) / 32) : 0ull;
-        const unsigned long long per_iter = 2 * n_sub + 2 * n_phi + n_accept;
+        const unsigned long long per_iter = 2 * n_sub; // SUBJECT items; the phi level's items are published as they become runnable
+        require(per_iter < 0x7fffffffull && n_phi < 0xffffffull && (unsigned long long)npop * ((C + 31) / 32) < 0xffffffull, "too many work items per iteration");
+        SA.per_iter = (unsigned int)per_iter;
+        {   // urgent queues: a phi half 0 that may run; no CLOSE items
+            std::vector<unsigned long long> uq = {n_phi << 24, 0ull}; // batch 0 of the phi level with n_phi items (gg_sampler.cuh urgent_word)
+            sy_urgent.upload(uq);
+            sy_close_list.alloc((size_t)npop * ((C + 31) / 32));
+            sy_close_list.zero();
+            SA.y.urgent = sy_urgent.p;
+            SA.y.close_list = sy_close_list.p;
+        }
         const int n_sm = sm_count();
         int warps = 8;
         while (warps > 1 && per_iter < (unsigned long long)n_sm * 24 && per_iter < (unsigned long long)n_sm * warps * 3) warps >>= 1;
@@ -1277,14 +1299,13 @@ struct ggdmc_engine {
         }
         require(per_sm >= 1, "sampler kernel does not fit on an SM (row table too large)");
         per_sm = std::min(per_sm, 24 / warps);
-        sampler_grid = (int)std::min<unsigned long long>((unsigned long long)per_sm * n_sm, (per_iter + warps - 1) / warps);
-        sampler_segments(n_sub, n_phi, n_accept, (unsigned long long)sampler_grid * warps);
+        sampler_grid = (int)std::min<unsigned long long>((unsigned long long)per_sm * n_sm, (per_iter + 2 * n_phi + warps - 1) / warps);
         if (const char *e = std::getenv("GGDMC_B200_BATCH")) sampler_max_batch = std::max(1, std::atoi(e));
         if (const char *e = std::getenv("GGDMC_B200_ITEMTRACE")) { // diagnostics: stamps of the first items of every launch
             (void)e;
             unsigned long long cap = 400000;
             if (const char *c = std::getenv("GGDMC_B200_ITEMTRACE_CAP")) cap = std::strtoull(c, nullptr, 10);
-            sy_trace.alloc((size_t)cap * 8);
+            sy_trace.alloc((size_t)cap * 8 + 8); // + the counter of the urgent items' slots
             sy_trace.zero();
             CUDA_CHECK(cudaStreamSynchronize(0));
             SA.trace = sy_trace.p;
@@ -1293,6 +1314,7 @@ struct ggdmc_engine {
         // the migration decisions of iteration 1 (later ones are drawn inside the kernel at the end of the previous iteration),
         // and the constants of the subject prior under the start state of phi (later ones travel with accepted proposals)
         k_sweep_begin<<<npop, 128, (size_t)2 * C * sizeof(int), stream>>>(subj.L, d_iter.p, 0, SA.decide_once, -1);
+        k_flags_init<<<(npop + 127) / 128, 128, 0, stream>>>(subj.L, sy_pop_flags.p, kPopFlagStride);
         if (kind == 2) {
             k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), stream>>>(phi.L, d_iter.p, 0, 0, -1);
             phi_constants(stream);
@@ -1302,39 +1324,11 @@ struct ggdmc_engine {
         persist = true;
     }
 
-    // Queue order of one iteration (gg_sampler.cuh).  A fit with many waves of subject items per half-sweep gets its phi
-    // items early: after two waves of half 0 the previous iteration is certainly finished, one wave later so is phi's half
-    // 0, and so on -- nobody ever waits, and the rest of half 0 finds phi ready and takes its MH decisions on the spot.
-    void sampler_segments(unsigned long long n_sub, unsigned long long n_phi, unsigned long long n_accept, unsigned long long workers)
-    {
-        int n = 0;
-        auto seg = [&](int kind, int half, unsigned long long first, unsigned long long count) {
-            if (count == 0) return;
-            SA.seg_kind[n] = kind; SA.seg_half[n] = half; SA.seg_first[n] = first; SA.seg_count[n] = count;
-            ++n;
-        };
-        const bool early_phi = n_phi > 0 && n_sub >= 5 * workers && std::getenv("GGDMC_B200_NO_EARLY_PHI") == nullptr;
-        if (early_phi) {
-            const unsigned long long a = 2 * workers, b = workers;
-            seg(kItemSubject, 0, 0, a);
-            seg(kItemPhi, 0, 0, n_phi);
-            seg(kItemSubject, 0, a, b);
-            seg(kItemPhi, 1, 0, n_phi);
-            seg(kItemSubject, 0, a + b, n_sub - a - b);
-        } else {
-            seg(kItemSubject, 0, 0, n_sub);
-            seg(kItemPhi, 0, 0, n_phi);
-            seg(kItemPhi, 1, 0, n_phi);
-        }
-        seg(kItemAccept, 0, 0, n_accept);
-        seg(kItemSubject, 1, 0, n_sub);
-        SA.n_seg = n;
-        SA.per_iter = 2 * n_sub + 2 * n_phi + n_accept;
-    }
-
     // iterations [h_iter + 1, h_iter + n] in one launch
     void run_persist(int n)
     {
+        require((unsigned long long)n * SA.per_iter < 0xfff00000ull, "too many work items for one launch (lower GGDMC_B200_BATCH)");
+        if (SA.trace) CUDA_CHECK(cudaMemsetAsync(sy_trace.p, 0, ((size_t)SA.trace_cap * 8 + 8) * 8, stream));
         SA.t_begin = h_iter + 1;
         SA.t_end = h_iter + 1 + (uint32_t)n;
         sampler_cfg = cudaLaunchConfig_t{};
@@ -1382,7 +1376,7 @@ struct ggdmc_engine {
         CUDA_CHECK(cudaMemcpy(h.data(), sy_trace.p, h.size() * 8, cudaMemcpyDeviceToHost));
         if (FILE *f = std::fopen(path, "wb")) {
             const unsigned long long hdr[8] = {SA.trace_cap, (unsigned long long)R * S, (unsigned long long)((C + 1) / 2), (unsigned long long)trials.d.nsplit,
-                                               SA.hier ? (unsigned long long)R * C * H.nsplit : 0ull, (unsigned long long)sampler_grid, (unsigned long long)sampler_threads, SA.per_iter};
+                                               SA.hier ? (unsigned long long)R * C * H.nsplit : 0ull, (unsigned long long)sampler_grid, (unsigned long long)sampler_threads, (unsigned long long)SA.per_iter};
             std::fwrite(hdr, 8, 8, f);
             std::fwrite(h.data(), 8, h.size(), f);
             std::fclose(f);
@@ -1415,7 +1409,7 @@ struct ggdmc_engine {
                 for (int p = 0; p < D2; ++p) sweep_phi(p, 0, p, ps);
             else
                 sweep_phi(0, 0, -1, ps);
-            phi_constants(ps);
+            if (!consts_travel) phi_constants(ps);
             cudaEvent_t join = nullptr;
             if (conc) {
                 CUDA_CHECK(cudaEventRecord(ev_join, side));
@@ -1517,7 +1511,7 @@ struct ggdmc_engine {
         for (int i = 0; i < n_iter;) {
             if (persist) {
                 // whole iterations per launch: up to the next stored sample when results are streamed, else up to the batch limit
-                int n = std::min(n_iter - i, sampler_max_batch);
+                int n = std::min(n_iter - i, (int)std::min<unsigned long long>((unsigned long long)sampler_max_batch, std::max<unsigned long long>(1ull, 0xfff00000ull / SA.per_iter - 1)));
                 if (per_slot) n = std::min(n, thin - (int)(h_iter % (uint32_t)thin));
                 run_persist(n);
                 i += n;
@@ -1717,6 +1711,7 @@ int ggdmc_b200_engine_state(ggdmc_engine_t *engine, double *phi_theta, double *p
 }
 
 int64_t ggdmc_b200_engine_launch_count(const ggdmc_engine_t *engine) { return engine ? engine->launches : 0; }
+int32_t ggdmc_b200_engine_is_persistent(const ggdmc_engine_t *engine) { return engine && engine->persist ? 1 : 0; }
 
 int ggdmc_b200_engine_profile(ggdmc_engine_t *engine, int32_t enable, char err[256])
 {

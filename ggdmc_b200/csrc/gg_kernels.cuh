@@ -963,13 +963,14 @@ __device__ __forceinline__ void accept_warp(const Level &L, int p, int c_begin, 
 // from the other parity), so the chain can be overwritten at once.  lp_lane0: log prior of the proposal (lane 0) when the
 // prior is fixed; ll_lane0: its log-likelihood (lane 0) when there is one trial chunk.  scratch: D doubles of shared memory.
 __device__ __forceinline__ void accept_self(const Level &L, int p, int src, uint32_t iter, int sweep, const double *prop_sm, double lp_lane0,
-                                            const double *ll_part, int nsplit, double ll_lane0, double *scratch, int lane)
+                                            const double *ll_part, int nsplit, double ll_lane0, double *scratch, int lane, int tgt = -1)
 {
     const int C = L.nchain, D = L.npar;
+    if (tgt < 0) tgt = src;
     // every global load of the decision is issued up front: they travel together
     double cur = 0.0, tmp_ll = ll_lane0;
     if (lane == 0) {
-        cur = ldm(L.lp + p * C + src) + ldm(L.ll + p * C + src); // src/de.cpp:121 / :577
+        cur = ldm(L.lp + p * C + tgt) + ldm(L.ll + p * C + tgt); // src/de.cpp:121 / :189-190 / :577 / :656-657
         if (nsplit > 1) {
             const double *part = ll_part + ((size_t)p * C + src) * nsplit;
             tmp_ll = 0.0;
@@ -1007,26 +1008,30 @@ __device__ __forceinline__ void accept_self(const Level &L, int p, int src, uint
         }
     }
     if (__shfl_sync(0xffffffffu, acc, 0)) {
-        double *th = L.theta + ((size_t)p * C + src) * D;
+        double *th = L.theta + ((size_t)p * C + tgt) * D;
         for (int d = lane; d < D; d += 32) th[d] = prop_sm[d];
         if (lane == 0) {
-            L.lp[p * C + src] = tmp_lp;
-            L.ll[p * C + src] = tmp_ll;
+            L.lp[p * C + tgt] = tmp_lp;
+            L.ll[p * C + tgt] = tmp_ll;
         }
     }
 }
 
-__global__ void k_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *ll_part, int nsplit)
+// One WARP per pending proposal (lane = parameter for the log prior under phi and for the copy): the decision's loads are
+// one round trip wide instead of one per parameter.  Dynamic shared memory: (warps per block) x npar doubles.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *ll_part, int nsplit)
 {
-    const int C = L.nchain;
+    extern __shared__ double sm_acc[];
+    const int C = L.nchain, D = L.npar, lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int g = blockIdx.x * WARPS + wl;
     int p, src;
     if (step < 0) {
-        int g = blockIdx.x * blockDim.x + threadIdx.x;
         if (g >= L.npop * C) return;
         p = g / C;
         src = g - p * C;
     } else {
-        p = blockIdx.x * blockDim.x + threadIdx.x;
+        p = g;
         if (p >= L.npop) return;
         const int mode = L.mode[p];
         if (mode) {
@@ -1035,7 +1040,17 @@ __global__ void k_accept(Level L, const uint32_t *d_iter, int sweep, int step, c
         } else
             src = step;
     }
-    accept_one(L, p, src, *d_iter, sweep, ll_part, nsplit);
+    const int tgt = L.target[p * C + src];
+    if (tgt < 0) return;
+    const double *pr = L.prop + ((size_t)p * C + src) * D;
+    double *scratch = sm_acc + (size_t)wl * D;
+    double lp0 = 0.0, ll0 = 0.0;
+    if (lane == 0) {
+        L.target[p * C + src] = -1; // proposal consumed
+        if (!L.prior_ovr) lp0 = L.prop_lp[p * C + src];
+        if (nsplit == 1) ll0 = ll_part[(size_t)p * C + src];
+    }
+    accept_self(L, p, src, *d_iter, sweep, pr, lp0, ll_part, nsplit, ll0, scratch, lane, tgt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1122,14 +1137,36 @@ __device__ __forceinline__ void hyper_block(const HyperArgs &H, int r, int c, in
             ds[k] = e - si * D;
             xs[k] = e < n_el ? ldm(xbase + (size_t)(s_begin + si) * H.x_subj_stride + ds[k]) : 0.0;
         }
+        // log density of the truncated normal: regular arguments (finite, sd > 0, |z| far from overflow -- every element
+        // of an ordinary fit) take dnorm4's main line directly, so the eight divisions of a pass are independent
+        // instructions instead of eight branchy calls; anything else goes through dnorm4's full rules
+        double tc[4], tp[4];
+        bool slow = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int d = ds[k];
+            const double x = xs[k];
+            const double zc = (x - cm[d]) / cs[d], zp = has_prop ? (x - pm[d]) / ps[d] : 0.0;
+            tc[k] = -(kLnSqrt2Pi + 0.5 * zc * zc + cls[d]) - cl[d];
+            tp[k] = -(kLnSqrt2Pi + 0.5 * zp * zp + pls[d]) - pl[d];
+            const bool reg = H.like.dist[d] == 1 && H.like.log_p[d] != 0 && fabs(zc) < 1e150 && fabs(zp) < 1e150 && cs[d] > 0.0 && cs[d] < 1e300 &&
+                             (!has_prop || (ps[d] > 0.0 && ps[d] < 1e300));
+            slow = slow || (!reg && e0 + k * BLOCK < n_el);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (e0 + k * BLOCK >= n_el) break;
             const int d = ds[k];
             const double x = xs[k];
+            const double lo = H.like.lower[d], up = H.like.upper[d];
+            if (!slow) {
+                const bool outside = (x < lo) || (x > up);
+                if (H.need_cur) sum_c += outside ? -INFINITY : tc[k];
+                if (has_prop) sum_p += outside ? -INFINITY : tp[k];
+                continue;
+            }
             const int dist = H.like.dist[d];
             const bool lg = H.like.log_p[d] != 0;
-            const double lo = H.like.lower[d], up = H.like.upper[d];
             if (dist == 1 && lg) { // TNORM, log scale: the hierarchical fits of the reference
                 const bool outside = (x < lo) || (x > up);
                 if (H.need_cur) sum_c += outside ? -INFINITY : dnorm4_log_pre(x, cm[d], cs[d], cls[d]) - cl[d];
@@ -1223,6 +1260,28 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
+// sum of the nsplit partial sums of one value, in index order (bit-reproducible), eight loads in flight at a time: the
+// caller sits on the critical path of the phi step and every load is an L2 round trip
+__device__ __forceinline__ double sum_partials(const double *hp, int nsplit)
+{
+    double v = 0.0;
+    int q = 0;
+    for (; q + 8 <= nsplit; q += 8) {
+        double x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = ldm(hp + q + k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += x[k];
+    }
+    for (; q + 2 <= nsplit; q += 2) {
+        const double a = ldm(hp + q), b = ldm(hp + q + 1);
+        v += a;
+        v += b;
+    }
+    if (q < nsplit) v += ldm(hp + q);
+    return v;
+}
+
 // group-wide: reduce the nsplit partials of every value, exchange with the peers, leave the all-rank sums in hsum
 template <int G = 0>
 __device__ __forceinline__ bool reduce_exchange_block(const double *hpart, int n, int nsplit, double *hsum, const P2PWindow &w)
@@ -1231,8 +1290,7 @@ __device__ __forceinline__ bool reduce_exchange_block(const double *hpart, int n
     const unsigned long long seq = ldm(w.seq) + 1;
     const int b = (int)(seq & 1ull);
     for (int i = tid; i < n; i += nthr) {
-        double v = 0.0;
-        for (int k = 0; k < nsplit; ++k) v += *(volatile const double *)(hpart + (size_t)i * nsplit + k);
+        const double v = sum_partials(hpart + (size_t)i * nsplit, nsplit);
         for (int q = 0; q < w.n_rank; ++q) w.slots[q][((size_t)b * w.n_rank + w.rank) * kP2PMaxN + i] = v;
     }
     __threadfence_system();
@@ -1426,9 +1484,12 @@ __device__ __forceinline__ int phi_half_part(const Level &L, const HyperArgs &H,
         }
     }
     Grp<BLOCK>::sync();
-    double vc, vp;
-    hyper_block<BLOCK>(H, r, c, split, L.theta + ((size_t)r * C + c) * D2, sprop, k >= 0, true, sm_h, vc, vp,
-                       (H.prop_consts && split == 0) ? H.prop_consts + ((size_t)r * C + c) * D2 : nullptr);
+    double vc = 0.0, vp = 0.0;
+    // A chain that does not propose in this half is nobody's target either (crossover: target = source; migration: the
+    // targets are the proposing set), so neither of its two sums is ever read.
+    if (k >= 0)
+        hyper_block<BLOCK>(H, r, c, split, L.theta + ((size_t)r * C + c) * D2, sprop, true, true, sm_h, vc, vp,
+                           (H.prop_consts && split == 0) ? H.prop_consts + ((size_t)r * C + c) * D2 : nullptr);
     if (tid == 0) {
         double *o = hpart + (((size_t)r * C + c) * 2) * H.nsplit + split;
         o[0] = vc;
@@ -1448,17 +1509,7 @@ __device__ __forceinline__ bool phi_half_finish(const Level &L, const HyperArgs 
     if (use_p2p) {
         if (!reduce_exchange_block<BLOCK>(hpart, n, H.nsplit, hsum, w)) return false;
     } else {
-        for (int i = tid; i < n; i += BLOCK) {
-            const double *hp = hpart + (size_t)i * H.nsplit;
-            double v = 0.0;
-            int q = 0;
-            for (; q + 4 <= H.nsplit; q += 4) { // same order of additions, four loads in flight
-                const double a = ldm(hp + q), b = ldm(hp + q + 1), c = ldm(hp + q + 2), e = ldm(hp + q + 3);
-                v += a; v += b; v += c; v += e;
-            }
-            for (; q < H.nsplit; ++q) v += ldm(hp + q);
-            hsum[i] = v;
-        }
+        for (int i = tid; i < n; i += BLOCK) hsum[i] = sum_partials(hpart + (size_t)i * H.nsplit, H.nsplit);
     }
     __threadfence();
     Grp<BLOCK>::sync();
@@ -1534,6 +1585,14 @@ __global__ void k_store_advance(Level A, Level Bv, int has_b, uint32_t *d_iter, 
 }
 
 __global__ void k_iter_advance(uint32_t *d_iter) { *d_iter += 1; }
+// the sweep decisions of a level into the persistent kernel's per-population flag lines (words 2 and 3 of `stride` ints)
+__global__ void k_flags_init(Level L, unsigned int *flags, int stride)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= L.npop) return;
+    flags[(size_t)p * stride + 2] = (unsigned int)L.mode[p];
+    flags[(size_t)p * stride + 3] = L.mode[p] == 1 ? (unsigned int)L.mig_n[p] : 0u;
+}
 __global__ void k_stamp(unsigned long long *t) { *t = BlockTrace::now(); }
 
 // ------------------------------------------------------------------------------------------------

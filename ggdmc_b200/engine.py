@@ -419,6 +419,11 @@ class Engine:
         return int(n.value), float(ms.value), int(k.value)
 
     @property
+    def persistent(self) -> bool:
+        """True when the iterations run inside the persistent sampler kernel (whole iterations per launch)."""
+        return bool(B.lib().ggdmc_b200_engine_is_persistent(self.h))
+
+    @property
     def launch_count(self) -> int:
         return int(B.lib().ggdmc_b200_engine_launch_count(self.h))
 

@@ -14,6 +14,8 @@
 //
 // [[Rcpp::depends(Rcpp)]]
 #include <Rcpp.h>
+#include <climits>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -60,18 +62,22 @@ FlatModel flatten_model(const Rcpp::S4 &dmi)
         for (int j = 0; j < n_acc; ++j) {
             const int acc = n1(c, j);
             for (int r = 0; r < rows; ++r) {
-                int found = -1;
+                int found = -1, n_found = 0;
                 for (int k = 0; k < n_pxc; ++k) {
                     const std::string core = pxc[k].substr(0, pxc[k].find('.'));
-                    if (core == kCore[r] && mb[c + n_cell * (k + (size_t)n_pxc * acc)]) found = k;
+                    if (core == kCore[r] && mb[c + n_cell * (k + (size_t)n_pxc * acc)]) { found = k; ++n_found; }
                 }
-                if (found < 0) Rcpp::stop("model_boolean has no source for a core parameter");
-                int src = -1;
+                // exactly one parameter_x_condition column feeds a (cell, accumulator, core parameter)
+                if (n_found != 1)
+                    Rcpp::stop(n_found ? "model_boolean has more than one source for a core parameter" : "model_boolean has no source for a core parameter");
+                const int kNotFound = INT32_MIN;
+                int src = kNotFound; // >= 0: free parameter, < 0: constant -1 - index
                 for (size_t q = 0; q < m.pnames.size(); ++q)
                     if (m.pnames[q] == pxc[found]) src = (int)q;
-                if (src < 0)
+                if (src == kNotFound)
                     for (size_t q = 0; q < cnames.size(); ++q)
                         if (cnames[q] == pxc[found]) src = -1 - (int)q;
+                if (src == kNotFound) Rcpp::stop("parameter '" + pxc[found] + "' is neither a free parameter (pnames) nor a constant");
                 m.param_src[((size_t)c * rows + r) * n_acc + j] = src;
             }
         }
@@ -83,6 +89,16 @@ FlatModel flatten_model(const Rcpp::S4 &dmi)
     m.c.n_acc = n_acc; m.c.n_cell = n_cell; m.c.npar = (int)m.pnames.size(); m.c.n_const = (int)m.const_val.size();
     m.c.param_src = m.param_src.data(); m.c.const_val = m.const_val.data(); m.c.posdrift = m.posdrift.data();
     return m;
+}
+
+// The ABI takes ONE model for all subjects of a call (true of every script of the reference, which builds every dmi from
+// the same `model` object; src/de2R.cpp:129 would allow one likelihood object per dmi): refuse anything else loudly.
+void require_same_model(const FlatModel &first, const Rcpp::S4 &dmi, int subject)
+{
+    const FlatModel other = flatten_model(dmi);
+    if (other.c.type != first.c.type || other.param_src != first.param_src || other.const_val != first.const_val ||
+        other.posdrift != first.posdrift || other.pnames != first.pnames || other.cell_names != first.cell_names)
+        Rcpp::stop("all subjects of one call must share one model (subject " + std::to_string(subject + 1) + " differs from subject 1)");
 }
 
 struct FlatTrials {
@@ -127,6 +143,18 @@ struct FlatPrior {
     }
 };
 
+// options(ggdmc.schedule = "reference" | "parallel" | "simultaneous"); unset = the two-half parallel schedule
+int schedule_option()
+{
+    Rcpp::Environment base = Rcpp::Environment::base_env();
+    Rcpp::Function get_option = base["getOption"];
+    const std::string v = Rcpp::as<std::string>(get_option("ggdmc.schedule", "parallel"));
+    if (v == "reference") return GGDMC_SCHEDULE_REFERENCE;
+    if (v == "simultaneous") return GGDMC_SCHEDULE_SIMULTANEOUS;
+    if (v != "parallel") Rcpp::stop("options(ggdmc.schedule) must be \"parallel\", \"reference\" or \"simultaneous\"");
+    return GGDMC_SCHEDULE_PARALLEL;
+}
+
 struct FlatConfig {
     std::vector<uint64_t> seeds; // one Philox key per replicate
     ggdmc_config_t c{};
@@ -150,7 +178,7 @@ struct FlatConfig {
         c.gamma_precursor = de.slot("gamma_precursor"); c.rp = de.slot("rp");
         c.is_hblocked = Rcpp::as<bool>(de.slot("is_hblocked")); c.is_pblocked = Rcpp::as<bool>(de.slot("is_pblocked"));
         c.nparameter = de.slot("nparameter");
-        c.schedule = GGDMC_SCHEDULE_PARALLEL; // options(ggdmc.schedule = "reference") could select the other
+        c.schedule = schedule_option();
         c.n_replicate = 1; c.device = -1;
         seeds.push_back((uint64_t)Rcpp::as<double>(config_r.slot("seed"))); // config@seed -> Philox key (R/model-class.R:1514-1515)
         c.seed = seeds.data();
@@ -170,11 +198,12 @@ struct StartState {
         Rcpp::IntegerVector d = th.attr("dim");
         const size_t npar = d[0], nchain = d[1], nmc = d[2], blk = npar * nchain;
         size_t s = nmc;
-        while (s-- > 0) {
-            bool ok = true;
-            for (size_t i = 0; i < blk && ok; ++i) ok = R_finite(th[s * blk + i]);
-            if (ok) break;
+        bool found = false;
+        while (!found && s-- > 0) {
+            found = true;
+            for (size_t i = 0; i < blk && found; ++i) found = R_finite(th[s * blk + i]);
         }
+        if (!found) Rcpp::stop("samples has no slice with finite thetas");
         Rcpp::NumericMatrix lpm = samples.slot("summed_log_prior"), llm = samples.slot("log_likelihoods");
         theta.insert(theta.end(), th.begin() + s * blk, th.begin() + (s + 1) * blk); // npar x nchain col-major == [nchain][npar]
         for (size_t k = 0; k < nchain; ++k) { lp.push_back(lpm(k, s)); ll.push_back(llm(k, s)); }
@@ -253,7 +282,10 @@ Rcpp::List run(const Rcpp::S4 &config_r, const Rcpp::List &dmis, const Rcpp::Lis
     const int S = dmis.size();
     FlatModel m = flatten_model(Rcpp::as<Rcpp::S4>(dmis[0]));
     FlatTrials t;
-    for (int s = 0; s < S; ++s) t.add(Rcpp::as<Rcpp::S4>(dmis[s]), m.cell_names);
+    for (int s = 0; s < S; ++s) {
+        if (s > 0) require_same_model(m, Rcpp::as<Rcpp::S4>(dmis[s]), s);
+        t.add(Rcpp::as<Rcpp::S4>(dmis[s]), m.cell_names);
+    }
     t.finish();
     FlatConfig cfg(config_r);
     Rcpp::List subj_r = samples["subject_theta"];
@@ -319,7 +351,10 @@ Rcpp::List run_batch(const Rcpp::List &configs, const Rcpp::List &dmis, const Rc
     FlatPrior pp(priors.slot("p_prior")), hp(priors.slot("h_prior"));
     FlatModel m = flatten_model(Rcpp::as<Rcpp::S4>(dmis[0]));
     FlatTrials t;
-    for (int s = 0; s < S; ++s) t.add(Rcpp::as<Rcpp::S4>(dmis[s]), m.cell_names);
+    for (int s = 0; s < S; ++s) {
+        if (s > 0) require_same_model(m, Rcpp::as<Rcpp::S4>(dmis[s]), s);
+        t.add(Rcpp::as<Rcpp::S4>(dmis[s]), m.cell_names);
+    }
     t.finish();
     FlatConfig cfg(configs);
     std::vector<StartState> starts(S);
@@ -369,7 +404,10 @@ Rcpp::NumericMatrix sumloglike_init_batch(const Rcpp::List &dmis, const Rcpp::Nu
     const int S = dmis.size();
     FlatModel m = flatten_model(Rcpp::as<Rcpp::S4>(dmis[0]));
     FlatTrials t;
-    for (int s = 0; s < S; ++s) t.add(Rcpp::as<Rcpp::S4>(dmis[s]), m.cell_names);
+    for (int s = 0; s < S; ++s) {
+        if (s > 0) require_same_model(m, Rcpp::as<Rcpp::S4>(dmis[s]), s);
+        t.add(Rcpp::as<Rcpp::S4>(dmis[s]), m.cell_names);
+    }
     t.finish();
     Rcpp::IntegerVector d = theta.attr("dim");
     if (d.size() != 3 || d[0] != m.c.npar || d[2] != S) Rcpp::stop("theta must be npar x n_candidate x n_subject");

@@ -240,6 +240,10 @@ int ggdmc_b200_engine_counters(ggdmc_engine_t *engine, int64_t *trial_lik, doubl
                                char err[256]);
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int64_t ggdmc_b200_engine_launch_count(const ggdmc_engine_t *engine);
+/* 1: the engine's iterations run inside the persistent sampler kernel (the PARALLEL schedule of an LBA fit without
+ * per-parameter sweeps; whole iterations per launch), 0: as a sequence of launches per iteration.  With profiling on,
+ * ggdmc_b200_engine_counters then reports the launches of that kernel instead of the likelihood kernel's. */
+int32_t ggdmc_b200_engine_is_persistent(const ggdmc_engine_t *engine);
 void ggdmc_b200_engine_destroy(ggdmc_engine_t *engine);
 
 /* ---- multi-GPU (one process per GPU; subjects sharded; phi replicated) ---------------------- */

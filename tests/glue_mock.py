@@ -36,6 +36,7 @@ def lib():
                             ("gh_list_set", None, [vp, C.c_long, vp]), ("gh_get_attr", vp, [vp, C.c_char_p]), ("gh_list_get", vp, [vp, C.c_long]),
                             ("gh_length", C.c_long, [vp]), ("gh_kind", C.c_int, [vp]), ("gh_real_ptr", C.POINTER(C.c_double), [vp]),
                             ("gh_int_ptr", C.POINTER(C.c_int), [vp]), ("gh_str_at", C.c_char_p, [vp, C.c_long]), ("gh_last_error", C.c_char_p, []),
+                            ("gh_set_option", None, [C.c_char_p, C.c_char_p]), ("gh_schedule_option", C.c_int, []),
                             ("gh_run_subject", vp, [vp, vp, vp]), ("gh_run_hyper", vp, [vp, vp, vp]), ("gh_run", vp, [vp, vp, vp]),
                             ("gh_run_subject_batch", vp, [vp, vp, vp]), ("gh_run_batch", vp, [vp, vp, vp]),
                             ("gh_sumloglike_init_batch", vp, [vp, vp]), ("gh_sumlogprior_batch", vp, [vp, vp, vp, vp]),

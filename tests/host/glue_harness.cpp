@@ -38,6 +38,15 @@ const double *gh_real_ptr(void *o) { return static_cast<RObject *>(o)->p->real.d
 const int *gh_int_ptr(void *o) { return static_cast<RObject *>(o)->p->ints.data(); }
 const char *gh_str_at(void *o, long i) { return static_cast<RObject *>(o)->p->str.at((size_t)i).c_str(); }
 const char *gh_last_error() { return g_err.c_str(); }
+void gh_set_option(const char *name, const char *value) // options(name = value); value == NULL removes it
+{
+    if (value) Rcpp::mock_options()[name] = value;
+    else Rcpp::mock_options().erase(name);
+}
+int gh_schedule_option() // what FlatConfig would put into ggdmc_config_t::schedule; -1 + gh_last_error() on error
+{
+    try { return schedule_option(); } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
 
 // the glue's entry points (R: .Call('_ggdmc_run_subject' | '_ggdmc_run_hyper' | '_ggdmc_run', ...)); null + gh_last_error() on error
 void *gh_run_subject(void *config, void *dmi, void *samples)

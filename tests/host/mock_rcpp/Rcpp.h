@@ -232,4 +232,28 @@ public:
     }
 };
 
+// options() of the mock R session (tests set them through the harness); getOption(name, default) is the one R function
+// the glue calls
+inline std::map<std::string, std::string> &mock_options()
+{
+    static std::map<std::string, std::string> o;
+    return o;
+}
+class Function {
+    std::string fn;
+public:
+    Function(const RObject &o) : fn(as<std::string>(o)) {}
+    RObject operator()(const char *name, const char *dflt) const
+    {
+        if (fn != "getOption") stop("the Rcpp stand-in only knows getOption()");
+        auto it = mock_options().find(name);
+        return RObject(std::vector<std::string>{it == mock_options().end() ? std::string(dflt) : it->second});
+    }
+};
+class Environment {
+public:
+    static Environment base_env() { return Environment(); }
+    RObject operator[](const char *name) const { return RObject(std::vector<std::string>{name}); }
+};
+
 } // namespace Rcpp

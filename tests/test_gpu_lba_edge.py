@@ -15,7 +15,7 @@ from oracle import binding as ob
 from helpers import GOLDEN, load_fixture, sane_starts
 import lba_edge
 from test_lba_edge_cpu import LOOSE, _close
-from test_gpu_sampler import SCHEDULES, compare
+from test_gpu_sampler import SCHEDULES, compare, kernel_path  # noqa: F401  (kernel_path: autouse fixture, both kernel paths)
 
 pytestmark = pytest.mark.gpu
 G = dict(np.load(os.path.join(GOLDEN, "lba_edge_ref.npz")))

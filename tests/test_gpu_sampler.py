@@ -18,6 +18,20 @@ pytestmark = pytest.mark.gpu
 SCHEDULES = [(B.SCHEDULE_PARALLEL, 1), (B.SCHEDULE_REFERENCE, 0), (B.SCHEDULE_SIMULTANEOUS, 2)]  # (engine schedule, oracle schedule)
 
 
+@pytest.fixture(autouse=True, params=["default", "persistent", "launches"])
+def kernel_path(request, monkeypatch):
+    """Every test of this module runs three times: with the engine's own choice between the persistent sampler kernel and
+    the launch sequence (persistent for fits without a phi level), with the persistent kernel forced wherever it applies
+    (the PARALLEL schedule of an LBA fit without per-parameter sweeps), and with the launch sequence forced."""
+    monkeypatch.delenv("GGDMC_B200_PERSIST", raising=False)
+    monkeypatch.delenv("GGDMC_B200_NO_PERSIST", raising=False)
+    if request.param == "persistent":
+        monkeypatch.setenv("GGDMC_B200_PERSIST", "1")
+    elif request.param == "launches":
+        monkeypatch.setenv("GGDMC_B200_NO_PERSIST", "1")
+    return request.param
+
+
 def subject_start(fx, od, oprior, nchain, rng, center=None, phi=None):
     th = sane_starts(fx, nchain, rng, center=center)
     D = th.shape[1]

@@ -30,13 +30,15 @@ if sys.argv[1] == "run":  # run <workload> <iterations per launch> <file> [subje
 
 raw = np.fromfile(sys.argv[1], dtype=np.uint64)
 cap, npop, nslot, nsplit, n_phi, grid, threads, per_iter = (int(x) for x in raw[:8])
-rec = raw[8:].reshape(-1, 8)
+rec = raw[8:8 + 8 * cap].reshape(-1, 8)
 rec = rec[rec[:, 0] > 0]
-kind = rec[:, 7].astype(int)
+kind = (rec[:, 7] & np.uint64(0xff)).astype(int)
+it = (rec[:, 7] >> np.uint64(8)).astype(np.int64)
+it -= it.min()
 warp_slot = (rec[:, 6] >> np.uint64(16)) & np.uint64(0xffff)
 rec[:, 6] &= np.uint64(0xffff)
 t0 = rec[:, 0].min()
-names = {0: "SUBJECT h0", 1: "SUBJECT h1", 2: "PHI h0", 3: "PHI h1", 4: "ACCEPT"}
+names = {0: "SUBJECT h0", 1: "SUBJECT h1", 2: "PHI h0", 3: "PHI h1", 4: "CLOSE"}
 print(f"{len(rec)} items traced (cap {cap}); {npop} populations x {nslot} slots x {nsplit} chunks; {n_phi} phi items per half; "
       f"grid {grid} x {threads} threads = {grid * threads // 32} workers")
 end = rec[:, 5].astype(np.int64)
@@ -56,8 +58,8 @@ for k in sorted(names):
         continue
     r = r.astype(np.int64)
     print(f"--- {names[k]}: {len(r)} items, first taken at {(r[:, 0].min() - int(t0)) / 1e3:.1f} us, last finished at {(r[:, 5].max() - int(t0)) / 1e3:.1f} us")
-    print(f"    wait for dependency : {us(r[:, 1] - r[:, 0])}")
     if k < 2:
+        print(f"    wait for dependency : {us(r[:, 1] - r[:, 0])}")
         ok = r[:, 2] > 0
         rr = r[ok]
         if len(rr):
@@ -73,20 +75,13 @@ for k in sorted(names):
     else:
         print(f"    MH decisions        : {us(r[:, 5] - r[:, 1])}")
         busy += float((r[:, 5] - r[:, 1]).sum())
-    print(f"    whole item          : {us(r[:, 5] - r[:, 0])}")
 workers = grid * threads // 32
-print(f"worker time not spent waiting: {busy / 1e3:.0f} us = {100 * busy / 1e3 / (span * workers):.1f} % of {workers} workers x span")
-# per-iteration boundaries: the iteration of an item = its index // items per iteration
-idx = np.nonzero(raw[8:].reshape(-1, 8)[:, 0] > 0)[0]
-it = idx // per_iter
-for i in np.unique(it)[:6]:
-    m = it == i
-    print(f"iteration +{i}: first item taken at {(rec[m, 0].min() - t0) / 1e3:8.1f} us, last item finished at {(rec[m, 5].max() - t0) / 1e3:8.1f} us")
+print(f"worker time in items (waits excluded): {busy / 1e3:.0f} us = {100 * busy / 1e3 / (span * workers):.1f} % of {workers} workers x span")
 for i in np.unique(it)[1:3]:
     m = it == i
     for k in sorted(names):
         mk = m & (kind == k)
         if mk.any():
             r = rec[mk].astype(np.int64)
-            print(f"   iteration +{i} {names[k]:11s}: dependency met {(r[:, 1].min() - int(t0)) / 1e3:8.1f} .. {(r[:, 1].max() - int(t0)) / 1e3:8.1f} us, finished "
+            print(f"   iteration +{i} {names[k]:11s}: {mk.sum():6d} items, started {(r[:, 1].min() - int(t0)) / 1e3:8.1f} .. {(r[:, 1].max() - int(t0)) / 1e3:8.1f} us, finished "
                   f"{(r[:, 5].min() - int(t0)) / 1e3:8.1f} .. {(r[:, 5].max() - int(t0)) / 1e3:8.1f} us")
