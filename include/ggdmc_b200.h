@@ -249,7 +249,17 @@ void ggdmc_b200_engine_destroy(ggdmc_engine_t *engine);
 /* ---- multi-GPU (one process per GPU; subjects sharded; phi replicated) ---------------------- */
 
 /* NCCL bootstrap: rank 0 calls get_unique_id, the bytes travel by any out-of-band channel
- * (bench.py uses torch.distributed), every rank calls comm_init before creating engines. */
+ * (bench.py uses torch.distributed), every rank calls comm_init before creating engines.
+ *
+ * Lock step.  A sharded fit exchanges the phi-level sums once per phi half-sweep through a peer-memory window (or
+ * ncclAllReduce with GGDMC_B200_NO_P2P=1), so every rank must create its engine and call run / iterate with the same
+ * configuration and the same number of iterations.  The ranks do NOT have to arrive at the same time: the end of
+ * engine creation and the start of every run / iterate call are peer barriers, and inside an exchange a rank waits up
+ * to GGDMC_B200_PEER_TIMEOUT_S seconds (default 120) for its peers.  If a peer never arrives, the waiting rank takes
+ * no MH decision on the incomplete sums, its call returns GGDMC_ERR_COMM ("peer exchange timed out"), and the
+ * communicator stays in that error state -- every later engine creation fails with GGDMC_ERR_COMM -- until
+ * ggdmc_b200_comm_finalize() and a new ggdmc_b200_comm_init().  One communicator per process: sharded fits of one
+ * process run one after the other. */
 int ggdmc_b200_comm_unique_id(uint8_t id[128], char err[256]);
 int ggdmc_b200_comm_init(int32_t n_rank, int32_t rank, const uint8_t id[128], int32_t device, char err[256]);
 void ggdmc_b200_comm_finalize(void);

@@ -185,3 +185,35 @@ def test_rcpp_glue_scores_start_value_candidates_in_bulk():
     lp2 = G.sumlogprior_batch(api.prior_list(pp), x.T, phi[:, :D].T, phi[:, D:].T)
     assert np.array_equal(lp2, E.sumlogprior(pp, x, np.ascontiguousarray(phi[:, :D]), np.ascontiguousarray(phi[:, D:])))
 
+
+
+def test_restart_with_changed_nmc_and_thin():
+    """RestartSampling_subject with a different nmc / thin (R/sampling.R:370-421 builds a new theta_input and passes the
+    previous fit as `samples`): through the Rcpp glue and through the Python mirror the continuation starts at the
+    previous fit's last slice, has the NEW nmc / thin, and is what the oracle produces from that state with the same seed
+    (the reference's theta_class constructor is not in de.o; that it starts from the last stored sample is what
+    R/sampling.R:426-429 relies on when it binds old and new samples together)."""
+    import glue_mock as G
+    from test_gpu_sampler import compare
+    fx, model, dmi_of = fixture_objects(2)
+    dmi = dmi_of("sub")
+    D, nchain = fx.ct.npar, 3 * fx.ct.npar
+    prior = api.Prior(nparameter=D, pnames=fx.ct.pnames, p_prior=api.prior_list(fx.prior("sub_prior")))
+    de = api.DEInput(sub_migration_prob=0.1, nparameter=D, nchain=nchain)
+    ti1 = api.ThetaInput(nmc=5, nchain=nchain, thin=2, nparameter=D, pnames=fx.ct.pnames)
+    first = api.run_subject(api.Config(prior=prior, theta_input=ti1, de_input=de, seed=11), dmi, init.initialise_theta(ti1, prior, dmi, seed=4))
+    ti2 = api.ThetaInput(nmc=8, nchain=nchain, thin=3, nparameter=D, pnames=fx.ct.pnames)
+    cfg2 = api.Config(prior=prior, theta_input=ti2, de_input=de, seed=12)
+    again_py = api.run_subject(cfg2, dmi, first)
+    again_r = G.run_subject(cfg2, dmi, first)
+    for again in (again_py, again_r):
+        assert again.theta.shape == (D, nchain, 8) and again.nmc == 8 and again.thin == 3
+        assert np.array_equal(again.theta[:, :, 0], first.theta[:, :, -1])
+        assert np.array_equal(again.log_likelihoods[:, 0], first.log_likelihoods[:, -1])
+    assert np.array_equal(again_py.theta, again_r.theta)
+    # the oracle from the same state: 7 x 3 iterations of run_chains in the engine's default (two-half) order
+    pop = ob.OPop(np.ascontiguousarray(first.theta[:, :, -1].T), first.summed_log_prior[:, -1].copy(), first.log_likelihoods[:, -1].copy(), 8, 3)
+    de_o = ob.make_de(D, nchain, sub_migration_prob=0.1, jacobi=1)
+    ob.run_subject(de_o, pop, fx.oprior("sub_prior"), fx.om, fx.odata("sub"), ob.make_rng(seed=12), 0, 7 * 3)
+    gpu = E.PopSamples(np.ascontiguousarray(again_py.theta.transpose(2, 1, 0))[None], again_py.summed_log_prior.T[None].copy(), again_py.log_likelihoods.T[None].copy())
+    compare(gpu, 0, pop, "restarted fit")
