@@ -1433,7 +1433,7 @@ struct ggdmc_engine {
     }
 
     // iteration() either as plain launches or as one graph launch
-    bool short_call = false; // a call of a few dozen iterations: capturing and instantiating the graph costs more than it saves
+    bool short_call = false; // a one-shot run* call of a few dozen iterations: capturing and instantiating the graph costs more than it saves
     void step_once()
     {
         if (!use_graph || profile || h_iter == 0 || (short_call && !graph_exec)) { // the very first iteration runs uncaptured (one-off kernel attribute calls)
@@ -1503,7 +1503,6 @@ struct ggdmc_engine {
     void iterate(int n_iter, float *elapsed_ms, ggdmc_progress_fn progress, void *user, int report_length)
     {
         CUDA_CHECK(cudaSetDevice(device));
-        short_call = n_iter < 48;
         peer_barrier(); // ranks that enter seconds apart (uploads, host work) meet here, not inside the first exchange
         CUDA_CHECK(cudaEventRecord(ev0, stream));
         const bool streaming = !sinks.empty();
@@ -1762,6 +1761,7 @@ int ggdmc_b200_run_subject(const ggdmc_model_t *model, const ggdmc_trials_t *tri
     ggdmc_engine e;
     e.create_lba(model, trials, p_prior, nullptr, cfg, nullptr, start);
     e.stream_results_to(e.subj, 1, out);
+    e.short_call = (cfg->nmc - 1) * cfg->thin < 48;
     e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length); // m_nsample - 1 iterations
     GG_CATCH
 }
@@ -1775,6 +1775,7 @@ int ggdmc_b200_run_hyper(const ggdmc_prior_t *p_prior, const ggdmc_prior_t *h_pr
     ggdmc_engine e;
     e.create_hyper(p_prior, h_prior, data_theta, n_subject, cfg, start);
     e.stream_results_to(e.phi, 1, out);
+    e.short_call = (cfg->nmc - 1) * cfg->thin < 48;
     e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length);
     GG_CATCH
 }
@@ -1793,6 +1794,7 @@ int ggdmc_b200_run(const ggdmc_model_t *model, const ggdmc_trials_t *trials, con
         pt.lap("create");
         e.stream_results_to(e.subj, e.S, subj_out);
         e.stream_results_to(e.phi, 1, phi_out);
+        e.short_call = (cfg->nmc - 1) * cfg->thin < 48;
         e.iterate((cfg->nmc - 1) * cfg->thin, nullptr, progress, user, cfg->report_length);
         pt.lap("iterate+download");
     }

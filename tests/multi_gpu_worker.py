@@ -22,7 +22,16 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
     S, ntr, n_iter = 10, 96, 12
-    for schedule in (B.SCHEDULE_PARALLEL, B.SCHEDULE_REFERENCE):
+    # (schedule, exchange path, kernel path): peer-memory window vs ncclAllReduce; launch sequence vs persistent sampler kernel
+    variants = [(B.SCHEDULE_PARALLEL, "p2p", "launches"), (B.SCHEDULE_REFERENCE, "p2p", "launches"), (B.SCHEDULE_PARALLEL, "nccl", "launches"),
+                (B.SCHEDULE_PARALLEL, "p2p", "persistent")]
+    for schedule, exchange, kernel in variants:
+        for k in ("GGDMC_B200_NO_P2P", "GGDMC_B200_PERSIST"):
+            os.environ.pop(k, None)
+        if exchange == "nccl":
+            os.environ["GGDMC_B200_NO_P2P"] = "1"
+        if kernel == "persistent":
+            os.environ["GGDMC_B200_PERSIST"] = "1"
         ref = None
         if rank == 0:  # the whole problem on one GPU, before any communicator exists
             w = W.hierarchical("t", 2, S, ntr, n_replicate=2)
@@ -57,7 +66,8 @@ def main():
                 assert np.array_equal(o["phi_theta"], out[0]["phi_theta"]) and np.array_equal(o["phi_ll"], out[0]["phi_ll"])
                 assert np.allclose(o["phi_ll"], ref["phi_ll"], rtol=1e-9, atol=0)
             assert not np.array_equal(ref["phi_theta"], w.phi_start.theta)
-            print(f"schedule {schedule}: {world}-GPU sharded run == single-GPU run ({S} subjects, {n_iter} iterations)", flush=True)
+            print(f"schedule {schedule}, exchange {exchange}, {kernel}: {world}-GPU sharded run == single-GPU run ({S} subjects, {n_iter} iterations, "
+                  f"theta bit-identical, phi identical on every rank)", flush=True)
         dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
