@@ -1184,7 +1184,7 @@ struct ggdmc_engine {
     template <int NACC>
     int sampler_blocks_per_sm()
     {
-        auto kern = k_sampler<NACC>;
+        auto kern = SA.hier ? k_sampler<NACC, true> : k_sampler<NACC, false>;
         allow_smem(kern, sampler_smem);
         int per_sm = 0;
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sampler_threads, sampler_smem));
@@ -1193,7 +1193,8 @@ struct ggdmc_engine {
     template <int NACC>
     void sampler_launch()
     {
-        CUDA_CHECK(cudaLaunchKernelEx(&sampler_cfg, k_sampler<NACC>, SA));
+        if (SA.hier) CUDA_CHECK(cudaLaunchKernelEx(&sampler_cfg, k_sampler<NACC, true>, SA));
+        else CUDA_CHECK(cudaLaunchKernelEx(&sampler_cfg, k_sampler<NACC, false>, SA));
     }
     cudaLaunchConfig_t sampler_cfg{};
 

@@ -222,7 +222,10 @@ __host__ __device__ inline size_t sampler_warp_bytes(int n_cell, int n_row, int 
 
 constexpr int kSamplerMaxThreads = 256; // a CTA is 1 .. 8 independent warps; 24 warps per SM at 80 registers
 
-template <int NACC>
+// HIER: the fit has a phi level.  A compile-time switch, not a field of the arguments: without a phi level none of the urgent-work code exists,
+// and the kernel of a run_subject fit is a third of the size -- its workers spend their time on short items spread over all
+// phases, so instruction fetch (ncu: stall_no_instruction) is what they wait for most after memory.
+template <int NACC, bool HIER>
 __global__ void __launch_bounds__(kSamplerMaxThreads, 3) k_sampler(SamplerArgs A)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(kSamplerMaxThreads, 3) k_sampler(SamplerArgs A
     int *ctl = reinterpret_cast<int *>(wsm + A.warp_bytes - 4 * sizeof(int)); // [4] scratch of sweep_begin_pop / phi_half_part
     int *sm_keys = reinterpret_cast<int *>(wsm);                               // [2 C], aliases the item's table
 
-    const unsigned int n_phi = A.hier ? (unsigned int)(P.npop * C * A.H.nsplit) : 0u; // PHI items of one half
+    const unsigned int n_phi = HIER ? (unsigned int)(P.npop * C * A.H.nsplit) : 0u; // PHI items of one half
     const int n_grp = (C + 31) / 32;                                                  // CLOSE items per population
     const unsigned int total = A.per_iter * (A.t_end - A.t_begin);
     const unsigned int per_pop_half = (unsigned int)(nslot * nsplit);
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(kSamplerMaxThreads, 3) k_sampler(SamplerArgs A
                 unsigned long long old;
                 asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;" : "=l"(old) : "l"(y.all_done) : "memory");
                 // the last population of the iteration: the next iteration's phi step can start
-                if (A.hier && old + 1 == (unsigned long long)S.npop * t && t + 1 < A.t_end) urgent_publish(y.urgent, 2 * (t + 1 - A.t_begin), n_phi);
+                if (HIER && old + 1 == (unsigned long long)S.npop * t && t + 1 < A.t_end) urgent_publish(y.urgent, 2 * (t + 1 - A.t_begin), n_phi);
             }
         }
     };
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(kSamplerMaxThreads, 3) k_sampler(SamplerArgs A
     ulonglong2 uq = make_ulonglong2(0ull, 0ull);
     bool have_uq = false;              // ... and a look at the urgent queues
     while (!dead) {
-        if (A.hier) {
+        if (HIER) {
             if (!have_uq) uq = peek_urgent();
             have_uq = false;
             if (serve_urgent(uq)) continue;
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(kSamplerMaxThreads, 3) k_sampler(SamplerArgs A
         }
         have_next = false;
         if (item >= total) {
-            if (!A.hier || item == 0xffffffffu) break;
+            if (!HIER || item == 0xffffffffu) break;
             // no SUBJECT items left: stay for the urgent work of the last iteration until every population has finished it
             int fin = 0;
             if (lane == 0) {
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(kSamplerMaxThreads, 3) k_sampler(SamplerArgs A
         uint4 f4 = make_uint4(0u, 0u, 0u, 0u);
         unsigned int phi_seen = 0;
         if (lane == 0) f4 = ld_flag_v4(pf);
-        else if (lane == 1 && A.hier) phi_seen = ld_flag_u32(y.phi_done);
+        else if (lane == 1 && HIER) phi_seen = ld_flag_u32(y.phi_done);
         if (!__shfl_sync(FULL, f4.x >= 2 * t + h, 0)) {
             // the population's previous half is still open: wait for it, and look for urgent work every eighth poll
             const unsigned long long since = globaltimer_ns();
@@ -490,15 +493,15 @@ __global__ void __launch_bounds__(kSamplerMaxThreads, 3) k_sampler(SamplerArgs A
                 st = __shfl_sync(FULL, st, 0);
                 if (st == 2) dead = true;
                 if (st) break;
-                if (A.hier && (poll & 7u) == 0u && serve_urgent(peek_urgent()) && dead) break;
+                if (HIER && (poll & 7u) == 0u && serve_urgent(peek_urgent()) && dead) break;
             }
             if (dead) break;
-            if (lane == 1 && A.hier) phi_seen = ld_flag_u32(y.phi_done);
+            if (lane == 1 && HIER) phi_seen = ld_flag_u32(y.phi_done);
         }
         if (tr) tr[1] = globaltimer_ns();
         const int mode = (int)__shfl_sync(FULL, f4.z, 0);
         const int nsteps = mode ? (int)__shfl_sync(FULL, f4.w, 0) : C;
-        const bool phi_ready = !A.hier || h == 1 || __shfl_sync(FULL, phi_seen, 1) >= 2 * t + 2;
+        const bool phi_ready = !HIER || h == 1 || __shfl_sync(FULL, phi_seen, 1) >= 2 * t + 2;
         double *sm_theta = reinterpret_cast<double *>(wsm + like_smem_bytes(M.n_row, M.n_cell, 32));
         double *sm_scratch = sm_theta + D;
         // sweep positions of this item: crossover -> chain 2 slot + h; migration (all of it in half 0) -> slot, slot + nslot
@@ -552,7 +555,7 @@ __global__ void __launch_bounds__(kSamplerMaxThreads, 3) k_sampler(SamplerArgs A
         unsigned int got = 0;
         if (lane < 2) got = atom_add_release_u32(lane == 0 ? pf + 1 : y.queue, 1u);
         ulonglong2 uq2 = make_ulonglong2(0ull, 0ull);
-        if (lane == 2 && A.hier) uq2 = ld_flag_v2u64(y.urgent);
+        if (lane == 2 && HIER) uq2 = ld_flag_v2u64(y.urgent);
         next_item = __shfl_sync(FULL, got, 1);
         if (*(volatile int *)y.abort) next_item = 0xffffffffu;
         have_next = true;
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(kSamplerMaxThreads, 3) k_sampler(SamplerArgs A
         uq.y = __shfl_sync(FULL, uq2.y, 2);
         have_uq = true;
         if (__shfl_sync(FULL, got, 0) == per_pop_half - 1) { // the population's half is complete
-            if (h == 1 || !A.hier) {
+            if (h == 1 || !HIER) {
                 if (mode != 0) { // migration: every decision of the sweep, now that every proposal is made
                     accept_warp(S, p, 0, C, t, 0, A.ll_part, nsplit, lane);
                     __syncwarp();
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__(kSamplerMaxThreads, 3) k_sampler(SamplerArgs A
         if (atom_add_release_u32(y.exit_ctr, 1u) == gridDim.x * (blockDim.x >> 5) - 1) {
             *y.exit_ctr = 0;
             *y.queue = 0u;
-            if (A.hier) {
+            if (HIER) {
                 y.urgent[0] = urgent_word(0u, n_phi); // the next launch starts with a phi half 0 that may run
                 y.urgent[1] = 0ull;
             }

@@ -3,7 +3,7 @@ from `ncu --csv --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
 Run on the GPU box (tools/ncu_profiles.sh does), then commit the JSON: bench.py quotes it as roofline.traffic together
 with the commit it was measured on (roofline.traffic_source).
 
-    python tools/ncu_traffic.py <commit> <workload>:<kernel>:<trial_lik_per_launch>:<csv> ...
+    python tools/ncu_traffic.py <commit> <workload>,<kernel>,<trial_lik_per_launch>,<csv> ...
 """
 import csv
 import json
@@ -15,7 +15,7 @@ out_path = os.path.join(ROOT, "profiles", "r02_traffic.json")
 commit = sys.argv[1]
 out = json.load(open(out_path)) if os.path.exists(out_path) else {}
 for spec in sys.argv[2:]:
-    workload, kernel, lik, path = spec.split(":", 3)
+    workload, kernel, lik, path = spec.split(",", 3)
     rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
     hdr = rows[0]
     i_name, i_metric, i_unit, i_val = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
