@@ -256,7 +256,7 @@ def committed_traffic(workload: str, kernel: str, lik_per_launch: float):
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         e = tj[workload][kernel]
         if abs(e["trial_lik_per_launch"] - lik_per_launch) < 0.03 * lik_per_launch:
-            return e["dram_bytes_per_launch"], f"profiles/r02_traffic.json: ncu --set full of commit {e.get('commit', '?')} ({e.get('command', '')}); this run is commit {git_head()}"
+            return e["dram_bytes_per_launch"], f"profiles/r02_traffic.json: ncu capture of commit {e.get('commit', '?')} ({e.get('command', '')}); this run is commit {git_head()}"
     except Exception:
         pass
     return None, "no committed ncu capture matches this workload / kernel / launch size"

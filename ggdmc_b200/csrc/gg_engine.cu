@@ -509,31 +509,33 @@ constexpr int kHyperBlock = 256;
 constexpr int kProposeWarps = 4;
 constexpr int kAcceptWarps = 4;
 
-// Launch shape of the likelihood kernel: (threads per block, minimum resident blocks per SM).
-// The default was picked by measurement on B200 (profiles/); GGDMC_B200_LIKE_VARIANT overrides it
-// for experiments.
-// variants: 0 (128, 6)  1 (128, 8)  2 (64, 12)  3 (64, 16)  4 (32, 24)  5 (32, 32)  6 (64, 10)  7 (64, 8)
-int like_variant()
-{
-    static int v = [] {
-        const char *e = std::getenv("GGDMC_B200_LIKE_VARIANT");
-        int x = e ? std::atoi(e) : 2;
-        return (x < 0 || x > 8) ? 2 : x;
-    }();
-    return v;
-}
+// Launch shape of the likelihood kernel: 64 threads per block, 12 resident blocks per SM (80 registers) -- picked by
+// measurement on B200 among (128, 6), (128, 8), (64, 8 / 10 / 12 / 16), (32, 24 / 32), (256, 3) in round 1
+// (profiles/r01_k_like.md); the other shapes are no longer compiled into the library.
+constexpr int kLikeBlock = 64, kLikeMinBlocks = 12;
 
 size_t like_smem(const DevModel &M, int block) { return like_smem_bytes(M.n_row, M.n_cell, block); }
 
-template <int NACC, int BLOCK, int MINB>
+// The trial loop reaches a cell's rows either directly -- the distinct rows are expanded into one row per (cell, accumulator)
+// after they are built -- or through the cell's row indices.  Expanded is one dependent shared-memory load shorter per
+// accumulator and trial (2 % of the launch on the README model); indexed keeps the table small (the 96-cell, 4-accumulator
+// model: 3 KB instead of 27 KB per block, 12 instead of 9 resident blocks).  Expanded while 12 blocks' tables stay below 64 KB.
+bool like_expand(const DevModel &M) { return (size_t)(M.n_row + M.n_cell * M.n_acc) * sizeof(CellAcc) * kLikeMinBlocks <= 64 * 1024; }
+size_t like_launch_smem(const DevModel &M, int block, bool expand)
+{
+    return like_smem(M, block) + (expand ? (size_t)M.n_cell * M.n_acc * sizeof(CellAcc) : (((size_t)M.n_cell * M.n_acc * sizeof(uint16_t) + 15) & ~(size_t)15));
+}
+
+template <int NACC, bool EXPAND>
 void launch_like_t(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
                    double *ll_part, cudaStream_t st, const int *prio)
 {
+    constexpr int BLOCK = kLikeBlock, MINB = kLikeMinBlocks;
     const int per_pop = step >= 0 ? 1 : (half < 0 ? L.nchain : (L.nchain + 1) / 2);
     dim3 grid(L.npop * per_pop, T.nsplit);
-    const size_t sm = like_smem(M, BLOCK);
+    const size_t sm = like_launch_smem(M, BLOCK, EXPAND);
     require(sm <= 220 * 1024, "cell table does not fit in shared memory");
-    allow_smem(k_like<NACC, BLOCK, MINB>, sm);
+    allow_smem(k_like<NACC, BLOCK, MINB, EXPAND>, sm);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = sm; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -541,29 +543,19 @@ void launch_like_t(const Level &L, const DevModel &M, const TrialData &T, const 
     at[0].val.priority = prio ? *prio : 0;
     cfg.attrs = at;
     cfg.numAttrs = prio ? 1 : 0;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_like<NACC, BLOCK, MINB>, L, M, T, d_iter, sweep, step, half, ll_part));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_like<NACC, BLOCK, MINB, EXPAND>, L, M, T, d_iter, sweep, step, half, ll_part));
 }
 
 template <int NACC>
 void launch_like_n(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
                    double *ll_part, cudaStream_t st, const int *prio)
 {
-    switch (like_variant()) {
-    case 0: launch_like_t<NACC, 128, 6>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 2: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 3: launch_like_t<NACC, 64, 16>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 1: launch_like_t<NACC, 128, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 4: launch_like_t<NACC, 32, 24>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 5: launch_like_t<NACC, 32, 32>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 6: launch_like_t<NACC, 64, 10>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 7: launch_like_t<NACC, 64, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 8: launch_like_t<NACC, 256, 3>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    default: launch_like_t<NACC, 64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio);
-    }
+    if (like_expand(M)) launch_like_t<NACC, true>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio);
+    else launch_like_t<NACC, false>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio);
 }
 
 // model type "fastdm": same grid and arguments as k_like.  Launch shape (threads per block, minimum resident blocks per
-// SM) picked by measurement (profiles/r01_k_like_ddm.md); GGDMC_B200_DDM_VARIANT overrides it for experiments.
+// SM) picked by measurement (profiles/r01_k_like_ddm.md).
 template <int BLOCK, int MINB>
 void launch_like_ddm_t(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
                        double *ll_part, cudaStream_t st, const int *prio)
@@ -583,25 +575,12 @@ void launch_like_ddm_t(const Level &L, const DevModel &M, const TrialData &T, co
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_like_ddm<BLOCK, MINB>, L, M, T, d_iter, sweep, step, half, ll_part));
 }
 
-constexpr int kDdmDefaultVariant = 1; // 128 threads x 6 blocks/SM (80 registers): +20 % over 4 blocks, 8 blocks (64 registers) spill too much
+// launch shape of the DDM kernel: 128 threads x 6 blocks per SM (80 registers), picked by measurement among eight shapes in round 1
+// (profiles/r01_k_like_ddm.md: +20 % over 4 blocks; 8 blocks = 64 registers spill too much)
 void launch_like_ddm(const Level &L, const DevModel &M, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
                      double *ll_part, cudaStream_t st, const int *prio)
 {
-    static const int v = [] {
-        const char *e = std::getenv("GGDMC_B200_DDM_VARIANT");
-        const int x = e ? std::atoi(e) : kDdmDefaultVariant;
-        return (x < 0 || x > 7) ? kDdmDefaultVariant : x;
-    }();
-    switch (v) {
-    case 5: launch_like_ddm_t<128, 5>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 6: launch_like_ddm_t<256, 3>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 7: launch_like_ddm_t<96, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 1: launch_like_ddm_t<128, 6>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 2: launch_like_ddm_t<128, 8>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 3: launch_like_ddm_t<64, 12>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    case 4: launch_like_ddm_t<64, 16>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio); break;
-    default: launch_like_ddm_t<128, 4>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio);
-    }
+    launch_like_ddm_t<128, 6>(L, M, T, d_iter, sweep, step, half, ll_part, st, prio);
 }
 
 void launch_like(const Level &L, const ModelDev &MD, const TrialData &T, const uint32_t *d_iter, int sweep, int step, int half,
@@ -620,15 +599,23 @@ void launch_like(const Level &L, const ModelDev &MD, const TrialData &T, const u
     }
 }
 
+// the parity probe runs the trial loop the sampler would run for this model: expanded or indexed table (like_expand)
+template <int NACC, bool EXPAND>
+void launch_trial_logdens_hot_t(const DevModel &M, const TrialData &T, const double *theta, int n_theta, int ntr, uint64_t seed, uint32_t pop,
+                                uint32_t iter, double *out, double *sums)
+{
+    const size_t sm = like_launch_smem(M, 64, EXPAND);
+    require(sm <= 220 * 1024, "cell table does not fit in shared memory");
+    allow_smem(k_trial_logdens_hot<NACC, 64, EXPAND>, sm);
+    k_trial_logdens_hot<NACC, 64, EXPAND><<<dim3(n_theta, T.nsplit), 64, sm>>>(M, T, theta, ntr, seed, pop, iter, out, sums);
+    CUDA_CHECK(cudaGetLastError());
+}
 template <int NACC>
 void launch_trial_logdens_hot(const DevModel &M, const TrialData &T, const double *theta, int n_theta, int ntr, uint64_t seed, uint32_t pop,
                               uint32_t iter, double *out, double *sums)
 {
-    const size_t sm = like_smem(M, 64);
-    require(sm <= 220 * 1024, "cell table does not fit in shared memory");
-    allow_smem(k_trial_logdens_hot<NACC, 64>, sm);
-    k_trial_logdens_hot<NACC, 64><<<dim3(n_theta, T.nsplit), 64, sm>>>(M, T, theta, ntr, seed, pop, iter, out, sums);
-    CUDA_CHECK(cudaGetLastError());
+    if (like_expand(M)) launch_trial_logdens_hot_t<NACC, true>(M, T, theta, n_theta, ntr, seed, pop, iter, out, sums);
+    else launch_trial_logdens_hot_t<NACC, false>(M, T, theta, n_theta, ntr, seed, pop, iter, out, sums);
 }
 } // namespace
 

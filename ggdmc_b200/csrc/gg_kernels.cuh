@@ -611,7 +611,9 @@ __device__ __noinline__ void like_cold(const CellAcc *rows, const uint16_t *row_
 // it is reused.  stamp (diagnostics, may be null): thread 0 writes the time the table was finished to stamp[0].
 // TRACE (parity entry point ggdmc_b200_trial_logdens_hot only): every density the loops fold into the running product is
 // also written, as its log, to trace_out[trial] -- the production loops, the production trial functions.
-template <int NACC, int G, bool TRACE = false>
+// EXPAND: after the distinct rows are built they are copied out into one row per (cell, accumulator) right behind the
+// like_smem_bytes() region (n_cell n_acc more rows of shared memory), and the trial loop indexes that table by cell.
+template <int NACC, int G, bool TRACE = false, bool EXPAND = false>
 __device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &T, const double *th, const DrawAddr &addr, int s, int split,
                                             unsigned char *sm_raw, double *trace_out = nullptr, unsigned long long *stamp = nullptr)
 {
@@ -623,6 +625,15 @@ __device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &
     double *red = reinterpret_cast<double *>(rows + M.n_row);
     uint8_t *bad = reinterpret_cast<uint8_t *>(red + G / 32);
     build_rows<G>(M, th, rows, bad, bad + M.n_cell, addr);
+    const CellAcc *ent = nullptr;
+    if constexpr (EXPAND) {
+        CellAcc *e = reinterpret_cast<CellAcc *>(sm_raw + like_smem_bytes(M.n_row, M.n_cell, G));
+        const double *src = reinterpret_cast<const double *>(rows);
+        double *dst = reinterpret_cast<double *>(e);
+        for (int i = tid; i < M.n_cell * na * 8; i += G) dst[i] = src[(int)M.row_of[i >> 3] * 8 + (i & 7)];
+        Grp<G>::sync();
+        ent = e;
+    }
     if (stamp && tid == 0) stamp[0] = BlockTrace::now();
     if (t_begin >= ntr) return 0.0; // empty chunk (a subject with fewer trials than the longest one)
 
@@ -646,12 +657,18 @@ __device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &
             const double2 r2 = __ldg(reinterpret_cast<const double2 *>(rt + t));
             const ushort2 c2 = __ldg(reinterpret_cast<const ushort2 *>(cl + t));
             const int c0 = c2.x, c1 = (t + 1 < t_end) ? c2.y : c2.x; // the partner of a last odd trial is padding
-            const RowRef e0{rows, row_of + c0 * na}, e1{rows, row_of + c1 * na};
-            const bool pair_ok = (t + 1 < t_end) && bad[c0] == kCellRegular && bad[c1] == kCellRegular && n1pdf_fast_ok<NACC>(r2.x, e0, na) &&
-                                 n1pdf_fast_ok<NACC>(r2.y, e1, na);
+            bool pair_ok = (t + 1 < t_end) && bad[c0] == kCellRegular && bad[c1] == kCellRegular;
+            double p0 = 0.0, p1 = 0.0;
+            if constexpr (EXPAND) {
+                const CellAcc *e0 = ent + c0 * na, *e1 = ent + c1 * na;
+                pair_ok = pair_ok && n1pdf_fast_ok<NACC>(r2.x, e0, na) && n1pdf_fast_ok<NACC>(r2.y, e1, na);
+                if (pair_ok) n1pdf_fast2<NACC>(r2.x, e0, r2.y, e1, na, p0, p1);
+            } else {
+                const RowRef e0{rows, row_of + c0 * na}, e1{rows, row_of + c1 * na};
+                pair_ok = pair_ok && n1pdf_fast_ok<NACC>(r2.x, e0, na) && n1pdf_fast_ok<NACC>(r2.y, e1, na);
+                if (pair_ok) n1pdf_fast2<NACC>(r2.x, e0, r2.y, e1, na, p0, p1);
+            }
             if (pair_ok) {
-                double p0, p1;
-                n1pdf_fast2<NACC>(r2.x, e0, r2.y, e1, na, p0, p1);
                 if (zf > 0.0) {
                     if (p0 <= 0.0) p0 = zf;
                     if (p1 <= 0.0) p1 = zf;
@@ -675,9 +692,18 @@ __device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &
             for (int h = 0; h < nh; ++h) {
                 const int c = h ? c2.y : c2.x;
                 const double r = h ? r2.y : r2.x;
-                const RowRef e{rows, row_of + c * na};
-                if (bad[c] == kCellRegular && n1pdf_fast_ok<NACC>(r, e, na)) {
-                    double pdf = n1pdf_fast<NACC>(r, e, na);
+                bool ok = bad[c] == kCellRegular;
+                double pdf = 0.0;
+                if constexpr (EXPAND) {
+                    const CellAcc *e = ent + c * na;
+                    ok = ok && n1pdf_fast_ok<NACC>(r, e, na);
+                    if (ok) pdf = n1pdf_fast<NACC>(r, e, na);
+                } else {
+                    const RowRef e{rows, row_of + c * na};
+                    ok = ok && n1pdf_fast_ok<NACC>(r, e, na);
+                    if (ok) pdf = n1pdf_fast<NACC>(r, e, na);
+                }
+                if (ok) {
                     if (zf > 0.0 && pdf <= 0.0) pdf = zf;
                     acc.mul_fast(pdf);
                     if constexpr (TRACE) trace_out[t + h] = log(pdf);
@@ -694,14 +720,14 @@ __device__ __forceinline__ double like_eval(const DevModel &M, const TrialData &
 }
 
 // sum-log-likelihood of ONE proposal (population p, chain) over one trial chunk, by the whole block
-template <int NACC, int BLOCK>
+template <int NACC, int BLOCK, bool EXPAND>
 __device__ __forceinline__ void like_one(const Level &L, const DevModel &M, const TrialData &T, uint32_t iter, int sweep, int p,
                                          int chain, int split, double *ll_part, unsigned char *sm_raw)
 {
     const int C = L.nchain, D = L.npar;
     unsigned long long *bslot = (T.btrace && threadIdx.x == 0) ? T.btrace + 5 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
-    const double v = like_eval<NACC, BLOCK>(M, T, L.prop + ((size_t)p * C + chain) * D, make_addr(L, p, iter, sweep, chain), p / L.n_rep, split,
-                                            sm_raw, nullptr, bslot ? bslot + 3 : nullptr);
+    const double v = like_eval<NACC, BLOCK, false, EXPAND>(M, T, L.prop + ((size_t)p * C + chain) * D, make_addr(L, p, iter, sweep, chain), p / L.n_rep,
+                                                           split, sm_raw, nullptr, bslot ? bslot + 3 : nullptr);
     if (threadIdx.x == 0) ll_part[((size_t)p * C + chain) * T.nsplit + split] = v;
 }
 
@@ -759,7 +785,7 @@ __device__ __forceinline__ void like_one_ddm(const Level &L, const DevModel &M, 
 // step < 0, half < 0: block x = (population, chain).  step < 0, half = 0 / 1 (PARALLEL schedule): block x =
 // (population, slot) with (nchain + 1) / 2 slots; a crossover population evaluates chain 2 slot + half, a
 // migrating population (whole migration in half 0) its chains slot and slot + nslots.
-template <int NACC, int BLOCK, int MINB>
+template <int NACC, int BLOCK, int MINB, bool EXPAND>
 __global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, TrialData T, const uint32_t *d_iter, int sweep, int step,
                                                        int half, double *ll_part /* [npop][C][nsplit] */)
 {
@@ -791,8 +817,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_like(Level L, DevModel M, Trial
             nchain_blk = 2;
         }
     }
+    DevModel Ms = M;
+    if constexpr (!EXPAND) {
+        // the cell -> row map next to the table: the trial loop reads it once per accumulator per trial (first used after
+        // build_rows' first barrier)
+        uint16_t *s_row_of = reinterpret_cast<uint16_t *>(sm_raw + like_smem_bytes(M.n_row, M.n_cell, BLOCK));
+        for (int i = threadIdx.x; i < M.n_cell * M.n_acc; i += BLOCK) s_row_of[i] = M.row_of[i];
+        Ms.row_of = s_row_of;
+    }
     for (int i = 0, chain = chain0; i < nchain_blk && chain < C; ++i, chain += stride) {
-        if (L.target[p * C + chain] >= 0) like_one<NACC, BLOCK>(L, M, T, iter, sweep, p, chain, blockIdx.y, ll_part, sm_raw);
+        if (L.target[p * C + chain] >= 0) like_one<NACC, BLOCK, EXPAND>(L, Ms, T, iter, sweep, p, chain, blockIdx.y, ll_part, sm_raw);
         if (nchain_blk > 1) __syncthreads(); // shared table and reduction scratch are reused by the next chain
     }
 }
@@ -855,14 +889,14 @@ __global__ void __launch_bounds__(BLOCK) k_trial_logdens(DevModel M, const doubl
 
 // Per-trial log densities through the PRODUCTION trial loops (like_eval with TRACE): block (theta k, subject 0, chunk y).
 // sums[k * nsplit + y] also receives the chunk's sum as the sampler would see it.
-template <int NACC, int BLOCK>
+template <int NACC, int BLOCK, bool EXPAND>
 __global__ void __launch_bounds__(BLOCK) k_trial_logdens_hot(DevModel M, TrialData T, const double *theta, int ntr, uint64_t seed, uint32_t pop,
                                                              uint32_t iter, double *out, double *sums)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int k = blockIdx.x;
     DrawAddr addr = {seed, pop, iter, 0u, (uint32_t)k};
-    const double v = like_eval<NACC, BLOCK, true>(M, T, theta + (size_t)k * M.npar, addr, 0, blockIdx.y, sm_raw, out + (size_t)k * ntr);
+    const double v = like_eval<NACC, BLOCK, true, EXPAND>(M, T, theta + (size_t)k * M.npar, addr, 0, blockIdx.y, sm_raw, out + (size_t)k * ntr);
     if (threadIdx.x == 0) sums[(size_t)k * T.nsplit + blockIdx.y] = v;
 }
 
@@ -1371,11 +1405,12 @@ __device__ __forceinline__ void phi_accept_one(const Level &L, int r, int src, u
 
 // Every MH decision of a phi half-sweep by ONE WARP: lane = chain for the decision (phi_accept_one's rules), then the whole
 // warp copies every accepted phi vector and the prior constants that belong to it.
+// base0 / stride: the groups of 32 chains this warp takes (one warp: 0 / 32; warp w of a block of W warps: 32 w / 32 W)
 __device__ __forceinline__ void phi_accept_warp(const Level &L, int n_rc, uint32_t iter, int sweep, const double *hsum, int need_cur,
-                                                const double *prop_consts, double *consts, int lane)
+                                                const double *prop_consts, double *consts, int lane, int base0 = 0, int stride = 32)
 {
     const int C = L.nchain, D = L.npar;
-    for (int base = 0; base < n_rc; base += 32) {
+    for (int base = base0; base < n_rc; base += stride) {
         const int g = base + lane; // = r * C + src
         int tgt = -1, acc = 0;
         double tmp_lp = 0.0, tmp_ll = 0.0;
@@ -1513,12 +1548,9 @@ __device__ __forceinline__ bool phi_half_finish(const Level &L, const HyperArgs 
     }
     __threadfence();
     Grp<BLOCK>::sync();
-    if constexpr (BLOCK == 32) {
-        phi_accept_warp(L, L.npop * C, iter, sweep, hsum, H.need_cur, H.prop_consts, H.consts, tid);
-    } else {
-        for (int g = tid; g < L.npop * C; g += BLOCK)
-            phi_accept_one(L, g / C, g - (g / C) * C, iter, sweep, false, hsum, H.need_cur, H.prop_consts, H.consts);
-    }
+    // lane = chain for the decision, the whole warp for the copies of an accepted vector (phi_accept_warp)
+    if constexpr (BLOCK == 32) phi_accept_warp(L, L.npop * C, iter, sweep, hsum, H.need_cur, H.prop_consts, H.consts, tid);
+    else phi_accept_warp(L, L.npop * C, iter, sweep, hsum, H.need_cur, H.prop_consts, H.consts, tid & 31, 32 * (tid >> 5), BLOCK);
     return true;
 }
 
