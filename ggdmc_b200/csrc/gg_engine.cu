@@ -1022,8 +1022,14 @@ struct ggdmc_engine {
     {
         const Level &L = G.L;
         const size_t prop_sm = (size_t)kProposeWarps * D * 8;
-        TR("k_sweep_begin", stream, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), stream, L, d_iter.p, sweep, decide_once, para_idx));
-        ++launches;
+        // An unblocked hierarchical sweep draws its migration decision one iteration ahead: at the end of the previous
+        // iteration's sweep of this group (below), where it overlaps other groups' likelihood launches, instead of in front
+        // of this iteration's first proposal kernel.  Only the very first iteration draws its own.
+        const bool ahead = sweep_ahead();
+        if (!ahead || h_iter <= 1) {
+            TR("k_sweep_begin", stream, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), stream, L, d_iter.p, sweep, decide_once, para_idx, 0));
+            ++launches;
+        }
         if (schedule != GGDMC_SCHEDULE_REFERENCE) {
             const int n = L.npop * C;
             const int nhalf = schedule == GGDMC_SCHEDULE_PARALLEL ? 2 : 1;
@@ -1047,8 +1053,15 @@ struct ggdmc_engine {
                 launches += 3;
             }
         }
+        if (ahead) {
+            TR("k_sweep_begin", stream, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), stream, L, d_iter.p, sweep, decide_once, para_idx, 1));
+            ++launches;
+        }
         CUDA_CHECK(cudaGetLastError());
     }
+    // sweep decisions one iteration ahead: hierarchical fits without per-parameter sweeps (GGDMC_B200_NO_SWEEP_AHEAD=1: off)
+    bool sweep_ahead() const { return kind == 2 && !is_pblocked && !is_hblocked && sweep_ahead_ok; }
+    bool sweep_ahead_ok = std::getenv("GGDMC_B200_NO_SWEEP_AHEAD") == nullptr;
 
     // the subject-level sweep(s) of one iteration, group by group (ev_fork has been recorded on `stream`)
     void sweep_groups(int decide_once, cudaEvent_t join, bool conc)
@@ -1095,8 +1108,11 @@ struct ggdmc_engine {
         Level &P = phi.L;
         const size_t prop_sm = (size_t)kProposeWarps * D2 * 8;
         const int need_cur = H.need_cur;
-        TR("k_sweep_begin", st, k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), st>>>(P, d_iter.p, sweep, decide_once, para_idx));
-        ++launches;
+        const bool ahead = sweep_ahead();
+        if (!ahead || h_iter <= 1) {
+            TR("k_sweep_begin", st, k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), st>>>(P, d_iter.p, sweep, decide_once, para_idx, 0));
+            ++launches;
+        }
         const bool multi = kind == 2 && g_nccl.comm && g_nccl.n_rank > 1;
         const bool p2p = multi && g_p2p.ready && R * C * 2 <= kP2PMaxN;
         if (schedule != GGDMC_SCHEDULE_REFERENCE && fuse_phi && (!multi || p2p)) {
@@ -1127,6 +1143,10 @@ struct ggdmc_engine {
                 TR("k_phi_accept", st, k_phi_accept<<<(R + 127) / 128, 128, 0, st>>>(P, d_iter.p, sweep, step, hsum.p, need_cur, p2p_status()));
                 launches += 2;
             }
+        }
+        if (ahead) { // the next iteration's decision, behind this iteration's phi step instead of in front of the next one's
+            TR("k_sweep_begin", st, k_sweep_begin<<<R, 128, (size_t)2 * C * sizeof(int), st>>>(P, d_iter.p, sweep, decide_once, para_idx, 1));
+            ++launches;
         }
         CUDA_CHECK(cudaGetLastError());
     }

@@ -219,11 +219,12 @@ __device__ __forceinline__ void sweep_begin_pop(const Level &L, int p, uint32_t 
     }
 }
 
-__global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int decide_once, int para_idx)
+// iter_ofs = 1: the decisions of the NEXT iteration, drawn at the end of this one (off the next iteration's critical path)
+__global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int decide_once, int para_idx, int iter_ofs = 0)
 {
     extern __shared__ int sm_keys[]; // keys [C], ranks [C]
     __shared__ int s_mode_n[2];
-    sweep_begin_pop(L, blockIdx.x, *d_iter, sweep, decide_once, para_idx, sm_keys, s_mode_n);
+    sweep_begin_pop(L, blockIdx.x, *d_iter + (uint32_t)iter_ofs, sweep, decide_once, para_idx, sm_keys, s_mode_n);
 }
 
 // ------------------------------------------------------------------------------------------------
