@@ -243,10 +243,23 @@ def run_reference(args, rank, world):
 
 
 def git_head() -> str:
+    """Identity of the benched build: the commit where git is available, and always the hash of the kernel sources (the
+    GPU box gets a snapshot without .git)."""
+    import hashlib
+    h = hashlib.sha1()
+    src = os.path.join(ROOT, "ggdmc_b200", "csrc")
+    for f in sorted(os.listdir(src)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(src, f), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "ggdmc_b200.h"), "rb").read())
+    ident = "src-" + h.hexdigest()[:12]
     try:
-        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True, timeout=5).stdout.strip() or "unknown"
+        c = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True, timeout=5).stdout.strip()
+        if c:
+            ident = c + "/" + ident
     except Exception:
-        return "unknown"
+        pass
+    return ident
 
 
 def committed_traffic(workload: str, kernel: str, lik_per_launch: float):
@@ -256,7 +269,9 @@ def committed_traffic(workload: str, kernel: str, lik_per_launch: float):
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         e = tj[workload][kernel]
         if abs(e["trial_lik_per_launch"] - lik_per_launch) < 0.03 * lik_per_launch:
-            return e["dram_bytes_per_launch"], f"profiles/r02_traffic.json: ncu capture of commit {e.get('commit', '?')} ({e.get('command', '')}); this run is commit {git_head()}"
+            same = e.get("commit", "?").split("/")[-1] == git_head().split("/")[-1]
+            return e["dram_bytes_per_launch"], (f"profiles/r02_traffic.json: ncu capture of build {e.get('commit', '?')} ({e.get('command', '')}); this run is build "
+                                                f"{git_head()} ({'the same kernel sources' if same else 'DIFFERENT kernel sources: regenerate with tools/ncu_profiles.sh'})")
     except Exception:
         pass
     return None, "no committed ncu capture matches this workload / kernel / launch size"

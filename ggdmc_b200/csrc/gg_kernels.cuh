@@ -509,13 +509,16 @@ struct LogProd {
     int e;
     double extra; // log of factors that are 0, subnormal, inf or NaN (rare)
     __device__ __forceinline__ void init() { m = 1.0; e = 0; extra = 0.0; }
-    // x finite and >= 0 (fast-path densities): a zero factor makes the product 0
+    // x >= 0 (fast-path densities): a zero factor makes the product 0.  A factor that is not a positive normal number after
+    // all -- inf or NaN from an overflowing intermediate (dt or sd_v near 1e-290), a negative value -- must not be folded
+    // in as if its bits were a mantissa and an exponent: it goes through log() like in mul(), so the sum becomes inf / NaN
+    // and the MH test rejects it like the reference's NaN ratio (src/de.cpp:83-87).  One unsigned compare covers all.
     __device__ __forceinline__ void mul_fast(double x)
     {
         const long long b = __double_as_longlong(x);
         const int ex = (int)(b >> 52);
-        if (ex == 0) {
-            extra = -INFINITY;
+        if ((unsigned)(ex - 1) >= 0x7feu) {
+            extra += (b << 1) == 0 ? -INFINITY : log(x); // zero (either sign) : subnormal, inf, NaN, negative
         } else {
             m *= __longlong_as_double((b & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll);
             const long long mb = __double_as_longlong(m);

@@ -12,7 +12,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_path = os.path.join(ROOT, "profiles", "r02_traffic.json")
-commit = sys.argv[1]
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+commit = bench.git_head() if sys.argv[1] in ("x", "auto") else sys.argv[1]
 out = json.load(open(out_path)) if os.path.exists(out_path) else {}
 for spec in sys.argv[2:]:
     workload, kernel, lik, path = spec.split(",", 3)
