@@ -931,30 +931,6 @@ __global__ void __launch_bounds__(BLOCK) k_trial_logdens_ddm(DevModel M, const d
 // ------------------------------------------------------------------------------------------------
 // K3: Metropolis accept / commit at the subject level (update_theta, src/de.cpp:81-108)
 // ------------------------------------------------------------------------------------------------
-// MH test of the proposal made from chain src of population p, if one is pending (update_theta, src/de.cpp:81-108)
-__device__ __forceinline__ void accept_one(const Level &L, int p, int src, uint32_t iter, int sweep, const double *ll_part, int nsplit)
-{
-    const int C = L.nchain, D = L.npar;
-    const int tgt = ldm(L.target + p * C + src);
-    if (tgt < 0) return;
-    double tmp_ll = 0.0;
-    const double *part = ll_part + ((size_t)p * C + src) * nsplit;
-    for (int k = 0; k < nsplit; ++k) tmp_ll += ldm(part + k);
-    const double tmp_lp = L.prior_ovr ? deferred_prop_lp(L, p, src) : ldm(L.prop_lp + p * C + src);
-    const double cur = ldm(L.lp + p * C + tgt) + ldm(L.ll + p * C + tgt); // src/de.cpp:121 / :189-190 / :577 / :656-657
-    const double mh = exp((tmp_lp + tmp_ll) - cur);                       // :147
-    L.target[p * C + src] = -1;                                            // proposal consumed
-    if (isnan(mh)) return;                                                 // :83-87, no draw
-    DrawAddr a = make_addr(L, p, iter, sweep, src);
-    if (draw_uniform(a, U_ACCEPT, 0) < mh) {                               // :88
-        const double *pr = L.prop + ((size_t)p * C + src) * D;
-        double *th = L.theta + ((size_t)p * C + tgt) * D;
-        for (int d = 0; d < D; ++d) th[d] = ldm(pr + d);
-        L.lp[p * C + tgt] = tmp_lp;
-        L.ll[p * C + tgt] = tmp_ll;
-    }
-}
-
 // MH tests of the pending proposals made from chains [c_begin, c_end) of population p by ONE WARP: lane = chain for the
 // decision (update_theta, src/de.cpp:81-108), then the whole warp copies every accepted vector (a lane copying its own
 // vector alone pays one memory round trip per element: the loads may alias the stores).
@@ -1620,7 +1596,6 @@ __global__ void k_store_advance(Level A, Level Bv, int has_b, uint32_t *d_iter, 
     }
 }
 
-__global__ void k_iter_advance(uint32_t *d_iter) { *d_iter += 1; }
 // the sweep decisions of a level into the persistent kernel's per-population flag lines (words 2 and 3 of `stride` ints)
 __global__ void k_flags_init(Level L, unsigned int *flags, int stride)
 {

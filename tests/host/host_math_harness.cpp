@@ -106,6 +106,20 @@ void hm_norm_pair(const double *z, int n, double *cdf, double *pdf)
         pdf[i] = p.pdf;
     }
 }
+// the trial loop's batched twins (table-driven exponential): four arguments in lock step / two at a time
+void hm_norm_pairs_hot(const double *z, int n, double *cdf4, double *pdf4, double *cdf2, double *pdf2)
+{
+    for (int i = 0; i + 4 <= n; i += 4) {
+        double zz[4] = {z[i], z[i + 1], z[i + 2], z[i + 3]}, c[4], p[4];
+        gg::fm::norm_pairs_stepmajor<4>(zz, c, p);
+        for (int k = 0; k < 4; ++k) { cdf4[i + k] = c[k]; pdf4[i + k] = p[k]; }
+        for (int h = 0; h < 4; h += 2) {
+            double z2[2] = {zz[h], zz[h + 1]}, c2[2], p2[2];
+            gg::fm::norm_pairs_finite<2>(z2, c2, p2);
+            cdf2[i + h] = c2[0]; cdf2[i + h + 1] = c2[1]; pdf2[i + h] = p2[0]; pdf2[i + h + 1] = p2[1];
+        }
+    }
+}
 double hm_rcp_pos(double d) { return gg::fm::rcp_pos(d); }
 void hm_norm_cdf_lowlatency(const double *z, int n, double *cdf)
 {

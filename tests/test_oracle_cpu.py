@@ -317,6 +317,19 @@ def test_fast_norm_pair_accuracy(hostmath):
     H.hm_norm_pair(zs.ctypes.data_as(dp), len(zs), cdf.ctypes.data_as(dp), pdf.ctypes.data_as(dp))
     assert list(cdf[:6]) == [0.5, 1.0, 0.0, 1.0, 0.0, 1.0] and np.isnan(cdf[6]) and np.isnan(pdf[6])
     assert pdf[0] == 0.3989422804014327 and list(pdf[1:6]) == [0.0] * 5
+    # the batched twins the trial loop runs (table-driven exponential: 2^(j/32) table + degree-6 polynomial): same accuracy
+    # class over the whole finite range, four-wide and two-wide versions bit-identical to each other
+    z = np.concatenate([rng.uniform(-37.5, 9, 4000), rng.uniform(-6, 6, 3000), rng.uniform(-1, 1, 1000), np.array([0.0, -37.5, 37.5, -45.0, 8.3, 1e-300, -1e-300, 5e-324])])
+    z = z[: len(z) // 4 * 4]
+    c4, p4, c2, p2 = (np.zeros_like(z) for _ in range(4))
+    H.hm_norm_pairs_hot(z.ctypes.data_as(dp), len(z), c4.ctypes.data_as(dp), p4.ctypes.data_as(dp), c2.ctypes.data_as(dp), p2.ctypes.data_as(dp))
+    assert np.array_equal(c4, c2) and np.array_equal(p4, p2)
+    worst_c = worst_p = 0.0
+    for zi, c, p_ in zip(z, c4, p4):
+        zc = max(min(float(zi), 37.5), -37.5)  # the loop clamps |z| at 37.5 (both values are below 1e-305 there)
+        rc, rp = mp.ncdf(mp.mpf(zc)), mp.npdf(mp.mpf(zc))
+        worst_c, worst_p = max(worst_c, float(abs((mp.mpf(float(c)) - rc) / rc))), max(worst_p, float(abs((mp.mpf(float(p_)) - rp) / rp)))
+    assert worst_c < 8e-16 and worst_p < 6e-16, (worst_c, worst_p)
     # the Estrin-scheme twin used by the cell-table build: same accuracy class, same special values
     z = np.concatenate([rng.uniform(-37.5, 9, 2000), rng.uniform(-6, 6, 2000)])
     low = np.zeros_like(z)
