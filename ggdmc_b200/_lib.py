@@ -81,11 +81,16 @@ def build(force: bool = False) -> str:
     src_dir = os.path.join(HERE, "csrc")
     srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh"))]
     srcs.append(os.path.join(os.path.dirname(HERE), "include", "ggdmc_b200.h"))
-    stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
-    if stale:
-        r = subprocess.run(["make", "-C", src_dir], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("building libggdmc_b200.so failed:\n" + r.stdout + r.stderr)
+    def stale():
+        return not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale():
+        import fcntl
+        with open(os.path.join(src_dir, ".build.lock"), "w") as lock:  # the ranks of one launch must not build side by side
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if force or stale():
+                r = subprocess.run(["make", "-C", src_dir], capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise RuntimeError("building libggdmc_b200.so failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
 
 

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <mutex>
 #include <numeric>
 #include <stdexcept>
 #include <string>
@@ -499,6 +500,38 @@ struct PhaseTimer { // GGDMC_B200_TIMING=1 prints host wall time per phase of a 
         t = n;
     }
 };
+// Streams are kept for the life of the process: creating one is a call into the kernel-mode driver (a channel allocation),
+// which costs a millisecond on a quiet box and tens of milliseconds when anything else talks to the driver (a monitoring
+// tool polling clocks is enough) -- measured inside ggdmc_b200_run, whose engine lives for one call.
+struct StreamCache {
+    struct Item { int device, prio; cudaStream_t s; };
+    std::mutex mu;
+    std::vector<Item> idle;
+    cudaStream_t get(int device, int prio)
+    {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (size_t i = 0; i < idle.size(); ++i)
+                if (idle[i].device == device && idle[i].prio == prio) {
+                    cudaStream_t s = idle[i].s;
+                    idle.erase(idle.begin() + (long)i);
+                    return s;
+                }
+        }
+        cudaStream_t s = nullptr;
+        CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio));
+        return s;
+    }
+    void put(int device, int prio, cudaStream_t s)
+    {
+        if (!s) return;
+        cudaStreamSynchronize(s);
+        std::lock_guard<std::mutex> g(mu);
+        idle.push_back(Item{device, prio, s});
+    }
+};
+StreamCache g_streams;
+
 template <class K>
 void allow_smem(K kernel, size_t bytes)
 {
@@ -731,16 +764,16 @@ struct ggdmc_engine {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (cudaEvent_t e : slot_ev) if (e) cudaEventDestroy(e);
-        if (copy_stream) cudaStreamDestroy(copy_stream);
+        g_streams.put(device, prio_lo, copy_stream);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         for (int g = 1; g < kMaxGroups; ++g) {
             if (ev_gdone[g]) cudaEventDestroy(ev_gdone[g]);
             if (ev_prop[g - 1]) cudaEventDestroy(ev_prop[g - 1]);
-            if (gstream[g]) cudaStreamDestroy(gstream[g]);
+            g_streams.put(device, prio_lo, gstream[g]);
         }
-        if (side) cudaStreamDestroy(side);
-        if (stream) cudaStreamDestroy(stream);
+        g_streams.put(device, prio_hi, side);
+        g_streams.put(device, prio_lo, stream);
         pt.lap("  ~stream");
     }
 
@@ -753,18 +786,21 @@ struct ggdmc_engine {
         require(cfg->n_replicate >= 1 && cfg->seed != nullptr, "need n_replicate >= 1 seeds");
         require(cfg->schedule >= GGDMC_SCHEDULE_REFERENCE && cfg->schedule <= GGDMC_SCHEDULE_SIMULTANEOUS, "bad schedule");
         require(cfg->nparameter >= 1, "de_input nparameter must be >= 1");
+        PhaseTimer pt;
         device = pick_device(cfg->device);
+        pt.lap("   device");
         R = cfg->n_replicate; C = cfg->nchain; nmc = cfg->nmc; thin = cfg->thin;
         schedule = (cfg->schedule == GGDMC_SCHEDULE_PARALLEL && cfg->nchain < 4) ? GGDMC_SCHEDULE_REFERENCE : cfg->schedule;
         is_hblocked = cfg->is_hblocked; is_pblocked = cfg->is_pblocked;
         subject_begin = cfg->subject_begin;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CUDA_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_lo));
-        CUDA_CHECK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
+        stream = g_streams.get(device, prio_lo);
+        side = g_streams.get(device, prio_hi);
         CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreate(&ev0));
         CUDA_CHECK(cudaEventCreate(&ev1));
+        pt.lap("   streams");
         seeds.upload(cfg->seed, R);
         uint32_t z = 0;
         d_iter.upload(&z, 1); // 0 while the start state is stored in slot 0, then 1 = first iteration
@@ -772,6 +808,7 @@ struct ggdmc_engine {
         done_ctr.zero();
         phi_ticket.alloc(1);
         phi_ticket.zero();
+        pt.lap("   counters");
     }
 
     void init_level_state(LevelDev &lv, const ggdmc_start_t *starts, int n_items, int D_)
@@ -922,7 +959,7 @@ struct ggdmc_engine {
             sg.T.offset += i0; sg.T.count += i0;
             groups.push_back(sg);
             if (g > 0) {
-                CUDA_CHECK(cudaStreamCreateWithPriority(&gstream[g], cudaStreamNonBlocking, prio_lo));
+                gstream[g] = g_streams.get(device, prio_lo);
                 CUDA_CHECK(cudaEventCreateWithFlags(&ev_gdone[g], cudaEventDisableTiming));
                 CUDA_CHECK(cudaEventCreateWithFlags(&ev_prop[g - 1], cudaEventDisableTiming));
             }
@@ -1478,7 +1515,7 @@ struct ggdmc_engine {
             outs[i].npar = lv.L.npar; outs[i].nchain = C; outs[i].nmc = nmc;
         }
         sinks.push_back(OutSink{&lv, n_items, outs});
-        if (!copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        if (!copy_stream) copy_stream = g_streams.get(device, prio_lo);
     }
     // copy slots [slots_sent, upto): one strided copy per array when the per-item arrays are adjacent
     void send_slots(int upto)
