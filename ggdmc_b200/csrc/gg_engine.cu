@@ -728,7 +728,9 @@ struct ggdmc_engine {
     struct SubjGroup { Level L; TrialData T; double *ll_part; int index; };
     std::vector<SubjGroup> groups;
     cudaStream_t gstream[kMaxGroups] = {};
-    cudaEvent_t ev_gdone[kMaxGroups] = {}, ev_prop[kMaxGroups] = {};
+    cudaEvent_t ev_gdone[kMaxGroups] = {}, ev_prop[kMaxGroups] = {}, ev_swept[kMaxGroups] = {}, ev_sb = nullptr;
+    DBuf<uint32_t> sb_iter;     // [kMaxGroups] iteration counters of the groups' decision launches on the side stream
+    DBuf<unsigned int> sb_done; // [kMaxGroups]
     // optional per-launch timing of the likelihood kernel (bench.py roofline)
     // one DE-MCMC iteration captured as a CUDA graph (fixed launch sequence: every data-dependent
     // decision is taken on the device); GGDMC_B200_NO_GRAPH=1 falls back to plain stream launches
@@ -767,6 +769,8 @@ struct ggdmc_engine {
         g_streams.put(device, prio_lo, copy_stream);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_sb) cudaEventDestroy(ev_sb);
+        for (cudaEvent_t e : ev_swept) if (e) cudaEventDestroy(e);
         for (int g = 1; g < kMaxGroups; ++g) {
             if (ev_gdone[g]) cudaEventDestroy(ev_gdone[g]);
             if (ev_prop[g - 1]) cudaEventDestroy(ev_prop[g - 1]);
@@ -798,6 +802,7 @@ struct ggdmc_engine {
         side = g_streams.get(device, prio_hi);
         CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_sb, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreate(&ev0));
         CUDA_CHECK(cudaEventCreate(&ev1));
         pt.lap("   streams");
@@ -958,6 +963,7 @@ struct ggdmc_engine {
             L.mode += p0; L.mig_n += p0; L.para += p0; L.mode0 += p0;
             sg.T.offset += i0; sg.T.count += i0;
             groups.push_back(sg);
+            CUDA_CHECK(cudaEventCreateWithFlags(&ev_swept[g], cudaEventDisableTiming));
             if (g > 0) {
                 gstream[g] = g_streams.get(device, prio_lo);
                 CUDA_CHECK(cudaEventCreateWithFlags(&ev_gdone[g], cudaEventDisableTiming));
@@ -971,6 +977,10 @@ struct ggdmc_engine {
         CUDA_CHECK(cudaStreamSynchronize(stream)); // slot-0 stores (which read iteration 0) are done
         const uint32_t one = 1;
         CUDA_CHECK(cudaMemcpy(d_iter.p, &one, sizeof(one), cudaMemcpyHostToDevice));
+        const std::vector<uint32_t> ones(kMaxGroups, 1u);
+        sb_iter.upload(ones);
+        sb_done.alloc(kMaxGroups);
+        sb_done.zero();
         CUDA_CHECK(cudaStreamSynchronize(0));
     }
 
@@ -1055,7 +1065,7 @@ struct ggdmc_engine {
     // wait_first / rec_first: the groups' FIRST proposal kernels of an iteration run one after the other instead of side by
     // side, so that group 0's likelihood launch -- the first thing able to fill the GPU -- starts as early as possible
     void sweep_lba(const SubjGroup &G, cudaStream_t stream, int sweep, int decide_once, int para_idx, cudaEvent_t join = nullptr,
-                   cudaEvent_t wait_first = nullptr, cudaEvent_t rec_first = nullptr)
+                   cudaEvent_t wait_first = nullptr, cudaEvent_t rec_first = nullptr, bool sb_aside = false)
     {
         const Level &L = G.L;
         const size_t prop_sm = (size_t)kProposeWarps * D * 8;
@@ -1064,34 +1074,45 @@ struct ggdmc_engine {
         // of this iteration's first proposal kernel.  Only the very first iteration draws its own.
         const bool ahead = sweep_ahead();
         if (!ahead || h_iter <= 1) {
-            TR("k_sweep_begin", stream, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), stream, L, d_iter.p, sweep, decide_once, para_idx, 0));
+            TR("k_sweep_begin", stream, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), stream, L, d_iter.p, sweep, decide_once, para_idx, 0, (uint32_t *)nullptr, (unsigned int *)nullptr));
             ++launches;
         }
+        const int nslot_warps = L.npop * ((C + 1) / 2);
         if (schedule != GGDMC_SCHEDULE_REFERENCE) {
             const int n = L.npop * C;
             const int nhalf = schedule == GGDMC_SCHEDULE_PARALLEL ? 2 : 1;
             for (int h = 0; h < nhalf; ++h) {
                 const int half = nhalf == 2 ? h : -1;
-                const int nw = half < 0 ? n : L.npop * ((C + 1) / 2); // warps: one per (population, chain) or per (population, slot)
+                const int nw = half < 0 ? n : nslot_warps; // warps: one per (population, chain) or per (population, slot)
                 if (h == 0 && wait_first) CUDA_CHECK(cudaStreamWaitEvent(stream, wait_first, 0));
                 TR("k_propose", stream, launch_hi(k_propose<kProposeWarps>, (nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream, L, d_iter.p, sweep, -1, half));
                 if (h == 0 && rec_first) CUDA_CHECK(cudaEventRecord(rec_first, stream));
+                ++launches;
                 timed_like(G, stream, sweep, -1, half);
+                if (sb_aside && h + 1 == nhalf) {
+                    // The next iteration's decisions, drawn on the side stream beside this half's MH tests instead of behind them: the
+                    // likelihood launch was the last reader of this iteration's.  The launch counts iterations by itself (sb_iter),
+                    // because the end-of-iteration kernel may advance the engine's counter while it runs.
+                    CUDA_CHECK(cudaEventRecord(ev_swept[G.index], stream));
+                    CUDA_CHECK(cudaStreamWaitEvent(side, ev_swept[G.index], 0));
+                    TR("k_sweep_begin", side, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), side, L, d_iter.p, sweep, decide_once, para_idx, 1, sb_iter.p + G.index, sb_done.p + G.index));
+                    ++launches;
+                }
                 if (join && h == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0)); // the MH test needs this iteration's phi
-                TR("k_accept", stream, launch_hi(k_accept<kAcceptWarps>, (n + kAcceptWarps - 1) / kAcceptWarps, kAcceptWarps * 32, (size_t)kAcceptWarps * D * 8, stream, L, d_iter.p, sweep, -1, (const double *)G.ll_part, G.T.nsplit));
-                launches += 3;
+                TR("k_accept", stream, launch_hi(k_accept<kAcceptWarps>, (nw + kAcceptWarps - 1) / kAcceptWarps, kAcceptWarps * 32, (size_t)kAcceptWarps * D * 8, stream, L, d_iter.p, sweep, -1, (const double *)G.ll_part, G.T.nsplit, half));
+                launches += 2;
             }
         } else {
             for (int step = 0; step < C; ++step) {
                 TR("k_propose", stream, launch_hi(k_propose<kProposeWarps>, (L.npop + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream, L, d_iter.p, sweep, step, -1));
                 timed_like(G, stream, sweep, step, -1);
                 if (join && step == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0));
-                TR("k_accept", stream, launch_hi(k_accept<kAcceptWarps>, (L.npop + kAcceptWarps - 1) / kAcceptWarps, kAcceptWarps * 32, (size_t)kAcceptWarps * D * 8, stream, L, d_iter.p, sweep, step, (const double *)G.ll_part, G.T.nsplit));
+                TR("k_accept", stream, launch_hi(k_accept<kAcceptWarps>, (L.npop + kAcceptWarps - 1) / kAcceptWarps, kAcceptWarps * 32, (size_t)kAcceptWarps * D * 8, stream, L, d_iter.p, sweep, step, (const double *)G.ll_part, G.T.nsplit, -1));
                 launches += 3;
             }
         }
-        if (ahead) {
-            TR("k_sweep_begin", stream, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), stream, L, d_iter.p, sweep, decide_once, para_idx, 1));
+        if (ahead && !sb_aside) {
+            TR("k_sweep_begin", stream, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), stream, L, d_iter.p, sweep, decide_once, para_idx, 1, (uint32_t *)nullptr, (unsigned int *)nullptr));
             ++launches;
         }
         CUDA_CHECK(cudaGetLastError());
@@ -1110,13 +1131,22 @@ struct ggdmc_engine {
             for (int p = 0; p < nsweep; ++p) {
                 const bool first = p == 0 && conc && groups.size() > 1;
                 sweep_lba(groups[g], st, p, decide_once, is_pblocked ? p : -1, p == 0 ? join : nullptr,
-                          first && g > 0 ? ev_prop[g - 1] : nullptr, first && g + 1 < groups.size() ? ev_prop[g] : nullptr);
+                          first && g > 0 ? ev_prop[g - 1] : nullptr, first && g + 1 < groups.size() ? ev_prop[g] : nullptr, sb_aside(conc));
             }
             if (st != stream) {
                 CUDA_CHECK(cudaEventRecord(ev_gdone[g], st));
                 CUDA_CHECK(cudaStreamWaitEvent(stream, ev_gdone[g], 0));
             }
         }
+    }
+    // the groups' next-iteration decisions run on the side stream (sweep_lba): the PARALLEL schedule of an unblocked hierarchy
+    bool sb_aside(bool conc) const { return conc && sweep_ahead() && schedule == GGDMC_SCHEDULE_PARALLEL && sb_aside_ok; }
+    bool sb_aside_ok = std::getenv("GGDMC_B200_NO_SB_ASIDE") == nullptr;
+    void join_groups(bool conc)
+    {
+        if (!sb_aside(conc)) return;
+        CUDA_CHECK(cudaEventRecord(ev_sb, side));
+        CUDA_CHECK(cudaStreamWaitEvent(stream, ev_sb, 0));
     }
 
     void hyper_eval(int step, cudaStream_t st)
@@ -1464,6 +1494,7 @@ struct ggdmc_engine {
             }
             sweep_groups(0, join, conc);
             store_and_advance(subj, &phi);
+            join_groups(conc);
         } else if (kind == 0) {
             if (conc && groups.size() > 1) CUDA_CHECK(cudaEventRecord(ev_fork, stream));
             sweep_groups(1, nullptr, conc);

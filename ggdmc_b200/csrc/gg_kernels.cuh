@@ -158,7 +158,7 @@ __device__ __forceinline__ double block_sum(double v, double *scratch /* [BLOCK/
 // block-wide; sm_keys: 2 * nchain ints of shared memory.  The caller provides a barrier before sm_keys is reused.
 template <int G = 0>
 __device__ __forceinline__ void sweep_begin_pop(const Level &L, int p, uint32_t iter, int sweep, int decide_once, int para_idx, int *sm_keys,
-                                                int *s_mode_n /* 2 ints of shared memory */)
+                                                int *s_mode_n /* 2 ints of shared memory */, bool clear_targets = true)
 {
     const int C = L.nchain, tid = Grp<G>::tid(), nthr = Grp<G>::size();
     DrawAddr a = make_addr(L, p, iter, decide_once ? 0 : sweep, 0);
@@ -185,7 +185,10 @@ __device__ __forceinline__ void sweep_begin_pop(const Level &L, int p, uint32_t 
             L.mig_n[p] = 0;
         }
     }
-    for (int c = tid; c < C; c += nthr) L.target[p * C + c] = -1;
+    // no proposal is pending between sweeps (every MH test consumes its own); the launch that runs beside the last half's
+    // MH tests must not touch them
+    if (clear_targets)
+        for (int c = tid; c < C; c += nthr) L.target[p * C + c] = -1;
     Grp<G>::sync();
     if (s_mode_n[0] != 1) return;
     // arma::shuffle keys for all chains, then the n smallest keys (ties by position), sorted by index
@@ -220,11 +223,26 @@ __device__ __forceinline__ void sweep_begin_pop(const Level &L, int p, uint32_t 
 }
 
 // iter_ofs = 1: the decisions of the NEXT iteration, drawn at the end of this one (off the next iteration's critical path)
-__global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int decide_once, int para_idx, int iter_ofs = 0)
+// own / own_done (may be null): the launch counts iterations by itself instead of reading the engine's counter -- it then
+// may run while the end-of-iteration kernel advances that one.  Every block reads *own before it signals completion; the
+// last block to finish increments it.
+__global__ void k_sweep_begin(Level L, const uint32_t *d_iter, int sweep, int decide_once, int para_idx, int iter_ofs = 0,
+                              uint32_t *own = nullptr, unsigned int *own_done = nullptr)
 {
     extern __shared__ int sm_keys[]; // keys [C], ranks [C]
     __shared__ int s_mode_n[2];
-    sweep_begin_pop(L, blockIdx.x, *d_iter + (uint32_t)iter_ofs, sweep, decide_once, para_idx, sm_keys, s_mode_n);
+    const uint32_t base = own ? *own : *d_iter;
+    sweep_begin_pop(L, blockIdx.x, base + (uint32_t)iter_ofs, sweep, decide_once, para_idx, sm_keys, s_mode_n, own == nullptr);
+    if (own) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(own_done, 1u) == gridDim.x - 1) {
+                *own_done = 0;
+                *own = base + 1;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1033,14 +1051,26 @@ __device__ __forceinline__ void accept_self(const Level &L, int p, int src, uint
 
 // One WARP per pending proposal (lane = parameter for the log prior under phi and for the copy): the decision's loads are
 // one round trip wide instead of one per parameter.  Dynamic shared memory: (warps per block) x npar doubles.
+// half = 0 / 1 (PARALLEL schedule): one warp per (population, slot).  Half 1: chain 2 slot + 1 (only crossover populations
+// propose there).  Half 0: chains 2 slot and 2 slot + 1 -- a crossover population has nothing pending on the odd one, a
+// migrating population may have on both.  The kernel does not read the sweep decisions (L.mode ...): the next iteration's
+// may be drawn while it runs.
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *ll_part, int nsplit)
+__global__ void __launch_bounds__(WARPS * 32) k_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *ll_part, int nsplit,
+                                                        int half = -1)
 {
     extern __shared__ double sm_acc[];
     const int C = L.nchain, D = L.npar, lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int g = blockIdx.x * WARPS + wl;
-    int p, src;
-    if (step < 0) {
+    int p, src, src2 = -1;
+    if (step < 0 && half >= 0) {
+        const int nslot = (C + 1) / 2;
+        if (g >= L.npop * nslot) return;
+        p = g / nslot;
+        const int slot = g - p * nslot;
+        src = 2 * slot + half;
+        if (half == 0) src2 = 2 * slot + 1;
+    } else if (step < 0) {
         if (g >= L.npop * C) return;
         p = g / C;
         src = g - p * C;
@@ -1054,17 +1084,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_accept(Level L, const uint32_t *
         } else
             src = step;
     }
-    const int tgt = L.target[p * C + src];
-    if (tgt < 0) return;
-    const double *pr = L.prop + ((size_t)p * C + src) * D;
-    double *scratch = sm_acc + (size_t)wl * D;
-    double lp0 = 0.0, ll0 = 0.0;
-    if (lane == 0) {
-        L.target[p * C + src] = -1; // proposal consumed
-        if (!L.prior_ovr) lp0 = L.prop_lp[p * C + src];
-        if (nsplit == 1) ll0 = ll_part[(size_t)p * C + src];
+    for (; src >= 0; src = src2, src2 = -1) {
+        if (src >= C) continue;
+        const int tgt = L.target[p * C + src];
+        if (tgt < 0) continue;
+        const double *pr = L.prop + ((size_t)p * C + src) * D;
+        double *scratch = sm_acc + (size_t)wl * D;
+        double lp0 = 0.0, ll0 = 0.0;
+        __syncwarp();
+        if (lane == 0) {
+            L.target[p * C + src] = -1; // proposal consumed
+            if (!L.prior_ovr) lp0 = L.prop_lp[p * C + src];
+            if (nsplit == 1) ll0 = ll_part[(size_t)p * C + src];
+        }
+        accept_self(L, p, src, *d_iter, sweep, pr, lp0, ll_part, nsplit, ll0, scratch, lane, tgt);
+        __syncwarp();
     }
-    accept_self(L, p, src, *d_iter, sweep, pr, lp0, ll_part, nsplit, ll0, scratch, lane, tgt);
 }
 
 // ------------------------------------------------------------------------------------------------
