@@ -18,6 +18,7 @@
 #include <numeric>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -816,12 +817,12 @@ struct ggdmc_engine {
         pt.lap("   counters");
     }
 
-    void init_level_state(LevelDev &lv, const ggdmc_start_t *starts, int n_items, int D_)
+    void init_level_state(LevelDev &lv, const ggdmc_start_t *starts, int n_items, int D_, bool pool_synced = false)
     {
         // starts[i] holds [R][C][D_] for item i (subject or phi); device population p = i * R + r,
         // so item i's block is one contiguous copy
         const size_t CD = (size_t)C * D_, blk = (size_t)R * CD, blk1 = (size_t)R * C;
-        CUDA_CHECK(cudaStreamSynchronize(0)); // pool allocations (ordered on the default stream) are now usable on `stream`
+        if (!pool_synced) CUDA_CHECK(cudaStreamSynchronize(0)); // pool allocations (ordered on the default stream) are now usable on `stream`
         bool adjacent = true;
         for (int i = 0; i < n_items; ++i) {
             require(starts[i].theta && starts[i].lp && starts[i].ll, "null start state");
@@ -862,24 +863,42 @@ struct ggdmc_engine {
         require(pp && pp->npar == D, "p_prior length != model npar");
         p_prior.upload(pp);
         pt.lap("  model");
-        trials.upload(t, m->n_cell, false, m->type == GGDMC_MODEL_DDM);
-        pt.lap("  trials");
+        require(t && t->n_subject >= 1, "no subjects");
         S = t->n_subject;
+        // The two large uploads of a call -- the trials and the subjects' start state, both from pageable memory -- go side by
+        // side: a second host thread stages the trials (default stream) while this one sends the start state (engine stream).
+        subj.create(R * S, R, C, D, nmc, thin);
+        CUDA_CHECK(cudaStreamSynchronize(0)); // pool allocations are usable on `stream` from here on
+        pt.lap("  alloc");
+        std::exception_ptr trials_err;
+        std::thread trials_thread([&] {
+            try {
+                CUDA_CHECK(cudaSetDevice(device));
+                trials.upload(t, m->n_cell, false, m->type == GGDMC_MODEL_DDM);
+            } catch (...) {
+                trials_err = std::current_exception();
+            }
+        });
+        try {
+            init_level_state(subj, subj_start, S, D, true);
+        } catch (...) {
+            trials_thread.join();
+            throw;
+        }
+        trials_thread.join();
+        if (trials_err) std::rethrow_exception(trials_err);
+        pt.lap("  uploads");
         const bool want_persist = persist_planned = sampler_wanted(hp != nullptr) && m->type == GGDMC_MODEL_LBA && schedule == GGDMC_SCHEDULE_PARALLEL && !is_hblocked &&
                                   !is_pblocked && (!(hp && g_nccl.comm && g_nccl.n_rank > 1) || (g_p2p.ready && R * C * 2 <= kP2PMaxN)) &&
                                   sampler_fits(m->npar, hp != nullptr);
         if (want_persist) sampler_chunking((int64_t)R * S * ((C + 1) / 2));
         else trials.set_chunking((int64_t)R * S * C);
-        subj.create(R * S, R, C, D, nmc, thin);
-        pt.lap("  alloc");
         Level &L = subj.L;
         L.n_rep = R; L.pop_id_base = subject_begin; L.is_phi = 0;
         L.gamma = cfg->gamma_precursor / std::sqrt(2.0 * cfg->nparameter); // src/de.cpp:12,24
         L.rp = cfg->rp; L.mig_prob = cfg->sub_migration_prob;
         L.seed = seeds.p; L.prior = p_prior.d; L.prior_ovr = nullptr;
         L.nmove = std::min(D, kind == 2 ? cfg->nparameter / 2 : cfg->nparameter); // src/de.cpp:136 / :592
-        init_level_state(subj, subj_start, S, D);
-        pt.lap("  state");
         ll_part.alloc((size_t)R * S * C * trials.d.nsplit);
         ll_part.zero();
         if (kind == 2) {
