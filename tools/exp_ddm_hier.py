@@ -1,4 +1,4 @@
-"""Experiment (GPU; written after round 1's GPU budget was spent -- host side dry-run on CPU, not yet run on a B200):
+"""Experiment (GPU; output of round 2 in profiles/r02_ddm_hier.txt):
 the reference README's second example as a hierarchical DDM recovery study -- S subjects (default 32) x 256 trials,
 free a, sz, t0, v, z (start-point variability ON: the midpoint-rule path), truncated-normal population
 distribution -- through the resident engine: DE-MCMC iterations/s, trial-likelihoods/s, R-hat and recovered population
