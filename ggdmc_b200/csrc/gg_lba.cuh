@@ -20,7 +20,7 @@ struct CellAcc {
 };
 
 // The table holds every DISTINCT (cell, accumulator) row once (the model says which entries draw the same six
-// parameters, gg_engine.cu ModelDev); a trial reaches its cell's rows through the cell's row indices.
+// parameters, gg_host.cuh ModelDev); a trial reaches its cell's rows through the cell's row indices.
 struct RowRef {
     const CellAcc *rows;
     const uint16_t *idx; // [n_acc] row of accumulator j
