@@ -301,20 +301,29 @@ def test_execution_paths_agree_bit_for_bit(monkeypatch):
     groups, per-launch priorities on or off -- every combination must produce the same samples, bit for bit."""
     from ggdmc_b200 import workloads as W
     w = W.hierarchical("paths", 6, 7, 64, n_replicate=2)
-    tun = W.tuning_for(w, nmc=4, thin=3, seeds=[31, 32], pop_migration_prob=0.3, sub_migration_prob=0.3)
 
-    def fit():
+    def fit(tun):
         phi, subj = E.run_hier(w.spec.ct, w.trials, w.spec.p_prior, w.spec.h_prior, tun, w.phi_start, w.subj_start)
         return [phi.theta.copy(), phi.lp.copy(), phi.ll.copy()] + [a.copy() for s in subj for a in (s.theta, s.lp, s.ll)]
 
-    base = fit()
-    assert np.all(np.isfinite(base[0])) and not np.array_equal(base[0][:, 0], base[0][:, -1])
-    for env in ({"GGDMC_B200_NO_GRAPH": "1"}, {"GGDMC_B200_NO_OVERLAP": "1"}, {"GGDMC_B200_NO_FUSED_PHI": "1"},
-                {"GGDMC_B200_NO_HI_SMALL": "1"}, {"GGDMC_B200_GROUPS": "1"}, {"GGDMC_B200_GROUPS": "3"},
-                {"GGDMC_B200_NO_GRAPH": "1", "GGDMC_B200_NO_FUSED_PHI": "1", "GGDMC_B200_GROUPS": "1", "GGDMC_B200_NO_OVERLAP": "1"}):
-        with monkeypatch.context() as m:
-            for k, v in env.items():
-                m.setenv(k, v)
-            other = fit()
-        for a, b in zip(base, other):
-            assert np.array_equal(a, b), env
+    # a one-shot call of 9 iterations runs plain launches whatever the switch says; 51 iterations are long enough for the
+    # iteration graph to be captured (the sweep decisions drawn one iteration ahead, and on the side stream beside the
+    # last MH tests, are part of it)
+    short = W.tuning_for(w, nmc=4, thin=3, seeds=[31, 32], pop_migration_prob=0.3, sub_migration_prob=0.3)
+    long_ = W.tuning_for(w, nmc=18, thin=3, seeds=[31, 32], pop_migration_prob=0.3, sub_migration_prob=0.3)
+    envs_short = ({"GGDMC_B200_NO_GRAPH": "1"}, {"GGDMC_B200_NO_OVERLAP": "1"}, {"GGDMC_B200_NO_FUSED_PHI": "1"},
+                  {"GGDMC_B200_NO_HI_SMALL": "1"}, {"GGDMC_B200_GROUPS": "1"}, {"GGDMC_B200_GROUPS": "3"},
+                  {"GGDMC_B200_NO_SB_ASIDE": "1"}, {"GGDMC_B200_NO_SWEEP_AHEAD": "1"},
+                  {"GGDMC_B200_NO_GRAPH": "1", "GGDMC_B200_NO_FUSED_PHI": "1", "GGDMC_B200_GROUPS": "1", "GGDMC_B200_NO_OVERLAP": "1"})
+    envs_long = ({"GGDMC_B200_NO_GRAPH": "1"}, {"GGDMC_B200_NO_SB_ASIDE": "1"}, {"GGDMC_B200_NO_SWEEP_AHEAD": "1", "GGDMC_B200_GROUPS": "3"},
+                 {"GGDMC_B200_NO_OVERLAP": "1", "GGDMC_B200_GROUPS": "2"})
+    for tun, envs in ((short, envs_short), (long_, envs_long)):
+        base = fit(tun)
+        assert np.all(np.isfinite(base[0])) and not np.array_equal(base[0][:, 0], base[0][:, -1])
+        for env in envs:
+            with monkeypatch.context() as m:
+                for k, v in env.items():
+                    m.setenv(k, v)
+                other = fit(tun)
+            for a, b in zip(base, other):
+                assert np.array_equal(a, b), env
