@@ -196,7 +196,7 @@ struct ggdmc_engine {
                                   !is_pblocked && (!(hp && g_nccl.comm && g_nccl.n_rank > 1) || (g_p2p.ready && R * C * 2 <= kP2PMaxN)) &&
                                   sampler_fits(m->npar, hp != nullptr);
         if (want_persist) sampler_chunking((int64_t)R * S * ((C + 1) / 2));
-        else trials.set_chunking((int64_t)R * S * C);
+        else trials.set_chunking((int64_t)R * S * C, m->type == GGDMC_MODEL_LBA && schedule == GGDMC_SCHEDULE_PARALLEL ? (int64_t)R * S * ((C + 1) / 2) : 0);
         Level &L = subj.L;
         L.n_rep = R; L.pop_id_base = subject_begin; L.is_phi = 0;
         L.gamma = cfg->gamma_precursor / std::sqrt(2.0 * cfg->nparameter); // src/de.cpp:12,24

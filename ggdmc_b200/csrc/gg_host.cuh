@@ -414,11 +414,16 @@ struct TrialsDev {
         counter.alloc(1); counter.zero();
         d.rt = rt.p; d.cell = cell.p; d.offset = offset.p; d.count = count.p; d.counter = counter.p;
     }
-    void set_chunking(int64_t blocks_per_split_unit)
+    // half_sweep_blocks > 0 (the sampler's PARALLEL half-sweeps of an LBA fit): a likelihood launch of less than one wave of
+    // blocks ends with its slowest block, and blocks of one wave differ by a factor of two (the warp schedulers favour some
+    // slots); two half-size blocks per proposal end sooner although each builds its own table (32 subjects x 39 proposals:
+    // 39 -> 36 us per launch; three chunks 37, four 44)
+    void set_chunking(int64_t blocks_per_split_unit, int64_t half_sweep_blocks = 0)
     {
         // enough blocks to fill 148 SMs a few times over, at least 256 trials per block
         int want = (int)std::max<int64_t>(1, (4 * 148 + blocks_per_split_unit - 1) / blocks_per_split_unit);
         int max_split = std::max(1, (max_count + 255) / 256);
+        if (half_sweep_blocks > 0 && half_sweep_blocks < 148 * 12) want = std::max(want, 2);
         int nsplit = std::min(want, max_split);
         if (const char *e = std::getenv("GGDMC_B200_NSPLIT")) nsplit = std::max(1, std::min(std::atoi(e), std::max(1, max_count / 8))); // experiments
         if (max_count > 8192) nsplit = std::max(nsplit, (max_count + 4095) / 4096);
