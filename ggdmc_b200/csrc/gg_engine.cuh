@@ -408,7 +408,8 @@ struct ggdmc_engine {
                 const int half = nhalf == 2 ? h : -1;
                 const int nw = half < 0 ? n : nslot_warps; // warps: one per (population, chain) or per (population, slot)
                 if (h == 0 && wait_first) CUDA_CHECK(cudaStreamWaitEvent(stream, wait_first, 0));
-                TR("k_propose", stream, launch_hi(k_propose<kProposeWarps>, (nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream, L, d_iter.p, sweep, -1, half));
+                const bool waves = nw > short_wave_warps; // several waves of warps: the register-capped build of the short kernels
+                TR("k_propose", stream, launch_hi(waves ? k_propose<kProposeWarps, kShortKernelMinBlocks> : k_propose<kProposeWarps, 0>, (nw + kProposeWarps - 1) / kProposeWarps, kProposeWarps * 32, prop_sm, stream, L, d_iter.p, sweep, -1, half));
                 if (h == 0 && rec_first) CUDA_CHECK(cudaEventRecord(rec_first, stream));
                 ++launches;
                 timed_like(G, stream, sweep, -1, half);
@@ -422,7 +423,7 @@ struct ggdmc_engine {
                     ++launches;
                 }
                 if (join && h == 0) CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0)); // the MH test needs this iteration's phi
-                TR("k_accept", stream, launch_hi(k_accept<kAcceptWarps>, (nw + kAcceptWarps - 1) / kAcceptWarps, kAcceptWarps * 32, (size_t)kAcceptWarps * D * 8, stream, L, d_iter.p, sweep, -1, (const double *)G.ll_part, G.T.nsplit, half));
+                TR("k_accept", stream, launch_hi(waves ? k_accept<kAcceptWarps, kShortKernelMinBlocks> : k_accept<kAcceptWarps, 0>, (nw + kAcceptWarps - 1) / kAcceptWarps, kAcceptWarps * 32, (size_t)kAcceptWarps * D * 8, stream, L, d_iter.p, sweep, -1, (const double *)G.ll_part, G.T.nsplit, half));
                 launches += 2;
             }
         } else {
@@ -465,6 +466,8 @@ struct ggdmc_engine {
     // the groups' next-iteration decisions run on the side stream (sweep_lba): the PARALLEL schedule of an unblocked hierarchy
     bool sb_aside(bool conc) const { return conc && sweep_ahead() && schedule == GGDMC_SCHEDULE_PARALLEL && sb_aside_ok; }
     bool sb_aside_ok = std::getenv("GGDMC_B200_NO_SB_ASIDE") == nullptr;
+    // GGDMC_B200_SHORT_WAVE_WARPS=n: launch size (warps) from which k_propose / k_accept run their register-capped build (tests: 0)
+    int short_wave_warps = std::getenv("GGDMC_B200_SHORT_WAVE_WARPS") ? std::atoi(std::getenv("GGDMC_B200_SHORT_WAVE_WARPS")) : kShortKernelWaveWarps;
     void join_groups(bool conc)
     {
         if (!sb_aside(conc)) return;

@@ -529,6 +529,8 @@ void allow_smem(K kernel, size_t bytes)
 constexpr int kHyperBlock = 256;
 constexpr int kProposeWarps = 4;
 constexpr int kAcceptWarps = 4;
+// k_propose / k_accept launches of more warps than this run the build capped at 48 registers (10 blocks of 4 warps per SM)
+constexpr int kShortKernelMinBlocks = 10, kShortKernelWaveWarps = 148 * 24;
 
 // Launch shape of the likelihood kernel: 64 threads per block, 12 resident blocks per SM (80 registers) -- picked by
 // measurement on B200 among (128, 6), (128, 8), (64, 8 / 10 / 12 / 16), (32, 24 / 32), (256, 3) in round 1

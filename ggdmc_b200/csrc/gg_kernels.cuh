@@ -432,9 +432,11 @@ __device__ __forceinline__ void propose_position(const Level &L, int p, int k, i
     __syncwarp();
 }
 
-// One warp per (population, sweep position).
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_propose(Level L, const uint32_t *d_iter, int sweep, int step, int half)
+// One warp per (population, sweep position).  MINB: resident blocks per SM the register budget is cut for -- 10 (48 registers,
+// ~120 B of spills) when the launch is several waves of warps, so that more of its latency chains are in flight at once
+// (1 024 subjects: 26 -> 13 us); 0 (no cap) for small launches, where the spills would only add latency.
+template <int WARPS, int MINB = 0>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_propose(Level L, const uint32_t *d_iter, int sweep, int step, int half)
 {
     extern __shared__ double sm_prop[]; // [WARPS][npar] prior terms scratch
     const int C = L.nchain, D = L.npar;
@@ -1055,8 +1057,8 @@ __device__ __forceinline__ void accept_self(const Level &L, int p, int src, uint
 // propose there).  Half 0: chains 2 slot and 2 slot + 1 -- a crossover population has nothing pending on the odd one, a
 // migrating population may have on both.  The kernel does not read the sweep decisions (L.mode ...): the next iteration's
 // may be drawn while it runs.
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *ll_part, int nsplit,
+template <int WARPS, int MINB = 0>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_accept(Level L, const uint32_t *d_iter, int sweep, int step, const double *ll_part, int nsplit,
                                                         int half = -1)
 {
     extern __shared__ double sm_acc[];

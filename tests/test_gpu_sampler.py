@@ -298,7 +298,8 @@ def test_hierarchical_replicates_batch_equals_separate_runs():
 def test_execution_paths_agree_bit_for_bit(monkeypatch):
     """The engine's execution strategies are scheduling only: the captured iteration graph vs plain launches, the phi
     sweep on its side stream vs in line, the fused phi half-sweep launch vs its four separate kernels, 1 / 2 / 3 subject
-    groups, per-launch priorities on or off -- every combination must produce the same samples, bit for bit."""
+    groups, per-launch priorities on or off, the register-capped build of the short kernels -- every combination must
+    produce the same samples, bit for bit."""
     from ggdmc_b200 import workloads as W
     w = W.hierarchical("paths", 6, 7, 64, n_replicate=2)
 
@@ -313,9 +314,9 @@ def test_execution_paths_agree_bit_for_bit(monkeypatch):
     long_ = W.tuning_for(w, nmc=18, thin=3, seeds=[31, 32], pop_migration_prob=0.3, sub_migration_prob=0.3)
     envs_short = ({"GGDMC_B200_NO_GRAPH": "1"}, {"GGDMC_B200_NO_OVERLAP": "1"}, {"GGDMC_B200_NO_FUSED_PHI": "1"},
                   {"GGDMC_B200_NO_HI_SMALL": "1"}, {"GGDMC_B200_GROUPS": "1"}, {"GGDMC_B200_GROUPS": "3"},
-                  {"GGDMC_B200_NO_SB_ASIDE": "1"}, {"GGDMC_B200_NO_SWEEP_AHEAD": "1"},
+                  {"GGDMC_B200_NO_SB_ASIDE": "1"}, {"GGDMC_B200_NO_SWEEP_AHEAD": "1"}, {"GGDMC_B200_SHORT_WAVE_WARPS": "0"},
                   {"GGDMC_B200_NO_GRAPH": "1", "GGDMC_B200_NO_FUSED_PHI": "1", "GGDMC_B200_GROUPS": "1", "GGDMC_B200_NO_OVERLAP": "1"})
-    envs_long = ({"GGDMC_B200_NO_GRAPH": "1"}, {"GGDMC_B200_NO_SB_ASIDE": "1"}, {"GGDMC_B200_NO_SWEEP_AHEAD": "1", "GGDMC_B200_GROUPS": "3"},
+    envs_long = ({"GGDMC_B200_NO_GRAPH": "1"}, {"GGDMC_B200_NO_SB_ASIDE": "1"}, {"GGDMC_B200_SHORT_WAVE_WARPS": "0"}, {"GGDMC_B200_NO_SWEEP_AHEAD": "1", "GGDMC_B200_GROUPS": "3"},
                  {"GGDMC_B200_NO_OVERLAP": "1", "GGDMC_B200_GROUPS": "2"})
     for tun, envs in ((short, envs_short), (long_, envs_long)):
         base = fit(tun)
