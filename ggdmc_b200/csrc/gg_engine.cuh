@@ -436,7 +436,9 @@ struct ggdmc_engine {
             }
         }
         if (ahead && !sb_aside) {
-            TR("k_sweep_begin", stream, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), stream, L, d_iter.p, sweep, decide_once, para_idx, 1, (uint32_t *)nullptr, (unsigned int *)nullptr));
+            // the group's own iteration counter advances here too (it equals the engine's at this point), so that a fit may
+            // switch between this order and the side-stream one (per-launch profiling on / off) at any iteration
+            TR("k_sweep_begin", stream, launch_hi(k_sweep_begin, L.npop, 128, (size_t)2 * C * sizeof(int), stream, L, d_iter.p, sweep, decide_once, para_idx, 1, sb_iter.p + G.index, sb_done.p + G.index));
             ++launches;
         }
         CUDA_CHECK(cudaGetLastError());

@@ -295,6 +295,37 @@ def test_hierarchical_replicates_batch_equals_separate_runs():
     assert not np.array_equal(phi_b.theta[0], phi_b.theta[1])
 
 
+def test_profiling_can_be_switched_mid_fit():
+    """Per-launch profiling (bench.py's roofline pass) runs an iteration as plain launches on one stream, with the sweep
+    decisions drawn in line instead of on the side stream; a resident fit may switch it on and off at any iteration and
+    must end in the same state as an undisturbed one (the groups' own iteration counters stay in step in both orders)."""
+    from ggdmc_b200 import workloads as W
+    w = W.hierarchical("paths", 6, 7, 64, n_replicate=1)
+    tun = W.tuning_for(w, nmc=2, thin=1 << 30, seeds=[77], pop_migration_prob=0.3, sub_migration_prob=0.3)
+
+    def engine():
+        return E.Engine(w.spec.ct, w.trials, w.spec.p_prior, w.spec.h_prior, tun, w.phi_start, w.subj_start)
+
+    a = engine()
+    a.iterate(60)
+    ref = a.state()
+    a.close()
+    b = engine()
+    b.iterate(3)
+    b.profile(True)
+    b.iterate(2)
+    b.profile(False)
+    b.iterate(50)  # long enough for the iteration graph to be captured after the switch
+    b.profile(True)
+    b.iterate(1)
+    b.profile(False)
+    b.iterate(4)
+    got = b.state()
+    b.close()
+    for k in ("phi_theta", "phi_lp", "phi_ll", "theta", "lp", "ll"):
+        assert np.array_equal(ref[k], got[k]), k
+
+
 def test_execution_paths_agree_bit_for_bit(monkeypatch):
     """The engine's execution strategies are scheduling only: the captured iteration graph vs plain launches, the phi
     sweep on its side stream vs in line, the fused phi half-sweep launch vs its four separate kernels, 1 / 2 / 3 subject
