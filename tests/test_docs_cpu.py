@@ -24,3 +24,19 @@ def test_cited_files_exist(doc):
     text = open(os.path.join(ROOT, doc), encoding="utf-8").read()
     missing = sorted({p for p in cited_paths(text) if p not in BUILT and not os.path.exists(os.path.join(ROOT, p))})
     assert not missing, f"{doc} cites files that do not exist: {missing}"
+
+
+@pytest.mark.parametrize("doc", DOCS)
+def test_cited_tests_exist(doc):
+    """`tests/file.py::test_name` citations name functions that exist (a trailing ... or * in the name is a prefix)."""
+    text = open(os.path.join(ROOT, doc), encoding="utf-8").read()
+    missing = []
+    for m in re.finditer(r"`(tests/[\w/]+\.py)::([\w]+)([^`]*)`", text):
+        path, name, rest = m.groups()
+        full = os.path.join(ROOT, path)
+        if not os.path.exists(full):
+            continue  # reported by test_cited_files_exist
+        src = open(full, encoding="utf-8").read()
+        if not re.search(r"def " + re.escape(name) + (r"\w*\(" if rest else r"\("), src):
+            missing.append(f"{path}::{name}")
+    assert not missing, f"{doc} cites tests that do not exist: {sorted(set(missing))}"
